@@ -1,0 +1,81 @@
+"""ctypes binding of the C ABI in include/mapquik_b200.h (libmapquik_b200.so).
+
+The library is the product; this module only declares its entry points.  It raises if the
+shared object is missing or cannot be loaded -- there is no CPU fallback.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+from . import _build
+
+MQ_OK = 0
+
+
+class MqError(RuntimeError):
+    pass
+
+
+class Params(C.Structure):
+    _fields_ = [("k", C.c_uint32), ("l", C.c_uint32), ("density", C.c_double), ("use_hpc", C.c_uint32),
+                ("c", C.c_uint32), ("s", C.c_uint32), ("g", C.c_uint32)]
+
+
+HIT_DTYPE = np.dtype([("mapped", "u1"), ("rc", "u1"), ("mapq", "u1"), ("pad_", "u1"), ("ref_idx", "<u4"),
+                      ("q_start", "<u8"), ("q_end", "<u8"), ("r_start", "<u8"), ("r_end", "<u8"),
+                      ("score", "<u8")])
+assert HIT_DTYPE.itemsize == 48
+
+EXPORTS = ["mq_create", "mq_destroy", "mq_strerror", "mq_last_error", "mq_abi_version", "mq_host_alloc",
+           "mq_host_free", "mq_index_add", "mq_index_add_segment", "mq_store_info", "mq_store_export",
+           "mq_store_import", "mq_index_freeze", "mq_index_nb_mers", "mq_map_batch", "mq_map_batch_device",
+           "mq_format_paf", "mq_minimizers", "mq_kminmers", "mq_index_get", "mq_matches", "mq_last_ms",
+           "mq_launch_count", "mq_stream", "mq_sync", "mq_table_bytes", "mq_table_slots"]
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    if not os.path.exists(path):
+        raise MqError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                      "(nvcc); there is no CPU fallback")
+    L = C.CDLL(path)
+    vp, u64p = C.c_void_p, C.POINTER(C.c_uint64)
+    L.mq_create.restype = C.c_int; L.mq_create.argtypes = [C.POINTER(vp), C.POINTER(Params), C.c_int]
+    L.mq_destroy.restype = None; L.mq_destroy.argtypes = [vp]
+    L.mq_strerror.restype = C.c_char_p; L.mq_strerror.argtypes = [C.c_int]
+    L.mq_last_error.restype = C.c_char_p; L.mq_last_error.argtypes = [vp]
+    L.mq_abi_version.restype = C.c_int
+    L.mq_host_alloc.restype = vp; L.mq_host_alloc.argtypes = [C.c_size_t]
+    L.mq_host_free.restype = None; L.mq_host_free.argtypes = [vp]
+    L.mq_index_add.restype = C.c_int; L.mq_index_add.argtypes = [vp, vp, vp, C.c_uint32, C.c_uint32, vp]
+    L.mq_index_add_segment.restype = C.c_int
+    L.mq_index_add_segment.argtypes = [vp, vp, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64]
+    L.mq_store_info.restype = C.c_int; L.mq_store_info.argtypes = [vp, u64p, C.POINTER(C.c_uint32)]
+    L.mq_store_export.restype = C.c_int; L.mq_store_export.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), vp]
+    L.mq_store_import.restype = C.c_int; L.mq_store_import.argtypes = [vp, vp, vp, C.c_uint64, vp, C.c_uint32]
+    L.mq_index_freeze.restype = C.c_int; L.mq_index_freeze.argtypes = [vp, vp, C.c_uint32, u64p, u64p]
+    L.mq_index_nb_mers.restype = C.c_int; L.mq_index_nb_mers.argtypes = [vp, vp, C.c_uint32]
+    L.mq_map_batch.restype = C.c_int; L.mq_map_batch.argtypes = [vp, vp, vp, C.c_uint32, vp]
+    L.mq_map_batch_device.restype = C.c_int
+    L.mq_map_batch_device.argtypes = [vp, vp, vp, C.c_uint32, C.c_uint64, vp]
+    L.mq_format_paf.restype = C.c_int
+    L.mq_format_paf.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64, vp]
+    L.mq_minimizers.restype = C.c_int
+    L.mq_minimizers.argtypes = [vp, vp, vp, C.c_uint32, vp, vp, vp, C.c_uint64, u64p]
+    L.mq_kminmers.restype = C.c_int
+    L.mq_kminmers.argtypes = [vp, vp, vp, C.c_uint32, vp, vp, vp, vp, vp, C.c_uint64, u64p]
+    L.mq_index_get.restype = C.c_int; L.mq_index_get.argtypes = [vp, vp, C.c_uint64, vp, vp, vp, vp, vp, vp]
+    L.mq_matches.restype = C.c_int; L.mq_matches.argtypes = [vp, vp, vp, C.c_uint32, vp, vp, C.c_uint64, u64p]
+    L.mq_last_ms.restype = C.c_double; L.mq_last_ms.argtypes = [vp, C.c_char_p]
+    L.mq_launch_count.restype = C.c_uint64; L.mq_launch_count.argtypes = [vp]
+    L.mq_stream.restype = vp; L.mq_stream.argtypes = [vp]
+    L.mq_sync.restype = C.c_int; L.mq_sync.argtypes = [vp]
+    L.mq_table_bytes.restype = C.c_uint64; L.mq_table_bytes.argtypes = [vp]
+    L.mq_table_slots.restype = C.c_uint64; L.mq_table_slots.argtypes = [vp]
+    _lib = L
+    return L

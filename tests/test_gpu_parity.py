@@ -1,0 +1,257 @@
+"""GPU parity: every stage of the CUDA path, through the C ABI, bit-exact against the CPU oracle."""
+import numpy as np
+import pytest
+
+from conftest import random_dna, revcomp
+from oracle import pyoracle as O
+from mapquik_b200 import Index, Params, concat, sim
+
+pytestmark = pytest.mark.gpu
+
+
+def oparams(p):
+    return O.params(p.k, p.l, p.density, p.use_hpc, p.c, p.s, p.g)
+
+
+def oracle_minimizers(seqs, offs, p):
+    pos, hs, so = [], [], [0]
+    for i in range(len(offs) - 1):
+        a, b = O.minimizers(seqs[int(offs[i]):int(offs[i + 1])], oparams(p))
+        pos.append(a); hs.append(b); so.append(so[-1] + len(a))
+    return np.array(so, np.uint64), np.concatenate(pos) if pos else np.zeros(0, np.uint64), \
+        np.concatenate(hs) if hs else np.zeros(0, np.uint64)
+
+
+def check_minimizers(seqs, offs, p):
+    ix = Index(p)
+    so, pos, hs = ix.minimizers(seqs, offs)
+    eso, epos, ehs = oracle_minimizers(seqs, offs, p)
+    assert np.array_equal(so, eso), (so[:10], eso[:10])
+    assert np.array_equal(pos.astype(np.uint64), epos)
+    assert np.array_equal(hs, ehs)
+    ix.close()
+    return len(pos)
+
+
+def adversarial_seqs(rng):
+    seqs = []
+    seqs.append(random_dna(rng, 50000))
+    seqs.append(np.frombuffer(b"A" * 5000, np.uint8))                       # one homopolymer: a single symbol
+    seqs.append(np.frombuffer(b"AC" * 4000, np.uint8))                      # dinucleotide repeat (period 2)
+    x = random_dna(rng, 30000).copy(); x[10000:10040] = ord("N"); x[20000] = ord("N"); seqs.append(x)
+    y = random_dna(rng, 40000).copy(); y[12000:32000] = ord("T"); seqs.append(y)   # 20 kb homopolymer inside
+    seqs.append(random_dna(rng, 34))                                        # shorter than l+k-1 (35)
+    seqs.append(random_dna(rng, 35))
+    seqs.append(random_dna(rng, 31))
+    seqs.append(np.zeros(0, np.uint8))                                      # empty record
+    seqs.append(random_dna(rng, 8191)); seqs.append(random_dna(rng, 8192)); seqs.append(random_dna(rng, 8193))
+    seqs.append(random_dna(rng, 16385)); seqs.append(random_dna(rng, 1)); seqs.append(random_dna(rng, 3))
+    z = np.repeat(random_dna(rng, 3000), rng.integers(1, 12, 3000)); seqs.append(z)    # many long runs
+    w = random_dna(rng, 9000).copy(); w[-2000:] = ord("G"); seqs.append(w)   # record ends in a long run
+    v = random_dna(rng, 9000).copy(); v[:3000] = ord("C"); seqs.append(v)    # record starts with a long run
+    seqs.append(np.frombuffer(b"acgtnACGT" * 500, np.uint8))                # lower case is NOT folded at the ABI
+    return seqs
+
+
+@pytest.mark.parametrize("l,density,hpc", [(31, 0.01, True), (16, 0.01, True), (31, 0.05, False), (5, 0.3, True),
+                                           (32, 0.02, True), (2, 0.5, True), (25, 1.0, True)])
+def test_minimizers_adversarial(l, density, hpc):
+    rng = np.random.default_rng(7)
+    buf, offs = concat_raw(adversarial_seqs(rng))
+    check_minimizers(buf, offs, Params(k=5, l=l, density=density, use_hpc=hpc))
+
+
+def concat_raw(seqs):
+    offs = np.zeros(len(seqs) + 1, np.uint64); offs[1:] = np.cumsum([len(s) for s in seqs])
+    return (np.concatenate(seqs) if seqs else np.zeros(0, np.uint8)), offs
+
+
+def test_minimizers_reads_and_genome():
+    g, go, _ = sim.genome(11, [1500000, 700001, 123457])
+    n = check_minimizers(g, go, Params())
+    assert n > 20000
+    rb, ro, _, _ = sim.reads(11, g, go, 500, 10000, 3000)
+    check_minimizers(rb, ro, Params())
+    check_minimizers(rb, ro, Params(l=16, k=8))
+
+
+def test_minimizers_dense_overflow_pool():
+    # density 1.0 selects every l-mer: every tile overflows its staged-event pool into the global pool
+    rng = np.random.default_rng(3)
+    buf, offs = concat_raw([random_dna(rng, 100000), random_dna(rng, 20000)])
+    check_minimizers(buf, offs, Params(l=7, density=1.0, use_hpc=False))
+
+
+def test_kminmers():
+    rng = np.random.default_rng(5)
+    g, go, _ = sim.genome(12, [300000, 50000])
+    seqs = [g[:300000], g[300000:], random_dna(rng, 200), random_dna(rng, 36), random_dna(rng, 20)]
+    buf, offs = concat_raw(seqs)
+    for p in (Params(), Params(k=8, l=16), Params(k=1, l=20, density=0.05), Params(k=3, l=31, use_hpc=False)):
+        ix = Index(p)
+        so, st, en, off, rev, hs = ix.kminmers(buf, offs)
+        exp = [O.kminmers(s, oparams(p)) for s in seqs]
+        eso = np.cumsum([0] + [len(e) for e in exp])
+        assert np.array_equal(so, eso.astype(np.uint64))
+        e = np.concatenate(exp)
+        assert np.array_equal(st, e["start"]) and np.array_equal(en, e["end"])
+        assert np.array_equal(off, e["offset"]) and np.array_equal(rev, e["rev"]) and np.array_equal(hs, e["hash"])
+        ix.close()
+
+
+def build_both(p, names, g, go):
+    ix = Index(p)
+    nb = ix.add_batch(names, g, go)
+    n_unique = ix.freeze()
+    oix = O.Index(oparams(p), 1 << 16)
+    onb = oix.add_batch(names, g, go)
+    assert np.array_equal(nb, onb)
+    assert n_unique == oix.count()
+    assert ix.n_keys == oix.slots()
+    return ix, oix
+
+
+def test_index_unique_or_tombstone():
+    # a genome with exact duplications: duplicated k-min-mers must be tombstones, the rest unique
+    rng = np.random.default_rng(9)
+    a = random_dna(rng, 200000)
+    b = np.concatenate([random_dna(rng, 50000), a[20000:90000], random_dna(rng, 30000), revcomp(a[100000:150000])])
+    buf, offs = concat_raw([a, b])
+    p = Params()
+    ix, oix = build_both(p, ["a", "b"], buf, offs)
+    assert ix.n_keys > ix.n_unique            # some tombstones exist
+    # probe every reference k-min-mer and a batch of absent keys
+    _, st, en, off, rev, hs = Index(p).kminmers(buf, offs)
+    keys = np.concatenate([hs, rng.integers(0, 2**63, 1000).astype(np.uint64), np.array([2**64 - 1, 0], np.uint64)])
+    f, rid, s, e, o, rc = ix.get(keys)
+    for i, h in enumerate(keys):
+        exp = oix.get(int(h))
+        assert bool(f[i]) == (exp is not None)
+        if exp is not None:
+            assert (int(rid[i]), int(s[i]), int(e[i]), int(o[i]), int(rc[i])) == exp
+    ix.close()
+
+
+def compare_matches(ix, oix, rb, ro):
+    mo, f = ix.matches(rb, ro)
+    for i in range(len(ro) - 1):
+        em = oix.chain_matches(rb[int(ro[i]):int(ro[i + 1])])
+        got = f[int(mo[i]):int(mo[i + 1])]
+        assert len(em) == len(got), (i, len(em), len(got))
+        if len(em):
+            exp = np.stack([em["q_start"], em["q_end"], em["r_start"], em["r_end"], em["count"],
+                            (em["ref_id"].astype(np.uint64) << 1) | em["rc"]], axis=1).astype(np.uint32)
+            assert np.array_equal(got, exp), (i, got[:5], exp[:5])
+
+
+def compare_hits(ix, oix, rb, ro, names=None):
+    hits = ix.map_batch(rb, ro)
+    ohits = oix.map_batch(rb, ro)
+    for f in ("mapped", "rc", "mapq", "ref_idx", "q_start", "q_end", "r_start", "r_end", "score"):
+        bad = np.nonzero(hits[f] != ohits[f])[0]
+        assert bad.size == 0, (f, bad[:10], hits[bad[:3]], ohits[bad[:3]])
+    if names is not None:
+        for i in range(min(len(names), 200)):
+            ln = int(ro[i + 1] - ro[i])
+            a = ix.paf_line(names[i], ln, hits[i])
+            b = oix.paf_line(names[i], ln, ohits[i]) if ohits[i]["mapped"] else None
+            assert a == b
+    return hits
+
+
+def test_matches_and_hits_ecoli_like():
+    p = Params()
+    g, go, names = sim.genome(21, [2000000, 1000000, 400000])
+    ix, oix = build_both(p, names, g, go)
+    rb, ro, rn, tr = sim.reads(21, g, go, 3000, 10000, 2500, contig_names=names)
+    compare_matches(ix, oix, rb, ro)
+    hits = compare_hits(ix, oix, rb, ro, rn)
+    assert hits["mapped"].mean() > 0.95
+    ok = (hits["ref_idx"] == tr["contig"]) & (hits["rc"] == tr["strand"]) & \
+        (np.minimum(hits["r_end"], tr["start"] + tr["len"]).astype(np.int64) -
+         np.maximum(hits["r_start"], tr["start"]).astype(np.int64) > 0.1 * tr["len"])
+    assert (ok | (hits["mapped"] == 0)).mean() > 0.99
+    ix.close()
+
+
+def test_hits_repetitive_many_refs():
+    # repeat-rich multi-contig genome: tombstones, short Matches, cross-reference ties, the fwd-Match
+    # `check` quirk (ref id / strand not compared) all get exercised
+    p = Params(k=3, l=15, density=0.03, c=2, s=3, g=500)
+    g, go, names = sim.genome(31, [300000] * 12, sat_frac=0.05, repeat_frac=0.9, n_families=6)
+    ix, oix = build_both(p, names, g, go)
+    assert ix.n_keys > 1.2 * ix.n_unique              # plenty of tombstones
+    rb, ro, rn, _ = sim.reads(31, g, go, 4000, 2500, 1000, min_len=300, error_rate=0.01, contig_names=names)
+    compare_matches(ix, oix, rb, ro)
+    hits = compare_hits(ix, oix, rb, ro, rn)
+    assert 0 < hits["mapped"].sum() < len(hits)      # both mapped and unmapped (ties / no hits) occur
+    ix.close()
+
+
+@pytest.mark.parametrize("k,l,d,hpc", [(8, 16, 0.01, True), (5, 31, 0.01, False), (7, 25, 0.02, True), (2, 31, 0.005, True)])
+def test_hits_param_sweep(k, l, d, hpc):
+    p = Params(k=k, l=l, density=d, use_hpc=hpc, g=100 if k == 8 else 2000)
+    g, go, names = sim.genome(41, [800000, 300000], segdup_frac=0.05)
+    ix, oix = build_both(p, names, g, go)
+    rb, ro, rn, _ = sim.reads(41, g, go, 1500, 9000, 3000, contig_names=names)
+    compare_matches(ix, oix, rb, ro)
+    compare_hits(ix, oix, rb, ro, rn)
+    ix.close()
+
+
+def test_edge_reads():
+    p = Params()
+    g, go, names = sim.genome(51, [500000])
+    ix, oix = build_both(p, names, g, go)
+    rng = np.random.default_rng(1)
+    seqs = [np.zeros(0, np.uint8), random_dna(rng, 10), random_dna(rng, 34), random_dna(rng, 5000),   # unrelated
+            g[1000:1035].copy(), g[0:3000].copy(), g[-3000:].copy(), revcomp(g[0:3000]), revcomp(g[-2500:]),
+            g[250000:250000 + 40000].copy(),                       # longer than several tiles
+            np.concatenate([g[1000:4000], g[400000:403000]]),        # chimeric: two Matches, gap filter
+            np.concatenate([g[1000:4000], revcomp(g[5000:8000])])]   # strand switch
+    buf, offs = concat_raw(seqs)
+    compare_matches(ix, oix, buf, offs)
+    compare_hits(ix, oix, buf, offs, [f"r{i}" for i in range(len(seqs))])
+    # empty batch
+    assert len(ix.map_batch(np.zeros(0, np.uint8), np.zeros(1, np.uint64))) == 0
+    ix.close()
+
+
+def test_segment_partitioned_index_equals_whole():
+    # multi-GPU style build: the reference is cut into base-range segments (with halo) and the result
+    # must equal the single-shot index
+    p = Params()
+    g, go, names = sim.genome(61, [700000, 350000])
+    whole = Index(p); whole.add_batch(names, g, go); nu = whole.freeze()
+    part = Index(p)
+    rng = np.random.default_rng(2)
+    order = []
+    for r in range(2):
+        a, b = int(go[r]), int(go[r + 1]); L = b - a
+        cuts = [0] + sorted(rng.integers(1, L, 5).tolist()) + [L]
+        for s, e in zip(cuts[:-1], cuts[1:]):
+            order.append((r, L, s, e - s, a))
+    for j in rng.permutation(len(order)):       # out of order on purpose
+        r, L, s, own, a = order[j]
+        lo = a + s - (1 if s > 0 else 0); hi = min(a + L, a + s + own + 4000)
+        part.add_segment(r, names[r], L, s, own, g[lo:hi])
+    nu2 = part.freeze()
+    assert nu == nu2 and whole.n_keys == part.n_keys
+    assert np.array_equal(whole.nb_mers(), part.nb_mers())
+    rb, ro, _, _ = sim.reads(61, g, go, 800, 8000, 2000)
+    h1 = whole.map_batch(rb, ro); h2 = part.map_batch(rb, ro)
+    assert h1.tobytes() == h2.tobytes()
+    whole.close(); part.close()
+
+
+def test_errors_and_state():
+    from mapquik_b200 import MqError
+    with pytest.raises(MqError):
+        Index(Params(l=40))
+    ix = Index(Params())
+    with pytest.raises(MqError):
+        ix.map_batch(np.zeros(4, np.uint8), np.array([0, 4], np.uint64))     # not frozen
+    ix.freeze({})
+    with pytest.raises(MqError):
+        ix.add_batch(["x"], np.zeros(4, np.uint8), np.array([0, 4], np.uint64))
+    ix.close()
