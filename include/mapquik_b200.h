@@ -149,12 +149,23 @@ int mq_matches(mq_ctx *, const uint8_t *seqs, const uint64_t *offs, uint32_t n, 
                uint32_t *fields6, uint64_t cap, uint64_t *n_total);
 
 /* device time of the stages of the last mq_index_* / mq_map_* call, CUDA events on the ctx stream.
- * names: "h2d","scan","gather","kminmer","insert","probe","chain","d2h","total".  Returns ms or <0. */
+ * names: "h2d","scan","scan_kernel" (k_scan_minimizers alone, also inside "scan"),"gather","insert","probe","chain","d2h","total".  Returns ms or <0. */
 double mq_last_ms(mq_ctx *, const char *stage);
 /* number of kernels this library launched on this ctx since creation */
 uint64_t mq_launch_count(mq_ctx *);
 void *mq_stream(mq_ctx *);                /* cudaStream_t the kernels run on */
 int mq_sync(mq_ctx *);
+uint64_t mq_scan_kernel_launches(mq_ctx *);     /* launches of the dominant kernel (k_scan_minimizers) */
+uint64_t mq_minimizer_count(mq_ctx *, int reset); /* minimizers produced since the last reset */
+/* device-memory helpers: keep inputs resident in HBM for mq_map_batch_device */
+void *mq_dev_alloc(mq_ctx *, size_t bytes);
+void  mq_dev_free(mq_ctx *, void *);
+int   mq_dev_upload(mq_ctx *, void *dst, const void *src, size_t bytes);
+int   mq_dev_download(mq_ctx *, void *dst, const void *src, size_t bytes);
+int   mq_dev_memset(mq_ctx *, void *dst, int value, size_t bytes);
+/* CUDA-event bracket on the ctx stream around any sequence of calls; end returns elapsed ms */
+int    mq_region_begin(mq_ctx *);
+double mq_region_end_ms(mq_ctx *);
 uint64_t mq_table_bytes(mq_ctx *);
 uint64_t mq_table_slots(mq_ctx *);
 

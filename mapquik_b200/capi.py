@@ -30,7 +30,9 @@ EXPORTS = ["mq_create", "mq_destroy", "mq_strerror", "mq_last_error", "mq_abi_ve
            "mq_host_free", "mq_index_add", "mq_index_add_segment", "mq_store_info", "mq_store_export",
            "mq_store_import", "mq_index_freeze", "mq_index_nb_mers", "mq_map_batch", "mq_map_batch_device",
            "mq_format_paf", "mq_minimizers", "mq_kminmers", "mq_index_get", "mq_matches", "mq_last_ms",
-           "mq_launch_count", "mq_stream", "mq_sync", "mq_table_bytes", "mq_table_slots"]
+           "mq_launch_count", "mq_stream", "mq_sync", "mq_table_bytes", "mq_table_slots", "mq_scan_kernel_launches",
+           "mq_minimizer_count", "mq_dev_alloc", "mq_dev_free", "mq_dev_upload", "mq_dev_download", "mq_dev_memset",
+           "mq_region_begin", "mq_region_end_ms"]
 
 _lib = None
 
@@ -77,5 +79,14 @@ def lib():
     L.mq_sync.restype = C.c_int; L.mq_sync.argtypes = [vp]
     L.mq_table_bytes.restype = C.c_uint64; L.mq_table_bytes.argtypes = [vp]
     L.mq_table_slots.restype = C.c_uint64; L.mq_table_slots.argtypes = [vp]
+    L.mq_scan_kernel_launches.restype = C.c_uint64; L.mq_scan_kernel_launches.argtypes = [vp]
+    L.mq_minimizer_count.restype = C.c_uint64; L.mq_minimizer_count.argtypes = [vp, C.c_int]
+    L.mq_dev_alloc.restype = vp; L.mq_dev_alloc.argtypes = [vp, C.c_size_t]
+    L.mq_dev_free.restype = None; L.mq_dev_free.argtypes = [vp, vp]
+    L.mq_dev_upload.restype = C.c_int; L.mq_dev_upload.argtypes = [vp, vp, vp, C.c_size_t]
+    L.mq_dev_download.restype = C.c_int; L.mq_dev_download.argtypes = [vp, vp, vp, C.c_size_t]
+    L.mq_dev_memset.restype = C.c_int; L.mq_dev_memset.argtypes = [vp, vp, C.c_int, C.c_size_t]
+    L.mq_region_begin.restype = C.c_int; L.mq_region_begin.argtypes = [vp]
+    L.mq_region_end_ms.restype = C.c_double; L.mq_region_end_ms.argtypes = [vp]
     _lib = L
     return L

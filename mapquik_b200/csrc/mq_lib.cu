@@ -35,8 +35,10 @@ struct mq_ctx {
     uint64_t bound = 0;
     ScanTables tab{};
     std::string err;
-    uint64_t launches = 0;
+    uint64_t launches = 0, scan_kernel_launches = 0;
     int n_sm = 148;
+    cudaEvent_t region_a = nullptr, region_b = nullptr;
+    uint64_t last_minimizers = 0;
     // per-batch workspace
     DBuf d_seqs, d_offs, d_first_tile, d_tile_seq, d_ev_hash, d_ev_meta, d_lane_cnt, d_tile_cnt, d_blocksums,
          d_scalars, d_ovf_tile, d_ovf_meta, d_ovf_hash, d_pos, d_hash, d_seq_off, d_matches, d_nmatch, d_hits,
@@ -213,8 +215,12 @@ int run_scan(mq_ctx *c, const uint8_t *d_seqs, const uint64_t *d_offs, uint32_t 
             a.tile_ticket = tickets; a.emit_len = d_emit_len;
             const uint32_t ctas_needed = (n_tiles + SCAN_WARPS - 1) / SCAN_WARPS;
             const uint32_t grid = std::min<uint32_t>(ctas_needed, (uint32_t)c->n_sm * 6);
-            k_scan_minimizers<<<grid, SCAN_WARPS * 32, SCAN_WARPS * TILE_SMEM, c->stream>>>(a, c->tab);
+            {
+                StageTimer tk(c, "scan_kernel");   // the dominant kernel alone (roofline numerator)
+                k_scan_minimizers<<<grid, SCAN_WARPS * 32, SCAN_WARPS * TILE_SMEM, c->stream>>>(a, c->tab);
+            }
             c->launches += 2;
+            c->scan_kernel_launches++;
             CK(cudaGetLastError());
         }
         {
@@ -251,6 +257,7 @@ int run_scan(mq_ctx *c, const uint8_t *d_seqs, const uint64_t *d_offs, uint32_t 
         CK(cudaGetLastError());
     }
     *M_out = M;
+    c->last_minimizers += M;
     return MQ_OK;
 }
 
@@ -374,6 +381,7 @@ void mq_destroy(mq_ctx *c) {
                     &c->d_misc, &c->st_pos, &c->st_hash, &c->d_table, &c->d_ref_lens};
     for (DBuf *b : bufs) dfree(*b);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
+    if (c->region_a) { cudaEventDestroy(c->region_a); cudaEventDestroy(c->region_b); }
     if (c->h_pin) cudaFreeHost(c->h_pin);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -388,10 +396,60 @@ uint64_t mq_launch_count(mq_ctx *c) { return c ? c->launches : 0; }
 double mq_last_ms(mq_ctx *c, const char *stage) {
     if (!c || !stage) return -1.0;
     timers_collect(c);
-    if (!strcmp(stage, "total")) { double s = 0; for (auto &kv : c->ms) s += kv.second; return s; }
+    if (!strcmp(stage, "total")) { double s = 0; for (auto &kv : c->ms) if (kv.first != "scan_kernel") s += kv.second; return s; }
     auto it = c->ms.find(stage);
     return it == c->ms.end() ? 0.0 : it->second;
 }
+uint64_t mq_scan_kernel_launches(mq_ctx *c) { return c ? c->scan_kernel_launches : 0; }
+uint64_t mq_minimizer_count(mq_ctx *c, int reset) { if (!c) return 0; uint64_t v = c->last_minimizers; if (reset) c->last_minimizers = 0; return v; }
+
+// device-memory helpers so that callers can keep inputs resident in HBM without another runtime
+void *mq_dev_alloc(mq_ctx *c, size_t bytes) {
+    if (!c) return nullptr;
+    cudaSetDevice(c->device);
+    void *p = nullptr;
+    if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void mq_dev_free(mq_ctx *c, void *p) { if (c && p) { cudaSetDevice(c->device); cudaFree(p); } }
+int mq_dev_upload(mq_ctx *c, void *dst, const void *src, size_t bytes) {
+    if (!c || (bytes && (!dst || !src))) return MQ_ERR_ARG;
+    cudaSetDevice(c->device);
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return MQ_OK;
+}
+int mq_dev_download(mq_ctx *c, void *dst, const void *src, size_t bytes) {
+    if (!c || (bytes && (!dst || !src))) return MQ_ERR_ARG;
+    cudaSetDevice(c->device);
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return MQ_OK;
+}
+int mq_dev_memset(mq_ctx *c, void *dst, int value, size_t bytes) {
+    if (!c || (bytes && !dst)) return MQ_ERR_ARG;
+    cudaSetDevice(c->device);
+    CK(cudaMemsetAsync(dst, value, bytes, c->stream));
+    return MQ_OK;
+}
+// CUDA-event bracket on the ctx stream around any sequence of calls
+int mq_region_begin(mq_ctx *c) {
+    if (!c) return MQ_ERR_ARG;
+    cudaSetDevice(c->device);
+    if (!c->region_a) { CK(cudaEventCreate(&c->region_a)); CK(cudaEventCreate(&c->region_b)); }
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaEventRecord(c->region_a, c->stream));
+    return MQ_OK;
+}
+double mq_region_end_ms(mq_ctx *c) {
+    if (!c || !c->region_a) return -1.0;
+    cudaSetDevice(c->device);
+    if (cudaEventRecord(c->region_b, c->stream) != cudaSuccess) return -1.0;
+    if (cudaEventSynchronize(c->region_b) != cudaSuccess) return -1.0;
+    float ms = 0; cudaEventElapsedTime(&ms, c->region_a, c->region_b);
+    return ms;
+}
+
 uint64_t mq_table_bytes(mq_ctx *c) { return c && c->frozen ? (c->tmask + 2) * sizeof(Slot) : 0; }
 uint64_t mq_table_slots(mq_ctx *c) { return c && c->frozen ? c->tmask + 1 : 0; }
 
