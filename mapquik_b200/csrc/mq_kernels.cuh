@@ -332,7 +332,9 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) k_scan_minimizers(ScanArgs a,
         }
         anyN = __any_sync(0xffffffffu, anyN != 0);
         __syncwarp();
-        const uint32_t data_end = TWs + hcount;               // logical end: tile window then halo symbols
+        // logical end of the symbols a right-walk may visit: a full tile continues into its halo, a
+        // partial (record-final) tile ends with the record -- do not walk its blank tail
+        const uint32_t data_end = own_hi < TWs ? own_hi : TWs + hcount;
 
         // ---- warm-up: window of the l-1 symbols right of my chunk (append mode) ------------------
         LaneState st; st.F = 0; st.R = 0; st.W = 0; st.WN = 0;

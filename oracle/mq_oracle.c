@@ -321,10 +321,10 @@ static int match_check(const orc_match *m, const orc_kminmer *q, const slot_t *r
     return (A && B && (m->rc && d1)) || (!m->rc && d2);
 }
 
-static size_t chain_matches_alloc(const orc_index *ix, const uint8_t *seq, size_t n, const orc_params *p,
-                                  orc_match **outp) {
+/* core of chain_matches over an explicit k-min-mer list (also exported for unit tests that
+ * craft k-min-mers by hand) */
+static size_t chain_matches_kms(const orc_index *ix, const orc_kminmer *km, size_t q, orc_match **outp) {
     *outp = NULL;
-    orc_kminmer *km; size_t q = kminmers_alloc(seq, n, p, &km);
     if (!q) return 0;
     orc_match *out = (orc_match *)malloc(q * sizeof(orc_match)); size_t cap = q;
     size_t nm = 0, i = 0;
@@ -349,8 +349,21 @@ static size_t chain_matches_alloc(const orc_index *ix, const uint8_t *seq, size_
         if (nm < cap) out[nm] = m;
         nm++;
     }
-    free(km);
     *outp = out;
+    return nm;
+}
+static size_t chain_matches_alloc(const orc_index *ix, const uint8_t *seq, size_t n, const orc_params *p,
+                                  orc_match **outp) {
+    *outp = NULL;
+    orc_kminmer *km; size_t q = kminmers_alloc(seq, n, p, &km);
+    size_t nm = chain_matches_kms(ix, km, q, outp);
+    free(km);
+    return nm;
+}
+size_t orc_chain_matches_kms(const orc_index *ix, const orc_kminmer *km, size_t q, orc_match *out, size_t cap) {
+    orc_match *ms; size_t nm = chain_matches_kms(ix, km, q, &ms);
+    for (size_t i = 0; i < nm && out && i < cap; i++) out[i] = ms[i];
+    free(ms);
     return nm;
 }
 size_t orc_chain_matches(const orc_index *ix, const uint8_t *seq, size_t n, const orc_params *p,
@@ -435,21 +448,20 @@ static int cmp_match_ref(const void *a, const void *b) {  /* stable by (ref_id, 
     return 0;
 }
 
-int orc_find_matches(const orc_index *ix, const uint8_t *seq, size_t n, const uint64_t *ref_lens,
-                     uint32_t n_refs, const orc_params *p, orc_hit *out) {
+/* mers.rs:80-92 on an explicit Match list (query order); q_len = read length */
+static int best_of_matches(orc_match *ms, size_t nm, uint64_t q_len, const uint64_t *ref_lens, uint32_t n_refs,
+                           const orc_params *p, orc_hit *out) {
     memset(out, 0, sizeof(*out));
-    orc_match *ms; size_t nm = chain_matches_alloc(ix, seq, n, p, &ms);
-    if (!nm) { free(ms); return 0; }
-    /* group per reference id keeping query order inside each group (HashMap<usize,Vec<Match>>);
-     * merge-sort style stable grouping: insertion sort keeps it dependency-free and stable */
+    if (!nm) return 0;
+    /* group per reference id keeping query order inside each group (HashMap<usize,Vec<Match>>):
+     * stable insertion sort by ref id */
     for (size_t i = 1; i < nm; i++) {
         orc_match t = ms[i]; size_t j = i;
         while (j > 0 && cmp_match_ref(&ms[j - 1], &t) > 0) { ms[j] = ms[j - 1]; j--; }
         ms[j] = t;
     }
-    /* mers.rs:80-92 + determine_best_match/find_largest_two_chains (104-129):
-     * unique greatest score wins, tie for the maximum => unmapped.  The result does
-     * not depend on HashMap iteration order. */
+    /* determine_best_match / find_largest_two_chains (mers.rs:104-129): unique greatest score wins,
+     * tie for the maximum => unmapped.  Independent of HashMap iteration order. */
     orc_hit best; memset(&best, 0, sizeof(best));
     uint64_t max_c = 0, second_c = 0; size_t groups = 0;
     for (size_t i = 0; i < nm;) {
@@ -463,16 +475,37 @@ int orc_find_matches(const orc_index *ix, const uint8_t *seq, size_t n, const ui
         else if (t.score > second_c) second_c = t.score;
         i = j;
     }
-    free(ms);
     if (groups == 0) return 0;
     if (groups > 1 && max_c == second_c) return 0;
     if (best.ref_idx >= n_refs) return 0;   /* ref_map.get().unwrap() would panic; unreachable */
     uint64_t a, b, c, d;
-    orc_find_coords((uint64_t)n, ref_lens[best.ref_idx], best.rc, best.q_start, best.q_end,
+    orc_find_coords(q_len, ref_lens[best.ref_idx], best.rc, best.q_start, best.q_end,
                     best.r_start, best.r_end, &a, &b, &c, &d);
     best.q_start = a; best.q_end = b; best.r_start = c; best.r_end = d;
     *out = best;
     return 1;
+}
+int orc_find_matches(const orc_index *ix, const uint8_t *seq, size_t n, const uint64_t *ref_lens,
+                     uint32_t n_refs, const orc_params *p, orc_hit *out) {
+    orc_match *ms; size_t nm = chain_matches_alloc(ix, seq, n, p, &ms);
+    int r = best_of_matches(ms, nm, (uint64_t)n, ref_lens, n_refs, p, out);
+    free(ms);
+    return r;
+}
+int orc_find_matches_kms(const orc_index *ix, const orc_kminmer *km, size_t q, uint64_t q_len,
+                         const uint64_t *ref_lens, uint32_t n_refs, const orc_params *p, orc_hit *out) {
+    orc_match *ms; size_t nm = chain_matches_kms(ix, km, q, &ms);
+    int r = best_of_matches(ms, nm, q_len, ref_lens, n_refs, p, out);
+    free(ms);
+    return r;
+}
+int orc_best_of_matches(const orc_match *ms_in, size_t nm, uint64_t q_len, const uint64_t *ref_lens,
+                        uint32_t n_refs, const orc_params *p, orc_hit *out) {
+    orc_match *ms = (orc_match *)malloc((nm + 1) * sizeof(orc_match));
+    memcpy(ms, ms_in, nm * sizeof(orc_match));
+    int r = best_of_matches(ms, nm, q_len, ref_lens, n_refs, p, out);
+    free(ms);
+    return r;
 }
 
 void orc_index_add_batch(orc_index *ix, const uint8_t *seqs, const uint64_t *offs, uint32_t n,

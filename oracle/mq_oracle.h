@@ -111,6 +111,13 @@ int    orc_find_matches(const orc_index *, const uint8_t *seq, size_t n,
                         const uint64_t *ref_lens, uint32_t n_refs,
                         const orc_params *p, orc_hit *out);
 
+/* the same two steps on hand-crafted inputs (unit tests of the Match / Chain rules) */
+size_t orc_chain_matches_kms(const orc_index *, const orc_kminmer *km, size_t q, orc_match *out, size_t cap);
+int    orc_find_matches_kms(const orc_index *, const orc_kminmer *km, size_t q, uint64_t q_len,
+                            const uint64_t *ref_lens, uint32_t n_refs, const orc_params *p, orc_hit *out);
+int    orc_best_of_matches(const orc_match *ms, size_t nm, uint64_t q_len, const uint64_t *ref_lens,
+                           uint32_t n_refs, const orc_params *p, orc_hit *out);
+
 /* batch forms (OpenMP: one task per record like closures.rs:85,183) */
 void orc_index_add_batch(orc_index *, const uint8_t *seqs, const uint64_t *offs, uint32_t n,
                          uint32_t first_ref_idx, const orc_params *p, uint64_t *nb_mers_out,

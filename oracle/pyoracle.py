@@ -76,6 +76,12 @@ def lib():
         L.orc_index_get.argtypes = [C.c_void_p, C.c_uint64, u32p, u64p, u64p, u64p, u32p]
         L.orc_chain_matches.restype = C.c_size_t
         L.orc_chain_matches.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, PP, C.c_void_p, C.c_size_t]
+        L.orc_chain_matches_kms.restype = C.c_size_t
+        L.orc_chain_matches_kms.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+        L.orc_find_matches_kms.restype = C.c_int
+        L.orc_find_matches_kms.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64, C.c_void_p, C.c_uint32, PP, C.c_void_p]
+        L.orc_best_of_matches.restype = C.c_int
+        L.orc_best_of_matches.argtypes = [C.c_void_p, C.c_size_t, C.c_uint64, C.c_void_p, C.c_uint32, PP, C.c_void_p]
         L.orc_find_matches.restype = C.c_int
         L.orc_find_matches.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint32, PP, C.c_void_p]
         L.orc_index_add_batch.restype = None
@@ -181,6 +187,20 @@ class Index:
             L.orc_chain_matches(self.h, a.ctypes.data, a.size, C.byref(self.p), out.ctypes.data, n)
         return out
 
+    def chain_matches_kms(self, kms):
+        kms = np.ascontiguousarray(kms, dtype=KM_DTYPE); L = lib()
+        n = L.orc_chain_matches_kms(self.h, kms.ctypes.data, kms.size, None, 0)
+        out = np.zeros(n, MATCH_DTYPE)
+        if n:
+            L.orc_chain_matches_kms(self.h, kms.ctypes.data, kms.size, out.ctypes.data, n)
+        return out
+
+    def find_matches_kms(self, kms, q_len):
+        kms = np.ascontiguousarray(kms, dtype=KM_DTYPE); hit = np.zeros(1, HIT_DTYPE); lens = self._lens()
+        lib().orc_find_matches_kms(self.h, kms.ctypes.data, kms.size, q_len, lens.ctypes.data, lens.size,
+                                   C.byref(self.p), hit.ctypes.data)
+        return hit[0]
+
     def _lens(self):
         return np.asarray(self.ref_lens, dtype=np.uint64)
 
@@ -205,6 +225,13 @@ class Index:
                                  self.ref_lens[rid], h.ctypes.data)
         assert n > 0
         return buf.value.decode()
+
+
+def best_of_matches(matches, q_len, ref_lens, p):
+    ms = np.ascontiguousarray(matches, dtype=MATCH_DTYPE); lens = np.ascontiguousarray(ref_lens, dtype=np.uint64)
+    hit = np.zeros(1, HIT_DTYPE)
+    lib().orc_best_of_matches(ms.ctypes.data, ms.size, q_len, lens.ctypes.data, lens.size, C.byref(p), hit.ctypes.data)
+    return hit[0]
 
 
 def find_coords(q_len, r_len, rc, q_start, q_end, r_start, r_end):
