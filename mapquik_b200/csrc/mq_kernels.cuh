@@ -195,8 +195,19 @@ struct ScanArgs {
     uint32_t  ovf_cap;
     uint32_t *ovf_tile; uint32_t *ovf_meta; uint64_t *ovf_hash;
     uint32_t *tile_ticket;         // dynamic tile scheduler
-    const uint32_t *emit_len;      // per record (or NULL): only l-mers starting before this record offset are emitted
+    const uint32_t *emit_range;    // per record (or NULL): [lo, hi) record offsets; only l-mers STARTING inside are emitted
 };
+// emission window of a tile in x' coordinates (segment scans; the whole tile otherwise)
+__device__ __forceinline__ void emit_window(const ScanArgs &a, uint32_t sq, uint64_t gs, uint64_t tlo, uint32_t *xlo, uint32_t *xhi) {
+    *xlo = 0u; *xhi = 0x7FFFFFFFu;
+    if (a.emit_range) {
+        const int64_t sh = (int64_t)gs - (int64_t)tlo;
+        const int64_t lo = (int64_t)a.emit_range[2 * sq] + sh, hi = (int64_t)a.emit_range[2 * sq + 1] + sh;
+        *xlo = lo <= 0 ? 0u : (lo > 0x7FFFFFFF ? 0x7FFFFFFFu : (uint32_t)lo);
+        *xhi = hi <= 0 ? 0u : (hi > 0x7FFFFFFF ? 0x7FFFFFFFu : (uint32_t)hi);
+        if (*xhi < *xlo) *xhi = *xlo;
+    }
+}
 
 struct LaneState { uint64_t F, R, W; uint32_t WN; };
 
@@ -264,8 +275,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) k_scan_minimizers(ScanArgs a,
         const uint32_t own_lo = gs > tlo ? (uint32_t)(gs - tlo) : 0u;
         const uint32_t own_hi = (ge - tlo) < TWs ? (uint32_t)(ge - tlo) : TWs;      // exclusive
         const uint32_t magic = 0xFFFFFFFFu / Cs + 1u;          // x / Cs == umulhi(x, magic) for x < 2^16
-        uint32_t xlim = 0xFFFFFFFFu;                            // emission limit in x' (segment scans only)
-        if (a.emit_len) { int64_t v = (int64_t)a.emit_len[sq] + (int64_t)gs - (int64_t)tlo; xlim = v <= 0 ? 0u : (v > 0x7FFFFFFF ? 0x7FFFFFFFu : (uint32_t)v); }
+        uint32_t xlo, xlim; emit_window(a, sq, gs, tlo, &xlo, &xlim);   // segment scans only
 
         // ---- stage + digest the tile ------------------------------------------------------------
         const uint32_t *gw = (const uint32_t *)(a.seqs + tlo);
@@ -381,7 +391,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) k_scan_minimizers(ScanArgs a,
                     uint32_t fh = (uint32_t)(st.F >> 32), rh = (uint32_t)(st.R >> 32);
                     if (min(fh, rh) <= bound_hi) {
                         uint64_t h = st.F < st.R ? st.F : st.R;
-                        if (h < a.bound && (uint32_t)x < xlim) emit_event<true>((uint32_t)x, h, lane, nloc, tev, tile, a);
+                        if (h < a.bound && (uint32_t)x - xlo < xlim - xlo) emit_event<true>((uint32_t)x, h, lane, nloc, tev, tile, a);
                     }
                 }
             }
@@ -399,7 +409,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) k_scan_minimizers(ScanArgs a,
                     uint32_t fh = (uint32_t)(F >> 32), rh = (uint32_t)(R >> 32);
                     if (min(fh, rh) <= bound_hi) {
                         uint64_t h = F < R ? F : R;
-                        if (h < a.bound && (uint32_t)x < xlim) emit_event<false>((uint32_t)x, h, lane, nloc, tev, tile, a);
+                        if (h < a.bound && (uint32_t)x - xlo < xlim - xlo) emit_event<false>((uint32_t)x, h, lane, nloc, tev, tile, a);
                     }
                 }
             }
@@ -418,15 +428,18 @@ struct GatherArgs {
     const uint32_t *tile_seq; const uint32_t *first_tile; const uint64_t *offs;
     const uint32_t *pos_base;        // per record: position of its first byte inside its reference (or NULL)
     uint32_t n_tiles;
+    uint32_t grid_align;             // 4: k_scan_minimizers (v1) tiles, 16: k_scan_minimizers_v2 tiles
     uint32_t *out_pos; uint64_t *out_hash;
 };
 __device__ __forceinline__ void tile_origin(const GatherArgs &g, uint32_t tile, int64_t *x0_to_pos) {
     uint32_t sq = g.tile_seq[tile];
-    uint64_t gs = g.offs[sq], ge = g.offs[sq + 1], A = gs & ~3ull;
+    const uint64_t am = (uint64_t)g.grid_align - 1;
+    uint64_t gs = g.offs[sq], ge = g.offs[sq + 1], A = gs & ~am;
     uint32_t ft = g.first_tile[sq], nt = g.first_tile[sq + 1] - ft, ti = tile - ft;
     uint64_t span = ge - A;
     uint32_t Cs = (uint32_t)((span + 32ull * nt - 1) / (32ull * nt));
-    Cs = (Cs + 7u) & ~7u;
+    const uint32_t cm = g.grid_align == 16 ? 15u : 7u;
+    Cs = (Cs + cm) & ~cm;
     uint64_t tlo = A + (uint64_t)ti * 32u * Cs;
     *x0_to_pos = (int64_t)tlo - (int64_t)gs + (g.pos_base ? (int64_t)g.pos_base[sq] : 0);
 }

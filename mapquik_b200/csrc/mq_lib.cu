@@ -3,6 +3,8 @@
 // computing entry point fails with MQ_ERR_CUDA when no CUDA device is usable.
 #include "../../include/mapquik_b200.h"
 #include "mq_kernels.cuh"
+#include "mq_scan_v2.cuh"
+#include <cstdlib>
 
 #include <algorithm>
 #include <array>
@@ -34,6 +36,8 @@ struct mq_ctx {
     cudaStream_t stream = nullptr;
     uint64_t bound = 0;
     ScanTables tab{};
+    ScanTablesV2 tab2{};
+    bool scan_v1 = false;          // MQ_SCAN_V1=1 selects the first-generation scan kernel (A/B, debugging)
     std::string err;
     uint64_t launches = 0, scan_kernel_launches = 0;
     int n_sm = 148;
@@ -147,6 +151,19 @@ void fill_tables(ScanTables &T, uint32_t l) {
         T.pairR[i | (o << 2)] = T.inR[i] ^ T.outR[o];
     }
 }
+void fill_tables_v2(ScanTablesV2 &T, const ScanTables &S, uint32_t l) {
+    memcpy(T.pairF, S.pairF, sizeof(T.pairF)); memcpy(T.pairR, S.pairR, sizeof(T.pairR));
+    memcpy(T.inF, S.inF, sizeof(T.inF)); memcpy(T.outF, S.outF, sizeof(T.outF));
+    memcpy(T.inR, S.inR, sizeof(T.inR)); memcpy(T.outR, S.outR, sizeof(T.outR));
+    T.F0 = 0; T.R0 = 0;                       // window of l phantom 'A's
+    for (uint32_t i = 0; i < l; i++) { T.F0 ^= hrol(SEED_A, l - 1 - i); T.R0 ^= hrol(SEED_T, i); }
+    for (uint32_t p = 0; p < 16; p++) {       // byte-permute selectors: run-start bytes first, zero fill
+        uint32_t sel = 0, j = 0;
+        for (uint32_t b = 0; b < 4; b++) if (p & (1u << b)) sel |= b << (4 * j++);
+        for (; j < 4; j++) sel |= 4u << (4 * j);
+        T.sel[p] = sel;
+    }
+}
 
 // scalars block layout (u64 words): 0 scan total, 1 counts[2] .. ; u32 view used for tickets
 enum { SC_TOTAL = 0, SC_COUNT0 = 1, SC_COUNT1 = 2, SC_TICKET = 3 /* u32[2] : ticket, ovf */, SC_WORDS = 8 };
@@ -171,7 +188,7 @@ int excl_scan(mq_ctx *c, uint32_t *data, uint64_t n, bool write_total, uint64_t 
 
 // S1 on a device-resident batch.  Result: c->d_pos / c->d_hash (M entries), c->d_seq_off (n+1).
 int run_scan(mq_ctx *c, const uint8_t *d_seqs, const uint64_t *d_offs, uint32_t n, uint32_t min_len,
-             const uint32_t *d_pos_base, const uint32_t *d_emit_len, uint64_t *M_out) {
+             const uint32_t *d_pos_base, const uint32_t *d_emit_range, uint64_t *M_out) {
     int rc;
     *M_out = 0;
     if ((rc = ensure(c, c->d_first_tile, ((size_t)n + 2) * 4))) return rc;
@@ -179,7 +196,8 @@ int run_scan(mq_ctx *c, const uint8_t *d_seqs, const uint64_t *d_offs, uint32_t 
     uint64_t n_tiles64 = 0;
     {
         StageTimer t(c, "scan");
-        k_tiles_per_seq<<<(n + 255) / 256, 256, 0, c->stream>>>(d_offs, n, min_len, c->d_first_tile.as<uint32_t>());
+        if (c->scan_v1) k_tiles_per_seq<<<(n + 255) / 256, 256, 0, c->stream>>>(d_offs, n, min_len, c->d_first_tile.as<uint32_t>());
+        else k_tiles_per_seq_v2<<<(n + 255) / 256, 256, 0, c->stream>>>(d_offs, n, min_len, c->d_first_tile.as<uint32_t>());
         c->launches++;
         if ((rc = excl_scan(c, c->d_first_tile.as<uint32_t>(), n, true, &n_tiles64))) return rc;
     }
@@ -212,12 +230,19 @@ int run_scan(mq_ctx *c, const uint8_t *d_seqs, const uint64_t *d_offs, uint32_t 
             a.lane_cnt = c->d_lane_cnt.as<uint16_t>(); a.tile_cnt = c->d_tile_cnt.as<uint32_t>();
             a.ovf_count = tickets + 1; a.ovf_cap = c->ovf_cap;
             a.ovf_tile = c->d_ovf_tile.as<uint32_t>(); a.ovf_meta = c->d_ovf_meta.as<uint32_t>(); a.ovf_hash = c->d_ovf_hash.as<uint64_t>();
-            a.tile_ticket = tickets; a.emit_len = d_emit_len;
-            const uint32_t ctas_needed = (n_tiles + SCAN_WARPS - 1) / SCAN_WARPS;
-            const uint32_t grid = std::min<uint32_t>(ctas_needed, (uint32_t)c->n_sm * 6);
+            a.tile_ticket = tickets; a.emit_range = d_emit_range;
             {
                 StageTimer tk(c, "scan_kernel");   // the dominant kernel alone (roofline numerator)
-                k_scan_minimizers<<<grid, SCAN_WARPS * 32, SCAN_WARPS * TILE_SMEM, c->stream>>>(a, c->tab);
+                if (c->scan_v1) {
+                    const uint32_t ctas_needed = (n_tiles + SCAN_WARPS - 1) / SCAN_WARPS;
+                    const uint32_t grid = std::min<uint32_t>(ctas_needed, (uint32_t)c->n_sm * 6);
+                    k_scan_minimizers<<<grid, SCAN_WARPS * 32, SCAN_WARPS * TILE_SMEM, c->stream>>>(a, c->tab);
+                } else {
+                    const uint32_t ctas_needed = (n_tiles + V2_WARPS - 1) / V2_WARPS;
+                    const uint32_t grid = std::min<uint32_t>(ctas_needed, (uint32_t)c->n_sm * 4);
+                    const size_t smem = (size_t)V2_WARPS * ((V2_WARP_SMEM + 15) & ~15);
+                    k_scan_minimizers_v2<<<grid, V2_WARPS * 32, smem, c->stream>>>(a, c->tab2);
+                }
             }
             c->launches += 2;
             c->scan_kernel_launches++;
@@ -243,7 +268,7 @@ int run_scan(mq_ctx *c, const uint8_t *d_seqs, const uint64_t *d_offs, uint32_t 
         // tile_cnt was scanned in place: the per-tile totals are recovered as differences
         g.tile_base = c->d_tile_cnt.as<uint32_t>();
         g.tile_seq = c->d_tile_seq.as<uint32_t>(); g.first_tile = c->d_first_tile.as<uint32_t>(); g.offs = d_offs;
-        g.pos_base = d_pos_base; g.n_tiles = n_tiles; g.out_pos = c->d_pos.as<uint32_t>(); g.out_hash = c->d_hash.as<uint64_t>();
+        g.pos_base = d_pos_base; g.n_tiles = n_tiles; g.grid_align = c->scan_v1 ? 4u : 16u; g.out_pos = c->d_pos.as<uint32_t>(); g.out_hash = c->d_hash.as<uint64_t>();
         k_gather_minimizers<<<(n_tiles + 7) / 8, 256, 0, c->stream>>>(g);
         c->launches++;
         if (n_ovf) {
@@ -360,6 +385,8 @@ int mq_create(mq_ctx **out, const mq_params *p, int device) {
     mq_ctx *c = new mq_ctx();
     c->p = *p; c->device = device; c->bound = hash_bound(p->density);
     fill_tables(c->tab, p->l);
+    fill_tables_v2(c->tab2, c->tab, p->l);
+    { const char *e = getenv("MQ_SCAN_V1"); c->scan_v1 = e && e[0] == '1'; }
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->n_sm = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return MQ_ERR_CUDA; }
@@ -492,21 +519,21 @@ int mq_index_add_segment(mq_ctx *c, const uint8_t *bytes, uint64_t n_bytes, uint
     if ((rc = ensure(c, c->d_seqs, n_bytes + PAD))) return rc;
     if ((rc = ensure(c, c->d_offs, 2 * 8))) return rc;
     if ((rc = ensure(c, c->d_pos_base, 4))) return rc;
-    if ((rc = ensure(c, c->d_emit_len, 4))) return rc;
+    if ((rc = ensure(c, c->d_emit_len, 8))) return rc;
     if ((rc = ensure_pin(c, 64))) return rc;
     {
         StageTimer t(c, "h2d");
-        uint64_t *ho = (uint64_t *)c->h_pin; ho[0] = ctx; ho[1] = n_bytes;
-        uint32_t *hu = (uint32_t *)(ho + 2); hu[0] = (uint32_t)seg_start; hu[1] = (uint32_t)own_len;
+        // the record handed to the scan INCLUDES the context byte, so run starts are decided exactly as
+        // in a whole-record scan; only l-mers starting in [ctx, ctx+own_len) are emitted
+        uint64_t *ho = (uint64_t *)c->h_pin; ho[0] = 0; ho[1] = n_bytes;
+        uint32_t *hu = (uint32_t *)(ho + 2); hu[0] = (uint32_t)(seg_start - ctx); hu[1] = (uint32_t)ctx; hu[2] = (uint32_t)(ctx + own_len);
         CK(cudaMemcpyAsync(c->d_seqs.p, bytes, n_bytes, cudaMemcpyHostToDevice, c->stream));
         CK(cudaMemsetAsync((uint8_t *)c->d_seqs.p + n_bytes, 0, PAD, c->stream));
         CK(cudaMemcpyAsync(c->d_offs.p, ho, 16, cudaMemcpyHostToDevice, c->stream));
         CK(cudaMemcpyAsync(c->d_pos_base.p, hu, 4, cudaMemcpyHostToDevice, c->stream));
-        CK(cudaMemcpyAsync(c->d_emit_len.p, hu + 1, 4, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(c->d_emit_len.p, hu + 1, 8, cudaMemcpyHostToDevice, c->stream));
     }
     uint64_t M = 0;
-    // record = bytes[ctx, n_bytes); with ctx == 1 the first byte's run-start flag is decided against
-    // the context byte, exactly as if the whole record were scanned (flag bit 0 of emit/flags below)
     if ((rc = run_scan(c, c->d_seqs.as<uint8_t>(), c->d_offs.as<uint64_t>(), 1, 0, c->d_pos_base.as<uint32_t>(),
                        c->d_emit_len.as<uint32_t>(), &M))) return rc;
     if ((rc = store_append(c, M))) return rc;
@@ -655,7 +682,7 @@ int mq_index_nb_mers(mq_ctx *c, uint64_t *nb, uint32_t n_refs) {
 int mq_map_batch_device(mq_ctx *c, const uint8_t *d_seqs, const uint64_t *d_offs, uint32_t n, uint64_t total_bytes, mq_hit *d_out) {
     if (!c || !d_offs || !d_out || (!d_seqs && total_bytes)) return MQ_ERR_ARG;
     if (!c->frozen) { c->err = "index not frozen"; return MQ_ERR_STATE; }
-    if (((uintptr_t)d_seqs & 3) != 0) { c->err = "device sequence buffer must be 4-byte aligned"; return MQ_ERR_ARG; }
+    if (((uintptr_t)d_seqs & 15) != 0) { c->err = "device sequence buffer must be 16-byte aligned"; return MQ_ERR_ARG; }
     cudaSetDevice(c->device);
     timers_reset(c);
     if (n == 0) return MQ_OK;

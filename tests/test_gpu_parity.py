@@ -22,6 +22,13 @@ def oracle_minimizers(seqs, offs, p):
         np.concatenate(hs) if hs else np.zeros(0, np.uint64)
 
 
+@pytest.fixture(params=["v2", "v1"])
+def scan_version(request, monkeypatch):
+    """both generations of the S1 kernel stay under test (MQ_SCAN_V1 is read at mq_create)"""
+    monkeypatch.setenv("MQ_SCAN_V1", "1" if request.param == "v1" else "0")
+    return request.param
+
+
 def check_minimizers(seqs, offs, p):
     ix = Index(p)
     so, pos, hs = ix.minimizers(seqs, offs)
@@ -55,7 +62,7 @@ def adversarial_seqs(rng):
 
 @pytest.mark.parametrize("l,density,hpc", [(31, 0.01, True), (16, 0.01, True), (31, 0.05, False), (5, 0.3, True),
                                            (32, 0.02, True), (2, 0.5, True), (25, 1.0, True)])
-def test_minimizers_adversarial(l, density, hpc):
+def test_minimizers_adversarial(l, density, hpc, scan_version):
     rng = np.random.default_rng(7)
     buf, offs = concat_raw(adversarial_seqs(rng))
     check_minimizers(buf, offs, Params(k=5, l=l, density=density, use_hpc=hpc))
@@ -66,7 +73,7 @@ def concat_raw(seqs):
     return (np.concatenate(seqs) if seqs else np.zeros(0, np.uint8)), offs
 
 
-def test_minimizers_reads_and_genome():
+def test_minimizers_reads_and_genome(scan_version):
     g, go, _ = sim.genome(11, [1500000, 700001, 123457])
     n = check_minimizers(g, go, Params())
     assert n > 20000
@@ -75,7 +82,7 @@ def test_minimizers_reads_and_genome():
     check_minimizers(rb, ro, Params(l=16, k=8))
 
 
-def test_minimizers_dense_overflow_pool():
+def test_minimizers_dense_overflow_pool(scan_version):
     # density 1.0 selects every l-mer: every tile overflows its staged-event pool into the global pool
     rng = np.random.default_rng(3)
     buf, offs = concat_raw([random_dna(rng, 100000), random_dna(rng, 20000)])
@@ -237,18 +244,21 @@ def test_edge_reads():
     ix.close()
 
 
-def test_segment_partitioned_index_equals_whole():
+def test_segment_partitioned_index_equals_whole(scan_version):
     # multi-GPU style build: the reference is cut into base-range segments (with halo) and the result
     # must equal the single-shot index
     p = Params()
     g, go, names = sim.genome(61, [700000, 350000])
+    g = g.copy(); g[100000:100900] = ord("G"); g[800000:800050] = ord("T")     # long runs for the cuts below
     whole = Index(p); whole.add_batch(names, g, go); nu = whole.freeze()
     part = Index(p)
     rng = np.random.default_rng(2)
     order = []
     for r in range(2):
         a, b = int(go[r]), int(go[r + 1]); L = b - a
-        cuts = [0] + sorted(rng.integers(1, L, 5).tolist()) + [L]
+        inside_run = [100450, 100451] if r == 0 else [800020 - a]           # cut points inside homopolymer runs
+        eq = np.nonzero(g[a + 1:b] == g[a:b - 1])[0][:40:13] + 1             # ... and inside ordinary 2-base runs
+        cuts = sorted(set([0, L] + rng.integers(1, L, 5).tolist() + inside_run + eq.tolist()))
         for s, e in zip(cuts[:-1], cuts[1:]):
             order.append((r, L, s, e - s, a))
     for j in rng.permutation(len(order)):       # out of order on purpose
