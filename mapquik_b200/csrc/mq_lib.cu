@@ -239,8 +239,8 @@ int run_scan(mq_ctx *c, const uint8_t *d_seqs, const uint64_t *d_offs, uint32_t 
                     k_scan_minimizers<<<grid, SCAN_WARPS * 32, SCAN_WARPS * TILE_SMEM, c->stream>>>(a, c->tab);
                 } else {
                     const uint32_t ctas_needed = (n_tiles + V2_WARPS - 1) / V2_WARPS;
-                    const uint32_t grid = std::min<uint32_t>(ctas_needed, (uint32_t)c->n_sm * 4);
-                    const size_t smem = (size_t)V2_WARPS * ((V2_WARP_SMEM + 15) & ~15);
+                    const uint32_t grid = std::min<uint32_t>(ctas_needed, (uint32_t)c->n_sm * 5);
+                    const size_t smem = (size_t)V2_WARPS * V2_WARP_BYTES;
                     k_scan_minimizers_v2<<<grid, V2_WARPS * 32, smem, c->stream>>>(a, c->tab2);
                 }
             }

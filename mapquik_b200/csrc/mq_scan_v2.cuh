@@ -24,12 +24,11 @@ namespace mq {
 constexpr int V2_CS_MAX  = 256;                 // raw bytes per lane chunk
 constexpr int V2_GPL_MAX = V2_CS_MAX / 16;      // 16-byte groups per lane
 constexpr int V2_STRIDE  = 256 + 32 + 4;        // bytes per lane stream: symbols + context + zero; 73 words (odd)
-constexpr int V2_WARP_SMEM = 33 * V2_STRIDE + 33 * 4 /*nsym*/ + 32 * V2_GPL_MAX * 2 /*run masks*/ + 32 * V2_GPL_MAX /*cum*/ + 12;
-constexpr int V2_WARPS   = 4;
+constexpr int V2_WARPS   = 3;                   // 3 x 15.1 KB = 45.4 KB dynamic smem -> 5 CTAs (15 warps) per SM
 
-struct ScanTablesV2 {
-    uint64_t pairF[16], pairR[16];              // [in + 4*out]
-    uint64_t inF[4], outF[4], inR[4], outR[4];
+struct ScanTablesV2 {                           // byte offsets are used directly by the kernel
+    uint64_t pairF[16], pairR[16];              // @0, @128 : [in + 4*out]
+    uint64_t inF[4], outF[4], inR[4], outR[4];  // @256, @288, @320, @352
     uint64_t F0, R0;                            // hash state of a window of l phantom 'A's
     uint32_t sel[16];                           // PRMT selectors compacting the run-start bytes of a word
 };
@@ -53,28 +52,67 @@ __device__ __forceinline__ void v2_geometry(uint64_t gs, uint64_t ge, uint32_t n
 
 struct V2Lane { uint64_t F, R; };
 
+// explicit shared-state-space accessors (32-bit shared addresses): keeps ptxas from re-deriving the
+// generic->shared window base (S2R SR_CgaCtaId + LEA) inside the hot loops
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint64_t lds64(uint32_t a) { uint64_t v; asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds16(uint32_t a) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts64(uint32_t a, uint64_t v) { asm volatile("st.shared.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory"); }
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
+// per-warp shared-memory layout (byte offsets from the warp's base)
+constexpr int V2_CAND      = 12;                                   // candidates a lane can park before it must flush
+constexpr int V2_OFF_NSYM  = 33 * V2_STRIDE;                       // u32[33]
+constexpr int V2_OFF_RUNM  = V2_OFF_NSYM + 33 * 4;                 // u16[32][16]
+constexpr int V2_OFF_CUM   = V2_OFF_RUNM + 32 * V2_GPL_MAX * 2;    // u8 [32][16]
+constexpr int V2_OFF_CH    = (V2_OFF_CUM + 32 * V2_GPL_MAX + 7) & ~7;   // u64[32][CAND+1]  candidate hashes
+constexpr int V2_CH_STRIDE = (V2_CAND + 1) * 8;
+constexpr int V2_OFF_CO    = V2_OFF_CH + 32 * V2_CH_STRIDE;        // u8 [32][16]       candidate ordinals
+constexpr int V2_WARP_BYTES = (V2_OFF_CO + 32 * 16 + 15) & ~15;
+
 // generic (N-aware, bounds-checked) step at ordinal o of the lane's logical stream
-__device__ __forceinline__ void v2_step_generic(V2Lane &s, const uint8_t *S, int o, int lim, uint32_t l, const ScanTablesV2 &T) {
-    const uint32_t in = S[o];
+__device__ __forceinline__ void v2_step_generic(V2Lane &s, uint32_t sa, int o, int lim, uint32_t l, uint32_t ta) {
+    const uint32_t in = lds8(sa + o);
     const int oo = o + (int)l;
-    const uint32_t out = oo < lim ? (uint32_t)S[oo] : 0u;
-    const uint64_t tf = ((in & 0x80u) ? 0ull : T.inF[(in >> 3) & 3]) ^ ((out & 0x80u) ? 0ull : T.outF[(out >> 3) & 3]);
-    const uint64_t tr = ((in & 0x80u) ? 0ull : T.inR[(in >> 3) & 3]) ^ ((out & 0x80u) ? 0ull : T.outR[(out >> 3) & 3]);
+    const uint32_t out = oo < lim ? lds8(sa + oo) : 0u;
+    // single-symbol tables live behind the pair tables: inF @256, outF @288, inR @320, outR @352
+    const uint64_t tf = ((in & 0x80u) ? 0ull : lds64(ta + 256 + (in & 0x18u))) ^ ((out & 0x80u) ? 0ull : lds64(ta + 288 + (out & 0x18u)));
+    const uint64_t tr = ((in & 0x80u) ? 0ull : lds64(ta + 320 + (in & 0x18u))) ^ ((out & 0x80u) ? 0ull : lds64(ta + 352 + (out & 0x18u)));
     s.F = ror1(s.F) ^ tf; s.R = rol1(s.R) ^ tr;
 }
 
-// raw offset (inside the lane chunk) of the symbol with ordinal o
-__device__ __noinline__ uint32_t v2_raw_offset(const uint16_t *runm, const uint8_t *cum, uint32_t gpl, uint32_t o) {
+// position of the k-th (0-based) set bit of a 16-bit mask
+__device__ __forceinline__ uint32_t select16(uint32_t m, uint32_t k) {
+    uint32_t pos = 0, c;
+    c = __popc(m & 0xFFu);        if (k >= c) { k -= c; pos += 8; m >>= 8; }
+    c = __popc(m & 0xFu);         if (k >= c) { k -= c; pos += 4; m >>= 4; }
+    c = __popc(m & 0x3u);         if (k >= c) { k -= c; pos += 2; m >>= 2; }
+    c = m & 1u;                   if (k >= c) { pos += 1; }
+    return pos;
+}
+// raw offset (inside the lane chunk) of the symbol with ordinal o: group = #(cum[g] <= o) - 1
+__device__ __forceinline__ uint32_t v2_raw_offset(uint32_t runm_a, uint32_t cum_a, uint32_t gpl, uint32_t o) {
     uint32_t g = 0;
-    while (g + 1 < gpl && (uint32_t)cum[g + 1] <= o) g++;
-    return 16u * g + __fns((uint32_t)runm[g], 0, (int)(o - cum[g]) + 1);
+#pragma unroll
+    for (int w = 0; w < 4; w++) {
+        const uint32_t cw = lds32(cum_a + 4 * w);
+        // bytes of cw that are <= o (only the first gpl entries are meaningful; later ones hold 0xFF)
+        g += __popc(__vcmpleu4(cw, o * 0x01010101u) & 0x01010101u);
+    }
+    g -= 1;
+    const uint32_t rm = lds16(runm_a + 2 * g), base = lds8(cum_a + g);
+    (void)gpl;
+    return 16u * g + select16(rm, o - base);
 }
 
-__device__ __forceinline__ void v2_emit(uint32_t x, uint64_t h, uint32_t lane, uint32_t &nloc, uint32_t *tile_ev_smem, uint32_t tile,
-                                        const ScanArgs &a) {
-    uint32_t slot = atomicAdd(tile_ev_smem, 1u);
-    uint32_t meta = x | (lane << 14) | (nloc << 19);
-    nloc++;
+__device__ __forceinline__ void v2_emit(uint32_t x, uint64_t h, uint32_t lane, uint32_t j, uint32_t ev_a, uint32_t tile, const ScanArgs &a) {
+    uint32_t slot;
+    asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(slot) : "r"(ev_a) : "memory");
+    const uint32_t meta = x | (lane << 14) | (j << 19);
     if (slot < EV_CAP) {
         a.ev_hash[(uint64_t)tile * EV_CAP + slot] = h;
         a.ev_meta[(uint64_t)tile * EV_CAP + slot] = meta;
@@ -83,6 +121,28 @@ __device__ __forceinline__ void v2_emit(uint32_t x, uint64_t h, uint32_t lane, u
         if (g < a.ovf_cap) { a.ovf_tile[g] = tile; a.ovf_meta[g] = meta; a.ovf_hash[g] = h; }
     }
 }
+// resolve and emit the candidates a lane has parked (ordinal -> raw position), oldest first
+__device__ __noinline__ void v2_flush(uint32_t nc, uint32_t j0, uint32_t ch_a, uint32_t co_a, uint32_t runm_a, uint32_t cum_a, uint32_t gpl,
+                                      uint32_t c_lo, uint32_t xlo, uint32_t xlim, uint32_t lane, uint32_t ev_a, uint32_t tile,
+                                      const ScanArgs &a, uint32_t *nloc) {
+    uint32_t j = j0;
+    for (uint32_t i = 0; i < nc; i++) {
+        const uint64_t h = lds64(ch_a + 8 * i);
+        const uint32_t o = lds8(co_a + i);
+        const uint32_t x = c_lo + v2_raw_offset(runm_a, cum_a, gpl, o);
+        if (x - xlo < xlim - xlo) { v2_emit(x, h, lane, j, ev_a, tile, a); j++; }
+    }
+    *nloc = j;
+}
+
+#define V2_CANDIDATE(ORD)                                                                                     \
+    if (min((uint32_t)(F >> 32), (uint32_t)(R >> 32)) <= bound_hi) {                                          \
+        const uint64_t h_ = F < R ? F : R;                                                                    \
+        if (h_ < bound) {                                                                                     \
+            sts64(ch_a + 8 * nc, h_); sts8(co_a + nc, (uint32_t)(ORD)); nc++;                                 \
+            if (nc == V2_CAND) { v2_flush(nc, nloc, ch_a, co_a, runm_a, cum_a, gpl, c_lo, xlo, xlim, lane, ev_a, tile, a, &nloc); nc = 0; } \
+        }                                                                                                     \
+    }
 
 __global__ void __launch_bounds__(V2_WARPS * 32) k_scan_minimizers_v2(ScanArgs a, ScanTablesV2 Tin) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -91,23 +151,27 @@ __global__ void __launch_bounds__(V2_WARPS * 32) k_scan_minimizers_v2(ScanArgs a
     for (uint32_t i = threadIdx.x; i < sizeof(ScanTablesV2) / 4; i += blockDim.x) ((uint32_t *)&T)[i] = ((const uint32_t *)&Tin)[i];
     __syncthreads();
     const uint32_t lane = lane_id(), wid = threadIdx.x >> 5;
-    uint8_t *WS = smem_raw + (size_t)wid * ((V2_WARP_SMEM + 15) & ~15);
-    uint8_t *S = WS + lane * V2_STRIDE;                    // my stream
-    uint32_t *nsym = (uint32_t *)(WS + 33 * V2_STRIDE);    // symbols per stream (32 lanes + halo)
-    uint16_t *runm = (uint16_t *)(nsym + 33) + lane * V2_GPL_MAX;
-    uint8_t *cum = (uint8_t *)((uint16_t *)(nsym + 33) + 32 * V2_GPL_MAX) + lane * V2_GPL_MAX;
+    uint8_t *WS = smem_raw + (size_t)wid * V2_WARP_BYTES;
+    const uint32_t ws_a = smem_addr(WS);
+    const uint32_t sa = ws_a + lane * V2_STRIDE;                     // my stream
+    const uint32_t nsym_a = ws_a + V2_OFF_NSYM;
+    const uint32_t runm_a = ws_a + V2_OFF_RUNM + lane * V2_GPL_MAX * 2;
+    const uint32_t cum_a = ws_a + V2_OFF_CUM + lane * V2_GPL_MAX;
+    const uint32_t ch_a = ws_a + V2_OFF_CH + lane * V2_CH_STRIDE;
+    const uint32_t co_a = ws_a + V2_OFF_CO + lane * 16;
+    const uint32_t ta = smem_addr(&T);                               // pairF @0, pairR @128, single-symbol tables @256..
+    const uint32_t ev_a = smem_addr(&ev_cnt[wid]);
     const uint32_t l = a.l;
     const bool hpc = a.use_hpc != 0;
     const uint32_t bound_hi = (uint32_t)(a.bound >> 32);
     const uint64_t bound = a.bound;
-    const uint8_t *TF = (const uint8_t *)T.pairF, *TR = (const uint8_t *)T.pairR;
 
     for (;;) {
         uint32_t tile = 0;
         if (lane == 0) tile = atomicAdd(a.tile_ticket, 1u);
         tile = __shfl_sync(0xffffffffu, tile, 0);
         if (tile >= a.n_tiles) break;
-        if (lane == 0) ev_cnt[wid] = 0;
+        if (lane == 0) sts32(ev_a, 0u);
 
         // ---- geometry -------------------------------------------------------------------------
         const uint32_t sq = a.tile_seq[tile];
@@ -126,7 +190,7 @@ __global__ void __launch_bounds__(V2_WARPS * 32) k_scan_minimizers_v2(ScanArgs a
         const uint32_t own_hi = (ge - tlo) < TWs ? (uint32_t)(ge - tlo) : TWs;
         uint32_t xlo, xlim; emit_window(a, sq, gs, tlo, &xlo, &xlim);
 
-        // ---- stage + compact my chunk -----------------------------------------------------------
+        // ---- stage + compact my chunk: one byte per homopolymer-run start ---------------------------
         const uint32_t c_lo = lane * Cs;                       // x' of my first byte
         uint32_t n = 0, bad = 0;
         {
@@ -134,9 +198,10 @@ __global__ void __launch_bounds__(V2_WARPS * 32) k_scan_minimizers_v2(ScanArgs a
             uint32_t prev = 0;
             if (c_lo > own_lo && c_lo < own_hi) prev = cp[-1];  // byte before my chunk (same record)
             else if (c_lo == own_lo && tlo + own_lo > gs) prev = cp[-1];
-            uint64_t acc = 0; uint32_t fill = 0, wout = 0;
+            else if (c_lo == own_lo) prev = (uint32_t)cp[0] ^ 0xFFu;   // record starts exactly at my chunk: force a run start
             uint4 nxt = make_uint4(0, 0, 0, 0);
             if (c_lo < own_hi && c_lo + 16 > own_lo) nxt = __ldg((const uint4 *)cp);
+            sts32(cum_a, 0xFFFFFFFFu); sts32(cum_a + 4, 0xFFFFFFFFu); sts32(cum_a + 8, 0xFFFFFFFFu); sts32(cum_a + 12, 0xFFFFFFFFu);
             for (uint32_t g = 0; g < gpl; g++) {
                 const uint4 v = nxt;
                 const uint32_t xg = c_lo + 16 * g;
@@ -144,6 +209,7 @@ __global__ void __launch_bounds__(V2_WARPS * 32) k_scan_minimizers_v2(ScanArgs a
                 const uint32_t xn = xg + 16;
                 if (g + 1 < gpl && xn < own_hi && xn + 16 > own_lo) nxt = __ldg((const uint4 *)(cp + 16 * (g + 1)));
                 uint32_t rm = 0;
+                sts8(cum_a + g, n);
                 if (live) {
                     const bool partial = xg < own_lo || xg + 16 > own_hi;
                     const uint32_t uw[4] = {v.x, v.y, v.z, v.w};
@@ -159,29 +225,24 @@ __global__ void __launch_bounds__(V2_WARPS * 32) k_scan_minimizers_v2(ScanArgs a
                             for (int b = 0; b < 4; b++) if (x + b >= own_lo && x + b < own_hi) m |= 0xFFu << (8 * b);
                             dg &= m;
                             if (x <= own_lo && own_lo < x + 4 && tlo + own_lo == gs) dg |= D_RUN << (8 * (own_lo - x));   // record start
-                        } else if (xg + 4 * w == own_lo && tlo + own_lo == gs) dg |= D_RUN;                             // aligned record start
-                        const uint32_t p = (((dg >> 3) & 0x01010101u) * 0x01020408u) >> 24;      // 4 run bits
-                        bad |= dg & 0x04040404u & ((dg & 0x08080808u) >> 1);           // non-ACGT among run starts
+                        }
+                        bad |= dg & 0x04040404u & ((dg & 0x08080808u) >> 1);                       // non-ACGT among run starts
                         const uint32_t symw = ((dg & 0x03030303u) << 3) | ((dg & 0x04040404u) << 5);
-                        const uint32_t comp = __byte_perm(symw, 0u, T.sel[p]);
-                        const uint32_t cnt = __popc(p);
-                        rm |= p << (4 * w);
-                        acc |= (uint64_t)comp << (8 * fill);
-                        fill += cnt;
-                        if (fill >= 4) { *(uint32_t *)(S + 4 * wout) = (uint32_t)acc; acc >>= 32; fill -= 4; wout++; }
+                        rm |= ((((dg >> 3) & 0x01010101u) * 0x01020408u) >> 24) << (4 * w);
+#pragma unroll
+                        for (int b = 0; b < 4; b++)
+                            if (dg & (D_RUN << (8 * b))) { sts8(sa + n, (symw >> (8 * b)) & 0xFFu); n++; }
                     }
                 }
-                runm[g] = (uint16_t)rm; cum[g] = (uint8_t)n;
-                n += __popc(rm);
+                sts16(runm_a + 2 * g, rm);
             }
-            *(uint32_t *)(S + 4 * wout) = (uint32_t)acc;     // tail (<= 3 symbols + zeros)
         }
-        nsym[lane] = n;
+        sts32(nsym_a + 4 * lane, n);
 
         // ---- halo stream (slot 32): up to l-1 run-start symbols right of the tile -------------------
         uint32_t hcount = 0;
         if (tlo + TWs < ge) {
-            uint8_t *H = WS + 32 * V2_STRIDE;
+            const uint32_t ha = ws_a + 32 * V2_STRIDE;
             uint64_t haddr = tlo + TWs;
             uint32_t hcarry = a.seqs[haddr - 1];
             while (hcount < l - 1 && haddr < ge) {
@@ -200,79 +261,77 @@ __global__ void __launch_bounds__(V2_WARPS * 32) k_scan_minimizers_v2(ScanArgs a
 #pragma unroll
                 for (int b = 0; b < 4; b++) {
                     const uint32_t d = (dg >> (8 * b)) & 0xFu;
-                    if (d & D_RUN) { if (r < l - 1) { H[r] = (uint8_t)(((d & 3u) << 3) | ((d & D_N) << 5)); bad |= d & D_N; } r++; }
+                    if (d & D_RUN) { if (r < l - 1) { sts8(ha + r, ((d & 3u) << 3) | ((d & D_N) << 5)); bad |= d & D_N; } r++; }
                 }
                 hcount = min(hcount + tot, l - 1);
                 haddr += 128;
             }
         }
-        if (lane == 0) nsym[32] = hcount;
+        if (lane == 0) sts32(nsym_a + 4 * 32, hcount);
         const bool anyN = __any_sync(0xffffffffu, bad != 0);
         __syncwarp();
 
         // ---- context: the next l-1 symbols after my chunk, from the streams to my right -----------------
         uint32_t c = 0;
         for (uint32_t j = lane + 1; j <= 32 && c < l - 1; j++) {
-            const uint32_t nj = nsym[j];
-            const uint8_t *Sj = WS + j * V2_STRIDE;
-            for (uint32_t i = 0; i < nj && c < l - 1; i++, c++) S[n + c] = Sj[i];
+            const uint32_t nj = lds32(nsym_a + 4 * j);
+            const uint32_t sj = ws_a + j * V2_STRIDE;
+            for (uint32_t i = 0; i < nj && c < l - 1; i++, c++) sts8(sa + n + c, lds8(sj + i));
         }
-        S[n + c] = 0; S[n + c + 1] = 0; S[n + c + 2] = 0; S[n + c + 3] = 0;
-        __syncwarp();          // (streams are private from here on; the sync orders my context reads before later tiles)
+        sts8(sa + n + c, 0); sts8(sa + n + c + 1, 0); sts8(sa + n + c + 2, 0); sts8(sa + n + c + 3, 0);
+        __syncwarp();
 
         // ---- phase 1: warm-up over context and record-final symbols, no emission ----------------------
         V2Lane st; st.F = T.F0; st.R = T.R0;
         const int lim = (int)(n + c);                           // symbols available in my logical stream
         int o = lim - 1;
         const int o2 = max(-1, min((int)n - 1, lim - (int)l));  // first ordinal whose window is complete and mine
-        for (; o > o2; o--) v2_step_generic(st, S, o, lim, l, T);
+        if (anyN) {
+            for (; o > o2; o--) v2_step_generic(st, sa, o, lim, l, ta);
+        } else {
+            // o > o2 == lim-l (or -1): the outgoing ordinal o+l lies beyond the stream, i.e. it is a phantom
+            // 'A' (code 0) -- the pair-table row for out == 0 is the whole step
+            for (; o > o2; o--) {
+                const uint32_t off = lds8(sa + o);
+                st.F = ror1(st.F) ^ lds64(ta + off); st.R = rol1(st.R) ^ lds64(ta + 128 + off);
+            }
+        }
 
-        // ---- phase 2: emitting scan of my own symbols -------------------------------------------------
-        uint32_t *tev = &ev_cnt[wid];
+        // ---- phase 2: scan of my own symbols; selected l-mers are parked, positions resolved after --------
+        uint64_t F = st.F, R = st.R;
+        uint32_t nc = 0;
         if (anyN) {
             for (; o >= 0; o--) {
-                v2_step_generic(st, S, o, lim, l, T);
-                if (min((uint32_t)(st.F >> 32), (uint32_t)(st.R >> 32)) <= bound_hi) {
-                    const uint64_t h = st.F < st.R ? st.F : st.R;
-                    if (h < bound) { const uint32_t x = c_lo + v2_raw_offset(runm, cum, gpl, (uint32_t)o); if (x - xlo < xlim - xlo) v2_emit(x, h, lane, nloc, tev, tile, a); }
-                }
+                st.F = F; st.R = R; v2_step_generic(st, sa, o, lim, l, ta); F = st.F; R = st.R;
+                V2_CANDIDATE(o)
             }
         } else {
-            uint64_t F = st.F, R = st.R;
-            // bring o+1 to a multiple of 4
-            for (; o >= 0 && ((o + 1) & 3); o--) {
-                const uint32_t off = (uint32_t)S[o] | ((uint32_t)S[o + (int)l] << 2);
-                F = ror1(F) ^ *(const uint64_t *)(TF + off); R = rol1(R) ^ *(const uint64_t *)(TR + off);
-                if (min((uint32_t)(F >> 32), (uint32_t)(R >> 32)) <= bound_hi) {
-                    const uint64_t h = F < R ? F : R;
-                    if (h < bound) { const uint32_t x = c_lo + v2_raw_offset(runm, cum, gpl, (uint32_t)o); if (x - xlo < xlim - xlo) v2_emit(x, h, lane, nloc, tev, tile, a); }
-                }
+            for (; o >= 0 && ((o + 1) & 3); o--) {                // bring o+1 to a multiple of 4
+                const uint32_t off = lds8(sa + o) | (lds8(sa + o + (int)l) << 2);
+                F = ror1(F) ^ lds64(ta + off); R = rol1(R) ^ lds64(ta + 128 + off);
+                V2_CANDIDATE(o)
             }
-            const uint32_t *S32 = (const uint32_t *)S;
-            const uint32_t lw = l >> 2, ls = 8 * (l & 3);
+            const uint32_t lw4 = (l >> 2) * 4, ls = 8 * (l & 3);
             for (int w = ((o + 1) >> 2) - 1; w >= 0; w--) {
-                const uint32_t inw = S32[w];
-                const uint32_t outw = __funnelshift_r(S32[w + lw], S32[w + lw + 1], ls);
+                const uint32_t inw = lds32(sa + 4 * w);
+                const uint32_t outw = __funnelshift_r(lds32(sa + 4 * w + lw4), lds32(sa + 4 * w + lw4 + 4), ls);
                 const uint32_t comb = inw | (outw << 2);          // per byte: in*8 + out*32 (bit 7 clear: no N in this tile)
 #pragma unroll
                 for (int b = 3; b >= 0; b--) {
                     const uint32_t off = (comb >> (8 * b)) & 0xFFu;
-                    F = ror1(F) ^ *(const uint64_t *)(TF + off); R = rol1(R) ^ *(const uint64_t *)(TR + off);
-                    if (min((uint32_t)(F >> 32), (uint32_t)(R >> 32)) <= bound_hi) {
-                        const uint64_t h = F < R ? F : R;
-                        if (h < bound) {
-                            const uint32_t x = c_lo + v2_raw_offset(runm, cum, gpl, (uint32_t)(4 * w + b));
-                            if (x - xlo < xlim - xlo) v2_emit(x, h, lane, nloc, tev, tile, a);
-                        }
-                    }
+                    const uint64_t tf = lds64(ta + off), tr = lds64(ta + 128 + off);
+                    F = ror1(F) ^ tf; R = rol1(R) ^ tr;
+                    V2_CANDIDATE(4 * w + b)
                 }
             }
         }
+        if (nc) v2_flush(nc, nloc, ch_a, co_a, runm_a, cum_a, gpl, c_lo, xlo, xlim, lane, ev_a, tile, a, &nloc);
         __syncwarp();
         a.lane_cnt[(uint64_t)tile * 32 + lane] = (uint16_t)nloc;
-        if (lane == 0) a.tile_cnt[tile] = *tev;
+        if (lane == 0) a.tile_cnt[tile] = lds32(ev_a);
         __syncwarp();
     }
 }
+#undef V2_CANDIDATE
 
 }  // namespace mq
