@@ -1,0 +1,74 @@
+"""The C++ host CLI (host/mapquik): same command line, console lines and PAF as the reference's
+`mapquik <reads> --reference <ref>` (src/main.rs, src/closures.rs) for this path."""
+import gzip
+import os
+import subprocess
+import sys
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+GOLD = os.path.join(HERE, "golden")
+sys.path.insert(0, GOLD)
+import make_golden as MG  # noqa: E402
+
+CLI = os.path.join(ROOT, "host", "mapquik")
+
+
+def ensure_cli():
+    if not os.path.exists(CLI):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "host"), "-s"])
+    return CLI
+
+
+def write_inputs(tmp_path, gz_reads=False):
+    names, seqs = MG.read_fasta_gz(os.path.join(GOLD, "nearperfect-ecoli.100.fa.gz"))
+    g = MG.scaffold_genome(names, seqs)
+    ref = tmp_path / "scaffold.genome.fa"
+    with open(ref, "wb") as f:                       # multi-line, partly lower-case: the CLI must upper-case
+        f.write(b">chr000913 stand-in\n")
+        b = g.tobytes()
+        b = b[:100000].lower() + b[100000:]
+        for i in range(0, len(b), 70):
+            f.write(b[i:i + 70] + b"\n")
+    reads = tmp_path / ("reads.fa.gz" if gz_reads else "reads.fa")
+    data = gzip.open(os.path.join(GOLD, "nearperfect-ecoli.100.fa.gz"), "rb").read()
+    if gz_reads:
+        with gzip.open(reads, "wb") as f:
+            f.write(data)
+    else:
+        reads.write_bytes(data)
+    return str(ref), str(reads)
+
+
+def test_cli_without_gpu_fails_loudly(tmp_path, have_gpu):
+    if have_gpu:
+        pytest.skip("GPU present")
+    ref, reads = write_inputs(tmp_path)
+    r = subprocess.run([ensure_cli(), reads, "--reference", ref, "-p", str(tmp_path / "out")], capture_output=True, text=True)
+    assert r.returncode != 0 and "no CPU fallback" in r.stderr
+
+
+def test_cli_argument_errors():
+    r = subprocess.run([ensure_cli()], capture_output=True, text=True)
+    assert r.returncode != 0 and "Please specify an input file." in r.stderr
+    r = subprocess.run([ensure_cli(), "x.fa"], capture_output=True, text=True)
+    assert r.returncode != 0 and "Please specify a reference file." in r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("gz,args,golden", [(False, [], "config1_default.paf"),
+                                            (True, ["-k", "8", "-d", "0.01", "-l", "16", "-g", "100", "--threads", "11", "--debug"],
+                                             "config1_script.paf")])
+def test_cli_reproduces_golden_paf(tmp_path, gz, args, golden):
+    ref, reads = write_inputs(tmp_path, gz_reads=gz)
+    prefix = str(tmp_path / "mapquik")
+    r = subprocess.run([ensure_cli(), reads, "--reference", ref, "-p", prefix] + args, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert open(prefix + ".paf").read() == open(os.path.join(GOLD, golden)).read()
+    out = r.stdout
+    assert "Indexed reference chr000913:" in out and "unique k-min-mers in" in out
+    assert "Mapped query sequences in" in out and "Total execution time:" in out and "Maximum RSS:" in out
+    if not args:
+        assert "Warning: Using default k value (5)." in out and "Warning: Using default output prefix" not in out
