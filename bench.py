@@ -104,6 +104,16 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def scan_traffic(n_reads):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one k_scan_minimizers_v2 launch on the default
+    workload, from the committed `ncu --set full` capture (profiles/scan_traffic.json); null otherwise."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "scan_traffic.json")))
+        return t["dram_bytes_per_launch"] if n_reads == t["reads_per_launch"] else None
+    except Exception:
+        return None
+
+
 def cpu_oracle_run(g, go, names, rb, ro, n_sample, steps, warmup, threads):
     """CPU oracle (port) on a bounded sample: returns (reads/s, bases/s, index_build_s)."""
     from oracle import pyoracle as O
@@ -330,8 +340,8 @@ def main():
                     "d2h_bytes_per_step": int(n_reads * 48), "gbp_per_s": bases_total * args.steps / (t_e2e / 1e3) / 1e9,
                     "stage_ms_last_step": e2e_stage},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "k_scan_minimizers", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak if peak else None, "traffic": None, "peak_source": peak_src,
+            "roofline": {"bound": "hbm", "kernel": "k_scan_minimizers_v2", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak if peak else None, "traffic": scan_traffic(n_reads), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(algo_bytes), "avg_launch_ms": scan_avg_ms,
                          "launches": int(scan_launches),
                          "note": "integer-issue bound (64-bit ntHash roll per base), see DESIGN.md section 5"},

@@ -25,7 +25,7 @@ struct DBuf {
     template <class T> T *as() const { return (T *)p; }
 };
 
-constexpr uint64_t MAP_SUB_BATCH_BYTES = 1ull << 30;   // bases per internal mapping sub-batch
+constexpr uint64_t MAP_SUB_BATCH_BYTES = 128ull << 20;  // bases per pipelined mapping sub-batch (H2D of i+1 overlaps compute of i)
 constexpr size_t   PAD = 256;                          // slack after sequence buffers (word loads)
 
 }  // namespace
@@ -56,6 +56,11 @@ struct mq_ctx {
     std::vector<uint64_t> nb_mers; uint64_t n_unique = 0, n_keys = 0;
     // pinned bounce buffers
     void *h_pin = nullptr; size_t h_pin_cap = 0;
+    // double-buffered upload path of mq_map_batch
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr};
+    DBuf d_seqs2[2], d_offs2[2];
+    void *h_offs2[2] = {nullptr, nullptr}; size_t h_offs2_cap[2] = {0, 0};
     // timings
     std::map<std::string, float> ms;
     std::vector<std::pair<std::string, std::pair<cudaEvent_t, cudaEvent_t>>> pending;
@@ -117,9 +122,11 @@ cudaEvent_t get_event(mq_ctx *c) {
     cudaEvent_t e; cudaEventCreate(&e); return e;
 }
 struct StageTimer {
-    mq_ctx *c; std::string name; cudaEvent_t a, b;
-    StageTimer(mq_ctx *c_, const char *n) : c(c_), name(n) { a = get_event(c); b = get_event(c); cudaEventRecord(a, c->stream); }
-    ~StageTimer() { cudaEventRecord(b, c->stream); c->pending.push_back({name, {a, b}}); }
+    mq_ctx *c; std::string name; cudaEvent_t a, b; cudaStream_t st;
+    StageTimer(mq_ctx *c_, const char *n, cudaStream_t s_ = nullptr) : c(c_), name(n), st(s_ ? s_ : c_->stream) {
+        a = get_event(c); b = get_event(c); cudaEventRecord(a, st);
+    }
+    ~StageTimer() { cudaEventRecord(b, st); c->pending.push_back({name, {a, b}}); }
 };
 void timers_reset(mq_ctx *c) { c->ms.clear(); }
 void timers_collect(mq_ctx *c) {
@@ -410,6 +417,12 @@ void mq_destroy(mq_ctx *c) {
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     if (c->region_a) { cudaEventDestroy(c->region_a); cudaEventDestroy(c->region_b); }
     if (c->h_pin) cudaFreeHost(c->h_pin);
+    for (int b = 0; b < 2; b++) {
+        dfree(c->d_seqs2[b]); dfree(c->d_offs2[b]);
+        if (c->h_offs2[b]) cudaFreeHost(c->h_offs2[b]);
+        if (c->ev_copied[b]) cudaEventDestroy(c->ev_copied[b]);
+    }
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -690,6 +703,31 @@ int mq_map_batch_device(mq_ctx *c, const uint8_t *d_seqs, const uint64_t *d_offs
     return rc;
 }
 
+// upload sub-batch [i0, i1) into double-buffer slot b on the copy stream
+static int upload_async(mq_ctx *c, int b, const uint8_t *seqs, const uint64_t *offs, uint32_t i0, uint32_t i1) {
+    const uint64_t b0 = offs[i0], nb = offs[i1] - b0; const uint32_t m = i1 - i0;
+    int rc;
+    if ((rc = ensure(c, c->d_seqs2[b], nb + PAD))) return rc;
+    if ((rc = ensure(c, c->d_offs2[b], ((size_t)m + 1) * 8))) return rc;
+    if (c->h_offs2_cap[b] < ((size_t)m + 1) * 8) {
+        if (c->h_offs2[b]) cudaFreeHost(c->h_offs2[b]);
+        c->h_offs2[b] = nullptr; c->h_offs2_cap[b] = 0;
+        size_t want = ((size_t)m + 1) * 8 * 2;
+        CK(cudaMallocHost(&c->h_offs2[b], want));
+        c->h_offs2_cap[b] = want;
+    }
+    uint64_t *ho = (uint64_t *)c->h_offs2[b];
+    for (uint32_t i = 0; i <= m; i++) ho[i] = offs[i0 + i] - b0;
+    {
+        StageTimer t(c, "h2d", c->copy_stream);
+        if (nb) CK(cudaMemcpyAsync(c->d_seqs2[b].p, seqs + b0, nb, cudaMemcpyHostToDevice, c->copy_stream));
+        CK(cudaMemsetAsync((uint8_t *)c->d_seqs2[b].p + nb, 0, PAD, c->copy_stream));
+        CK(cudaMemcpyAsync(c->d_offs2[b].p, ho, ((size_t)m + 1) * 8, cudaMemcpyHostToDevice, c->copy_stream));
+    }
+    CK(cudaEventRecord(c->ev_copied[b], c->copy_stream));
+    return MQ_OK;
+}
+
 int mq_map_batch(mq_ctx *c, const uint8_t *seqs, const uint64_t *offs, uint32_t n, mq_hit *out) {
     if (!c || !offs || (!seqs && n) || (!out && n)) return MQ_ERR_ARG;
     if (!c->frozen) { c->err = "index not frozen"; return MQ_ERR_STATE; }
@@ -697,21 +735,36 @@ int mq_map_batch(mq_ctx *c, const uint8_t *seqs, const uint64_t *offs, uint32_t 
     timers_reset(c);
     int rc;
     if ((rc = check_offs(c, offs, n))) return rc;
-    uint32_t i0 = 0;
-    while (i0 < n) {
+    if (n == 0) return MQ_OK;
+    if (!c->copy_stream) {
+        CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&c->ev_copied[0], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&c->ev_copied[1], cudaEventDisableTiming));
+    }
+    // sub-batch boundaries
+    std::vector<uint32_t> cut{0};
+    for (uint32_t i0 = 0; i0 < n;) {
         uint32_t i1 = i0 + 1;
         while (i1 < n && offs[i1 + 1] - offs[i0] <= MAP_SUB_BATCH_BYTES) i1++;
-        const uint32_t m = i1 - i0;
-        if ((rc = upload_batch(c, seqs, offs, i0, i1))) return rc;
+        cut.push_back(i1); i0 = i1;
+    }
+    const size_t ns = cut.size() - 1;
+    // H2D of sub-batch i+1 runs on the copy stream while sub-batch i computes
+    if ((rc = upload_async(c, 0, seqs, offs, cut[0], cut[1]))) return rc;
+    for (size_t i = 0; i < ns; i++) {
+        const int b = (int)(i & 1);
+        const uint32_t m = cut[i + 1] - cut[i];
+        if (i + 1 < ns && (rc = upload_async(c, 1 - b, seqs, offs, cut[i + 1], cut[i + 2]))) return rc;
+        CK(cudaStreamWaitEvent(c->stream, c->ev_copied[b], 0));
         if ((rc = ensure(c, c->d_hits, (size_t)m * sizeof(HitRec)))) return rc;
-        if ((rc = map_device(c, c->d_seqs.as<uint8_t>(), c->d_offs.as<uint64_t>(), m, c->d_hits.as<HitRec>()))) return rc;
+        if ((rc = map_device(c, c->d_seqs2[b].as<uint8_t>(), c->d_offs2[b].as<uint64_t>(), m, c->d_hits.as<HitRec>()))) return rc;
         {
             StageTimer t(c, "d2h");
-            CK(cudaMemcpyAsync(out + i0, c->d_hits.p, (size_t)m * sizeof(HitRec), cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaMemcpyAsync(out + cut[i], c->d_hits.p, (size_t)m * sizeof(HitRec), cudaMemcpyDeviceToHost, c->stream));
         }
-        CK(cudaStreamSynchronize(c->stream));
-        i0 = i1;
+        CK(cudaStreamSynchronize(c->stream));      // slot b and d_hits are free again
     }
+    CK(cudaStreamSynchronize(c->copy_stream));
     timers_collect(c);
     return MQ_OK;
 }

@@ -125,7 +125,7 @@ void mqsim_add_segdups(uint64_t seed, uint8_t *g, uint64_t n, double frac) {
 }
 
 // Fill `frac` of the genome with copies of `n_fam` repeat families (consensus 5-12 kb, each copy
-// diverged 1-10 % from its family consensus, random strand, 30 % of copies truncated) -- the
+// diverged 0.1-10 % (skewed towards young copies) from its family consensus, random strand, 30 % truncated) -- the
 // maize-like config (BASELINE.json configs[3]).
 void mqsim_add_repeat_families(uint64_t seed, uint8_t *g, uint64_t n, double frac, uint32_t n_fam) {
     if (frac <= 0 || n_fam == 0 || n < 50000) return;
@@ -147,7 +147,8 @@ void mqsim_add_repeat_families(uint64_t seed, uint8_t *g, uint64_t n, double fra
             std::reverse(tmp.begin(), tmp.end());
             for (auto &c : tmp) c = comp(c);
         }
-        double div = 0.01 + 0.09 * r.uni();
+        double u = r.uni();
+        double div = 0.001 + 0.099 * u * u * u;      // skewed young: median ~1.3 %, tail to 10 %
         uint64_t dst = r.below(n - len);
         mutate_copy(tmp.data(), len, g + dst, len, div, r);
         done += len;
