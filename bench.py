@@ -232,6 +232,9 @@ def main():
         torch.cuda.set_device(local_rank)
         device = torch.device(f"cuda:{local_rank}")
         dist.init_process_group("nccl", device_id=device)
+        warm = torch.zeros(1, device=device)
+        dist.all_reduce(warm)                 # communicator set-up is not part of the index build
+        torch.cuda.synchronize()
 
     from mapquik_b200 import Index, Params, capi, HIT_DTYPE
     L = capi.lib()

@@ -312,17 +312,23 @@ __global__ void __launch_bounds__(V2_WARPS * 32) k_scan_minimizers_v2(ScanArgs a
                 V2_CANDIDATE(o)
             }
             const uint32_t lw4 = (l >> 2) * 4, ls = 8 * (l & 3);
-            for (int w = ((o + 1) >> 2) - 1; w >= 0; w--) {
-                const uint32_t inw = lds32(sa + 4 * w);
-                const uint32_t outw = __funnelshift_r(lds32(sa + 4 * w + lw4), lds32(sa + 4 * w + lw4 + 4), ls);
-                const uint32_t comb = inw | (outw << 2);          // per byte: in*8 + out*32 (bit 7 clear: no N in this tile)
-#pragma unroll
-                for (int b = 3; b >= 0; b--) {
-                    const uint32_t off = (comb >> (8 * b)) & 0xFFu;
-                    const uint64_t tf = lds64(ta + off), tr = lds64(ta + 128 + off);
-                    F = ror1(F) ^ tf; R = rol1(R) ^ tr;
-                    V2_CANDIDATE(4 * w + b)
-                }
+            int w = ((o + 1) >> 2) - 1;
+            // software pipeline: the three stream words of the next iteration are loaded one iteration ahead,
+            // and the eight table loads of an iteration are issued before its four dependent hash steps
+            uint32_t inw = 0, ow0 = 0, ow1 = 0;
+            if (w >= 0) { inw = lds32(sa + 4 * w); ow0 = lds32(sa + 4 * w + lw4); ow1 = lds32(sa + 4 * w + lw4 + 4); }
+            for (; w >= 0; w--) {
+                const uint32_t comb = inw | (__funnelshift_r(ow0, ow1, ls) << 2);   // per byte: in*8 + out*32 (no N in this tile)
+                const uint32_t o3 = comb >> 24, o2b = (comb >> 16) & 0xFFu, o1b = (comb >> 8) & 0xFFu, o0b = comb & 0xFFu;
+                const uint64_t tf3 = lds64(ta + o3), tr3 = lds64(ta + 128 + o3);
+                const uint64_t tf2 = lds64(ta + o2b), tr2 = lds64(ta + 128 + o2b);
+                const uint64_t tf1 = lds64(ta + o1b), tr1 = lds64(ta + 128 + o1b);
+                const uint64_t tf0 = lds64(ta + o0b), tr0 = lds64(ta + 128 + o0b);
+                if (w > 0) { inw = lds32(sa + 4 * w - 4); ow0 = lds32(sa + 4 * w - 4 + lw4); ow1 = lds32(sa + 4 * w + lw4); }
+                F = ror1(F) ^ tf3; R = rol1(R) ^ tr3; V2_CANDIDATE(4 * w + 3)
+                F = ror1(F) ^ tf2; R = rol1(R) ^ tr2; V2_CANDIDATE(4 * w + 2)
+                F = ror1(F) ^ tf1; R = rol1(R) ^ tr1; V2_CANDIDATE(4 * w + 1)
+                F = ror1(F) ^ tf0; R = rol1(R) ^ tr0; V2_CANDIDATE(4 * w)
             }
         }
         if (nc) v2_flush(nc, nloc, ch_a, co_a, runm_a, cum_a, gpl, c_lo, xlo, xlim, lane, ev_a, tile, a, &nloc);
