@@ -124,10 +124,11 @@ __device__ __forceinline__ void v2_emit(uint32_t x, uint64_t h, uint32_t lane, u
 // resolve and emit the candidates a lane has parked (ordinal -> raw position), oldest first
 __device__ __noinline__ void v2_flush(uint32_t nc, uint32_t j0, uint32_t ch_a, uint32_t co_a, uint32_t runm_a, uint32_t cum_a, uint32_t gpl,
                                       uint32_t c_lo, uint32_t xlo, uint32_t xlim, uint32_t lane, uint32_t ev_a, uint32_t tile,
-                                      const ScanArgs &a, uint32_t *nloc) {
+                                      const ScanArgs &a, uint64_t bound, uint32_t *nloc) {
     uint32_t j = j0;
     for (uint32_t i = 0; i < nc; i++) {
         const uint64_t h = lds64(ch_a + 8 * i);
+        if (h >= bound) continue;                      // parked on the hi-word pre-filter only: exact test here
         const uint32_t o = lds8(co_a + i);
         const uint32_t x = c_lo + v2_raw_offset(runm_a, cum_a, gpl, o);
         if (x - xlo < xlim - xlo) { v2_emit(x, h, lane, j, ev_a, tile, a); j++; }
@@ -137,11 +138,8 @@ __device__ __noinline__ void v2_flush(uint32_t nc, uint32_t j0, uint32_t ch_a, u
 
 #define V2_CANDIDATE(ORD)                                                                                     \
     if (min((uint32_t)(F >> 32), (uint32_t)(R >> 32)) <= bound_hi) {                                          \
-        const uint64_t h_ = F < R ? F : R;                                                                    \
-        if (h_ < bound) {                                                                                     \
-            sts64(ch_a + 8 * nc, h_); sts8(co_a + nc, (uint32_t)(ORD)); nc++;                                 \
-            if (nc == V2_CAND) { v2_flush(nc, nloc, ch_a, co_a, runm_a, cum_a, gpl, c_lo, xlo, xlim, lane, ev_a, tile, a, &nloc); nc = 0; } \
-        }                                                                                                     \
+        sts64(ch_a + 8 * nc, F < R ? F : R); sts8(co_a + nc, (uint32_t)(ORD)); nc++;                          \
+        if (nc == V2_CAND) { v2_flush(nc, nloc, ch_a, co_a, runm_a, cum_a, gpl, c_lo, xlo, xlim, lane, ev_a, tile, a, bound, &nloc); nc = 0; } \
     }
 
 __global__ void __launch_bounds__(V2_WARPS * 32) k_scan_minimizers_v2(ScanArgs a, ScanTablesV2 Tin) {
@@ -229,9 +227,12 @@ __global__ void __launch_bounds__(V2_WARPS * 32) k_scan_minimizers_v2(ScanArgs a
                         bad |= dg & 0x04040404u & ((dg & 0x08080808u) >> 1);                       // non-ACGT among run starts
                         const uint32_t symw = ((dg & 0x03030303u) << 3) | ((dg & 0x04040404u) << 5);
                         rm |= ((((dg >> 3) & 0x01010101u) * 0x01020408u) >> 24) << (4 * w);
+                        // store every byte at the write cursor, advance the cursor only past run starts
 #pragma unroll
-                        for (int b = 0; b < 4; b++)
-                            if (dg & (D_RUN << (8 * b))) { sts8(sa + n, (symw >> (8 * b)) & 0xFFu); n++; }
+                        for (int b = 0; b < 4; b++) {
+                            sts8(sa + n, (symw >> (8 * b)) & 0xFFu);
+                            n += (dg >> (8 * b + 3)) & 1u;
+                        }
                     }
                 }
                 sts16(runm_a + 2 * g, rm);
@@ -331,7 +332,7 @@ __global__ void __launch_bounds__(V2_WARPS * 32) k_scan_minimizers_v2(ScanArgs a
                 F = ror1(F) ^ tf0; R = rol1(R) ^ tr0; V2_CANDIDATE(4 * w)
             }
         }
-        if (nc) v2_flush(nc, nloc, ch_a, co_a, runm_a, cum_a, gpl, c_lo, xlo, xlim, lane, ev_a, tile, a, &nloc);
+        if (nc) v2_flush(nc, nloc, ch_a, co_a, runm_a, cum_a, gpl, c_lo, xlo, xlim, lane, ev_a, tile, a, bound, &nloc);
         __syncwarp();
         a.lane_cnt[(uint64_t)tile * 32 + lane] = (uint16_t)nloc;
         if (lane == 0) a.tile_cnt[tile] = lds32(ev_a);
