@@ -239,6 +239,14 @@ __global__ void __launch_bounds__(V2_WARPS * 32) k_scan_minimizers_v2(ScanArgs a
             }
         }
         sts32(nsym_a + 4 * lane, n);
+        if (!__any_sync(0xffffffffu, n != 0)) {
+            // the whole tile lies inside one homopolymer run (or outside the record): no l-mer starts here,
+            // so neither halo nor context is needed -- this keeps giant runs (N-gaps) linear instead of quadratic
+            a.lane_cnt[(uint64_t)tile * 32 + lane] = 0;
+            if (lane == 0) a.tile_cnt[tile] = 0;
+            __syncwarp();
+            continue;
+        }
 
         // ---- halo stream (slot 32): up to l-1 run-start symbols right of the tile -------------------
         uint32_t hcount = 0;

@@ -89,6 +89,51 @@ def test_minimizers_dense_overflow_pool(scan_version):
     check_minimizers(buf, offs, Params(l=7, density=1.0, use_hpc=False))
 
 
+def test_giant_runs_stay_fast_and_exact():
+    # a 6 Mbp N-gap and a 3 Mbp homopolymer inside one record: tiles inside a run must not walk to its end
+    import time
+    rng = np.random.default_rng(12)
+    x = np.concatenate([random_dna(rng, 200000), np.full(6000000, ord("N"), np.uint8), random_dna(rng, 150000),
+                        np.full(3000000, ord("A"), np.uint8), random_dna(rng, 100000)])
+    buf, offs = concat_raw([x, random_dna(rng, 50000)])
+    t0 = time.perf_counter()
+    check_minimizers(buf, offs, Params())
+    assert time.perf_counter() - t0 < 60
+
+
+def test_batch_split_invariance_and_idempotence():
+    # size-independent properties at a larger size: mapping is a pure function of (read, index), so any
+    # partition of the batch and any repetition must give the same bytes
+    p = Params()
+    g, go, names = sim.genome(71, [3000000, 1000000])
+    ix = Index(p); ix.add_batch(names, g, go); ix.freeze()
+    rb, ro, _, _ = sim.reads(71, g, go, 20000, 12000, 4000)
+    whole = ix.map_batch(rb, ro)
+    assert ix.map_batch(rb, ro).tobytes() == whole.tobytes()
+    parts = []
+    for lo, hi in ((0, 1), (1, 7001), (7001, 7002), (7002, 20000)):
+        sub = ro[lo:hi + 1] - ro[lo]
+        parts.append(ix.map_batch(rb[int(ro[lo]):int(ro[hi])], sub))
+    assert np.concatenate(parts).tobytes() == whole.tobytes()
+    # minimizer positions are strictly increasing inside every record, hashes below the bound
+    so, pos, hs = ix.minimizers(rb[:int(ro[2000])], ro[:2001])
+    for i in range(2000):
+        q = pos[int(so[i]):int(so[i + 1])].astype(np.int64)
+        assert np.all(np.diff(q) > 0)
+    assert np.all(hs < 0x28f5c28f5c28f60)
+    # reference order does not matter (ids are relabelled, everything else is identical)
+    ix2 = Index(p)
+    ix2.add_batch([names[1]], g[int(go[1]):], np.array([0, int(go[2] - go[1])], np.uint64), first_ref_idx=0)
+    ix2.add_batch([names[0]], g[:int(go[1])], np.array([0, int(go[1])], np.uint64), first_ref_idx=1)
+    ix2.freeze()
+    assert ix2.n_unique == ix.n_unique and ix2.n_keys == ix.n_keys
+    h2 = ix2.map_batch(rb, ro)
+    assert np.array_equal(h2["ref_idx"][whole["mapped"] == 1], 1 - whole["ref_idx"][whole["mapped"] == 1])
+    for f in ("mapped", "rc", "mapq", "q_start", "q_end", "r_start", "r_end", "score"):
+        assert np.array_equal(h2[f], whole[f])
+    ix.close(); ix2.close()
+
+
 def test_kminmers():
     rng = np.random.default_rng(5)
     g, go, _ = sim.genome(12, [300000, 50000])
