@@ -5,14 +5,20 @@
 //     mapquik <reads.fa|fq[.gz]> --reference <ref.fa[.gz]> [-k K] [-l L] [-d D] [-c C] [-s S] [-g G]
 //             [-p PREFIX] [--nohpc] [--threads N] [-b B] [-q Q] [--low-memory] [--nosimd]
 //             [--parallelfastx] [--debug] [--gpu ID]
-// Host I/O is deliberately simple (single reader thread, batches into pinned memory); the reference's
-// seq_io / parallelfastx threading is out of scope.  All compute happens in the library.
+// Host I/O: one reader thread parses + upper-cases records straight into pinned batch buffers while the main
+// thread maps the previous batch on the GPU and writes its PAF lines in input order (closures.rs:117-123).
+// All compute happens in the library.
 #include "../include/mapquik_b200.h"
 
+#include <fcntl.h>
 #include <sys/resource.h>
+#include <unistd.h>
 #include <zlib.h>
 
 #include <chrono>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -37,60 +43,147 @@ bool is_fasta_name(const std::string &f) {   // main.rs:196,202 (same substring 
            f.find(".fa.") != std::string::npos || ends(".fa") || ends(".fasta");
 }
 
-// FASTA / FASTQ reader (gz transparently via zlib; multi-line FASTA accepted)
-struct Fastx {
-    gzFile f = nullptr; bool fasta;
-    std::vector<char> buf; size_t pos = 0, len = 0; bool eof = false;
-    std::string pending;        // header line already consumed (FASTA)
-    Fastx(const std::string &path, bool fasta_) : fasta(fasta_) {
-        f = gzopen(path.c_str(), "rb");
-        if (!f) die("Error opening file: " + path);
-        gzbuffer(f, 1 << 20);
-        buf.resize(1 << 22);
+// copy + closures.rs:63,106 `to_ascii_uppercase` in one pass (auto-vectorised)
+inline void copy_upper(uint8_t *dst, const char *src, size_t n) {
+    for (size_t i = 0; i < n; i++) { uint8_t c = (uint8_t)src[i]; dst[i] = (uint8_t)(c - ((c >= 'a' && c <= 'z') ? 32 : 0)); }
+}
+
+// growable byte buffer in pinned host memory (mq_host_alloc) so that mq_map_batch uploads at full PCIe speed
+struct PinnedBuf {
+    uint8_t *p = nullptr; size_t size = 0, cap = 0;
+    ~PinnedBuf() { if (p) mq_host_free(p); }
+    void reserve(size_t want) {
+        if (want <= cap) return;
+        size_t nc = cap ? cap : (64u << 20);
+        while (nc < want) nc += nc / 2;
+        uint8_t *np = (uint8_t *)mq_host_alloc(nc);
+        if (!np) die("pinned host allocation failed");
+        if (size) memcpy(np, p, size);
+        if (p) mq_host_free(p);
+        p = np; cap = nc;
     }
-    ~Fastx() { if (f) gzclose(f); }
-    bool getline(std::string &out) {
-        out.clear();
-        for (;;) {
-            if (pos == len) {
-                if (eof) return !out.empty();
-                int r = gzread(f, buf.data(), (unsigned)buf.size());
-                if (r <= 0) { eof = true; return !out.empty(); }
-                pos = 0; len = (size_t)r;
-            }
-            char *nl = (char *)memchr(buf.data() + pos, '\n', len - pos);
-            if (nl) { out.append(buf.data() + pos, nl - (buf.data() + pos)); pos = (nl - buf.data()) + 1; break; }
-            out.append(buf.data() + pos, len - pos); pos = len;
+    void append_upper(const char *src, size_t n) { reserve(size + n); copy_upper(p + size, src, n); size += n; }
+    void clear() { size = 0; }
+};
+
+// FASTA / FASTQ reader (gz transparently via zlib; multi-line FASTA accepted).  Lines are handed out as
+// views into a large refillable buffer; only lines that straddle a refill are copied.
+struct Fastx {
+    gzFile f = nullptr; int fd = -1; bool fasta;     // plain files bypass zlib (read(2) straight into the buffer)
+    std::vector<char> buf; size_t pos = 0, len = 0; bool eof = false;
+    std::string spill;            // storage for a line that straddled a refill
+    bool have_hdr = false; std::string hdr;   // FASTA header already consumed
+    Fastx(const std::string &path, bool fasta_) : fasta(fasta_) {
+        unsigned char magic[2] = {0, 0};
+        fd = open(path.c_str(), O_RDONLY);
+        if (fd < 0) die("Error opening file: " + path);
+        ssize_t got = pread(fd, magic, 2, 0);
+        if (got == 2 && magic[0] == 0x1f && magic[1] == 0x8b) {        // gzip: hand the descriptor to zlib
+            f = gzdopen(fd, "rb");
+            if (!f) die("Error opening compressed file: " + path);
+            gzbuffer(f, 1 << 20);
+            fd = -1;
+        } else {
+            posix_fadvise(fd, 0, 0, POSIX_FADV_SEQUENTIAL);
         }
-        if (!out.empty() && out.back() == '\r') out.pop_back();
+        buf.resize(32u << 20);
+    }
+    ~Fastx() { if (f) gzclose(f); if (fd >= 0) close(fd); }
+    bool refill() {
+        if (eof) return false;
+        long r = f ? (long)gzread(f, buf.data(), (unsigned)buf.size()) : (long)read(fd, buf.data(), buf.size());
+        if (r <= 0) { eof = true; return false; }
+        pos = 0; len = (size_t)r;
         return true;
     }
-    // next record: id (up to first whitespace, record.id() in closures.rs:64,107) + sequence appended to seq
-    bool next(std::string &id, std::vector<uint8_t> &seq) {
-        std::string line;
+    // next line without its terminator; the view stays valid until the next call
+    bool getline(const char *&ptr, size_t &n) {
+        if (pos == len && !refill()) return false;
+        char *nl = (char *)memchr(buf.data() + pos, '\n', len - pos);
+        if (nl) { ptr = buf.data() + pos; n = (size_t)(nl - ptr); pos += n + 1; }
+        else {
+            spill.assign(buf.data() + pos, len - pos); pos = len;
+            for (;;) {
+                if (!refill()) break;
+                char *q = (char *)memchr(buf.data(), '\n', len);
+                if (q) { spill.append(buf.data(), (size_t)(q - buf.data())); pos = (size_t)(q - buf.data()) + 1; break; }
+                spill.append(buf.data(), len); pos = len;
+            }
+            ptr = spill.data(); n = spill.size();
+        }
+        if (n && ptr[n - 1] == '\r') n--;
+        return true;
+    }
+    static std::string id_of(const char *p, size_t n) {       // record.id(): up to the first whitespace
+        size_t e = 1; while (e < n && p[e] != ' ' && p[e] != '\t') e++;
+        return std::string(p + 1, e - 1);
+    }
+    // next record: id + upper-cased sequence appended to seq
+    bool next(std::string &id, PinnedBuf &seq) {
+        const char *p; size_t n;
         if (fasta) {
-            std::string hdr;
-            if (!pending.empty()) { hdr.swap(pending); }
-            else { do { if (!getline(line)) return false; } while (line.empty() || line[0] != '>'); hdr = line; }
-            id = hdr.substr(1, hdr.find_first_of(" \t") == std::string::npos ? std::string::npos : hdr.find_first_of(" \t") - 1);
-            while (getline(line)) {
-                if (!line.empty() && line[0] == '>') { pending = line; break; }
-                seq.insert(seq.end(), line.begin(), line.end());
+            if (have_hdr) { id = hdr; have_hdr = false; }
+            else { do { if (!getline(p, n)) return false; } while (n == 0 || p[0] != '>'); id = id_of(p, n); }
+            while (getline(p, n)) {
+                if (n && p[0] == '>') { hdr = id_of(p, n); have_hdr = true; break; }
+                seq.append_upper(p, n);
             }
             return true;
         }
-        do { if (!getline(line)) return false; } while (line.empty());
-        if (line[0] != '@') die("malformed FASTQ record: " + line);
-        id = line.substr(1, line.find_first_of(" \t") == std::string::npos ? std::string::npos : line.find_first_of(" \t") - 1);
-        if (!getline(line)) return false;
-        seq.insert(seq.end(), line.begin(), line.end());
-        std::string plus, qual;
-        getline(plus); getline(qual);
+        do { if (!getline(p, n)) return false; } while (n == 0);
+        if (p[0] != '@') die("malformed FASTQ record");
+        id = id_of(p, n);
+        if (!getline(p, n)) return false;
+        seq.append_upper(p, n);
+        getline(p, n); getline(p, n);      // '+' line, qualities
         return true;
     }
 };
 
-inline void upper(uint8_t *p, size_t n) { for (size_t i = 0; i < n; i++) if (p[i] >= 'a' && p[i] <= 'z') p[i] -= 32; }  // closures.rs:63,106
+// one batch of records; two of them rotate between the reader thread and the GPU
+struct Batch {
+    PinnedBuf seqs; std::vector<uint64_t> offs{0}; std::vector<std::string> ids; bool last = false;
+    void clear() { seqs.clear(); offs.assign(1, 0); ids.clear(); last = false; }
+};
+struct BatchQueue {          // single producer / single consumer over two slots
+    std::mutex m; std::condition_variable cv; Batch slot[2]; int filled[2] = {0, 0};
+};
+void reader_thread(Fastx *fx, BatchQueue *q, size_t batch_bytes) {
+    int b = 0; std::string id;
+    for (;;) {
+        { std::unique_lock<std::mutex> lk(q->m); q->cv.wait(lk, [&] { return !q->filled[b]; }); }
+        Batch &B = q->slot[b]; B.clear();
+        B.seqs.reserve(batch_bytes + (48u << 20));      // one allocation per slot, no growth copies
+        bool more = true;
+        while (B.seqs.size < batch_bytes) {
+            if (!fx->next(id, B.seqs)) { more = false; break; }
+            B.offs.push_back(B.seqs.size); B.ids.push_back(id);
+        }
+        B.last = !more;
+        { std::lock_guard<std::mutex> lk(q->m); q->filled[b] = 1; }
+        q->cv.notify_all();
+        if (!more) return;
+        b ^= 1;
+    }
+}
+// run fn(batch) over every batch of the file; parsing of batch i+1 overlaps fn(batch i)
+template <class Fn> void for_each_batch(const std::string &path, bool fasta, size_t batch_bytes, Fn fn) {
+    Fastx fx(path, fasta);
+    BatchQueue q;
+    std::thread th(reader_thread, &fx, &q, batch_bytes);
+    int b = 0;
+    for (;;) {
+        { std::unique_lock<std::mutex> lk(q.m); q.cv.wait(lk, [&] { return q.filled[b] != 0; }); }
+        Batch &B = q.slot[b];
+        const bool last = B.last;
+        if (!B.ids.empty()) fn(B);
+        { std::lock_guard<std::mutex> lk(q.m); q.filled[b] = 0; }
+        q.cv.notify_all();
+        if (last) break;
+        b ^= 1;
+    }
+    th.join();
+}
 
 double secs(std::chrono::steady_clock::time_point a) { return std::chrono::duration<double>(std::chrono::steady_clock::now() - a).count(); }
 
@@ -162,30 +255,14 @@ int main(int argc, char **argv) {
     // ---- reference ------------------------------------------------------------------------------------
     auto t_idx = std::chrono::steady_clock::now();
     std::vector<std::string> ref_names; std::vector<uint64_t> ref_lens;
-    {
-        Fastx fx(o.reference, ref_fasta);
-        const size_t BATCH = o.low_memory ? (64u << 20) : (512u << 20);
-        std::vector<uint8_t> seqs; std::vector<uint64_t> offs{0}; std::vector<std::string> ids;
-        auto flush = [&]() {
-            if (ids.empty()) return;
-            std::vector<uint64_t> nb(ids.size());
-            ck(ctx, mq_index_add(ctx, seqs.data(), offs.data(), (uint32_t)ids.size(), (uint32_t)ref_names.size(), nb.data()), "mq_index_add");
-            for (size_t i = 0; i < ids.size(); i++) {
-                printf("Indexed reference %s: %llu k-min-mers.\n", ids[i].c_str(), (unsigned long long)nb[i]);   // closures.rs:58
-                ref_names.push_back(ids[i]); ref_lens.push_back(offs[i + 1] - offs[i]);
-            }
-            seqs.clear(); offs.assign(1, 0); ids.clear();
-        };
-        std::string id;
-        for (;;) {
-            size_t before = seqs.size();
-            if (!fx.next(id, seqs)) break;
-            upper(seqs.data() + before, seqs.size() - before);
-            offs.push_back(seqs.size()); ids.push_back(id);
-            if (seqs.size() >= BATCH) flush();
+    for_each_batch(o.reference, ref_fasta, o.low_memory ? (64u << 20) : (512u << 20), [&](Batch &B) {
+        std::vector<uint64_t> nb(B.ids.size());
+        ck(ctx, mq_index_add(ctx, B.seqs.p, B.offs.data(), (uint32_t)B.ids.size(), (uint32_t)ref_names.size(), nb.data()), "mq_index_add");
+        for (size_t i = 0; i < B.ids.size(); i++) {
+            printf("Indexed reference %s: %llu k-min-mers.\n", B.ids[i].c_str(), (unsigned long long)nb[i]);        // closures.rs:58
+            ref_names.push_back(B.ids[i]); ref_lens.push_back(B.offs[i + 1] - B.offs[i]);
         }
-        flush();
-    }
+    });
     uint64_t n_unique = 0;
     ck(ctx, mq_index_freeze(ctx, ref_lens.data(), (uint32_t)ref_lens.size(), &n_unique, nullptr), "mq_index_freeze");
     printf("Indexed %llu unique k-min-mers in %.6fs.\n", (unsigned long long)n_unique, secs(t_idx));                 // closures.rs:92
@@ -193,33 +270,21 @@ int main(int argc, char **argv) {
     // ---- reads ----------------------------------------------------------------------------------------
     auto t_map = std::chrono::steady_clock::now();
     {
-        Fastx fx(o.reads, reads_fasta);
-        const size_t BATCH = 256u << 20;
-        std::vector<uint8_t> seqs; std::vector<uint64_t> offs{0}; std::vector<std::string> ids; std::vector<mq_hit> hits;
-        std::vector<char> line(1 << 16);
-        auto flush = [&]() {
-            if (ids.empty()) return;
-            hits.resize(ids.size());
-            ck(ctx, mq_map_batch(ctx, seqs.data(), offs.data(), (uint32_t)ids.size(), hits.data()), "mq_map_batch");
-            for (size_t i = 0; i < ids.size(); i++) {                    // input order, closures.rs:117-123
+        std::vector<mq_hit> hits; std::vector<char> line(1 << 16);
+        for_each_batch(o.reads, reads_fasta, 256u << 20, [&](Batch &B) {
+            hits.resize(B.ids.size());
+            ck(ctx, mq_map_batch(ctx, B.seqs.p, B.offs.data(), (uint32_t)B.ids.size(), hits.data()), "mq_map_batch");
+            for (size_t i = 0; i < B.ids.size(); i++) {                  // input order, closures.rs:117-123
                 if (!hits[i].mapped) continue;
                 const std::string &rn = ref_names[hits[i].ref_idx];
-                if (line.size() < ids[i].size() + rn.size() + 256) line.resize(ids[i].size() + rn.size() + 256);
-                int n = mq_format_paf(line.data(), line.size(), ids[i].c_str(), offs[i + 1] - offs[i], rn.c_str(), ref_lens[hits[i].ref_idx], &hits[i]);
+                if (line.size() < B.ids[i].size() + rn.size() + 256) line.resize(B.ids[i].size() + rn.size() + 256);
+                int n = mq_format_paf(line.data(), line.size(), B.ids[i].c_str(), B.offs[i + 1] - B.offs[i], rn.c_str(),
+                                      ref_lens[hits[i].ref_idx], &hits[i]);
                 if (n < 0) die("mq_format_paf failed");
-                fwrite(line.data(), 1, (size_t)n, paf); fputc('\n', paf);
+                line[n] = '\n';
+                fwrite(line.data(), 1, (size_t)n + 1, paf);
             }
-            seqs.clear(); offs.assign(1, 0); ids.clear();
-        };
-        std::string id;
-        for (;;) {
-            size_t before = seqs.size();
-            if (!fx.next(id, seqs)) break;
-            upper(seqs.data() + before, seqs.size() - before);
-            offs.push_back(seqs.size()); ids.push_back(id);
-            if (seqs.size() >= BATCH) flush();
-        }
-        flush();
+        });
     }
     fclose(paf);
     printf("Mapped query sequences in %.6fs.\n", secs(t_map));                                                      // closures.rs:211
