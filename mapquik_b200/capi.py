@@ -41,7 +41,7 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB
+    path = os.environ.get("MQ_LIB", _build.LIB)      # MQ_LIB: A/B builds of the same ABI (tuning sweeps)
     if not os.path.exists(path):
         raise MqError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                       "(nvcc); there is no CPU fallback")

@@ -37,6 +37,7 @@ struct mq_ctx {
     uint64_t bound = 0;
     ScanTables tab{};
     ScanTablesV2 tab2{};
+    int v2_ctas_per_sm = 0;
     bool scan_v1 = false;          // MQ_SCAN_V1=1 selects the first-generation scan kernel (A/B, debugging)
     std::string err;
     uint64_t launches = 0, scan_kernel_launches = 0;
@@ -246,8 +247,14 @@ int run_scan(mq_ctx *c, const uint8_t *d_seqs, const uint64_t *d_offs, uint32_t 
                     k_scan_minimizers<<<grid, SCAN_WARPS * 32, SCAN_WARPS * TILE_SMEM, c->stream>>>(a, c->tab);
                 } else {
                     const uint32_t ctas_needed = (n_tiles + V2_WARPS - 1) / V2_WARPS;
-                    const uint32_t grid = std::min<uint32_t>(ctas_needed, (uint32_t)c->n_sm * 5);
                     const size_t smem = (size_t)V2_WARPS * V2_WARP_BYTES;
+                    if (c->v2_ctas_per_sm == 0) {      // persistent grid = every CTA the chip can hold
+                        int nb = 0;
+                        if (smem > 48 * 1024) cudaFuncSetAttribute(k_scan_minimizers_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_scan_minimizers_v2, V2_WARPS * 32, smem) != cudaSuccess || nb < 1) nb = 1;
+                        c->v2_ctas_per_sm = nb;
+                    }
+                    const uint32_t grid = std::min<uint32_t>(ctas_needed, (uint32_t)(c->n_sm * c->v2_ctas_per_sm));
                     k_scan_minimizers_v2<<<grid, V2_WARPS * 32, smem, c->stream>>>(a, c->tab2);
                 }
             }

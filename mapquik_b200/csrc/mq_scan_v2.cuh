@@ -21,10 +21,18 @@
 
 namespace mq {
 
-constexpr int V2_CS_MAX  = 256;                 // raw bytes per lane chunk
+#ifndef MQ_V2_CS_MAX
+#define MQ_V2_CS_MAX 128
+#endif
+#ifndef MQ_V2_WARPS
+#define MQ_V2_WARPS 2
+#endif
+constexpr int V2_CS_MAX  = MQ_V2_CS_MAX;        // raw bytes per lane chunk (<= 256, multiple of 16)
+constexpr int V2_TW_MAX  = 32 * V2_CS_MAX;      // raw bytes per warp tile
 constexpr int V2_GPL_MAX = V2_CS_MAX / 16;      // 16-byte groups per lane
-constexpr int V2_STRIDE  = 256 + 32 + 4;        // bytes per lane stream: symbols + context + zero; 73 words (odd)
-constexpr int V2_WARPS   = 3;                   // 3 x 15.1 KB = 45.4 KB dynamic smem -> 5 CTAs (15 warps) per SM
+constexpr int V2_STRIDE  = V2_CS_MAX + 32 + 4;  // bytes per lane stream: symbols + context + zero; odd number of words
+static_assert(((V2_STRIDE / 4) & 1) == 1 && V2_CS_MAX <= 256 && V2_CS_MAX % 16 == 0, "stream stride must be an odd word count");
+constexpr int V2_WARPS   = MQ_V2_WARPS;         // warps (= tiles in flight) per CTA
 
 struct ScanTablesV2 {                           // byte offsets are used directly by the kernel
     uint64_t pairF[16], pairR[16];              // @0, @128 : [in + 4*out]
@@ -39,7 +47,7 @@ __global__ void k_tiles_per_seq_v2(const uint64_t *offs, uint32_t n, uint32_t mi
     if (i >= n) return;
     uint64_t gs = offs[i], ge = offs[i + 1], len = ge - gs;
     uint32_t t = 0;
-    if (len >= min_len && len > 0) { uint64_t span = ge - (gs & ~15ull); t = (uint32_t)((span + TW_MAX - 1) / TW_MAX); }
+    if (len >= min_len && len > 0) { uint64_t span = ge - (gs & ~15ull); t = (uint32_t)((span + V2_TW_MAX - 1) / V2_TW_MAX); }
     tiles[i] = t;
 }
 
@@ -65,11 +73,11 @@ __device__ __forceinline__ void sts16(uint32_t a, uint32_t v) { asm volatile("st
 __device__ __forceinline__ void sts8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 
 // per-warp shared-memory layout (byte offsets from the warp's base)
-constexpr int V2_CAND      = 12;                                   // candidates a lane can park before it must flush
+constexpr int V2_CAND      = (V2_CS_MAX > 128 ? 12 : 8);                                  // candidates a lane can park before it must flush
 constexpr int V2_OFF_NSYM  = 33 * V2_STRIDE;                       // u32[33]
 constexpr int V2_OFF_RUNM  = V2_OFF_NSYM + 33 * 4;                 // u16[32][16]
-constexpr int V2_OFF_CUM   = V2_OFF_RUNM + 32 * V2_GPL_MAX * 2;    // u8 [32][16]
-constexpr int V2_OFF_CH    = (V2_OFF_CUM + 32 * V2_GPL_MAX + 7) & ~7;   // u64[32][CAND+1]  candidate hashes
+constexpr int V2_OFF_CUM   = V2_OFF_RUNM + 32 * V2_GPL_MAX * 2;    // u8 [32][16] (always 16 per lane: vector compare)
+constexpr int V2_OFF_CH    = (V2_OFF_CUM + 32 * 16 + 7) & ~7;   // u64[32][CAND+1]  candidate hashes
 constexpr int V2_CH_STRIDE = (V2_CAND + 1) * 8;
 constexpr int V2_OFF_CO    = V2_OFF_CH + 32 * V2_CH_STRIDE;        // u8 [32][16]       candidate ordinals
 constexpr int V2_WARP_BYTES = (V2_OFF_CO + 32 * 16 + 15) & ~15;
@@ -154,7 +162,7 @@ __global__ void __launch_bounds__(V2_WARPS * 32) k_scan_minimizers_v2(ScanArgs a
     const uint32_t sa = ws_a + lane * V2_STRIDE;                     // my stream
     const uint32_t nsym_a = ws_a + V2_OFF_NSYM;
     const uint32_t runm_a = ws_a + V2_OFF_RUNM + lane * V2_GPL_MAX * 2;
-    const uint32_t cum_a = ws_a + V2_OFF_CUM + lane * V2_GPL_MAX;
+    const uint32_t cum_a = ws_a + V2_OFF_CUM + lane * 16;
     const uint32_t ch_a = ws_a + V2_OFF_CH + lane * V2_CH_STRIDE;
     const uint32_t co_a = ws_a + V2_OFF_CO + lane * 16;
     const uint32_t ta = smem_addr(&T);                               // pairF @0, pairR @128, single-symbol tables @256..
