@@ -12,9 +12,11 @@
 
 #include <fcntl.h>
 #include <sys/resource.h>
+#include <sys/stat.h>
 #include <unistd.h>
 #include <zlib.h>
 
+#include <algorithm>
 #include <chrono>
 #include <condition_variable>
 #include <mutex>
@@ -72,6 +74,7 @@ struct Fastx {
     gzFile f = nullptr; int fd = -1; bool fasta;     // plain files bypass zlib (read(2) straight into the buffer)
     std::vector<char> buf; size_t pos = 0, len = 0; bool eof = false;
     std::string spill;            // storage for a line that straddled a refill
+    size_t file_bytes = ~(size_t)0 >> 1;   // on-disk size of a plain file (bounds the batch allocation)
     bool have_hdr = false; std::string hdr;   // FASTA header already consumed
     Fastx(const std::string &path, bool fasta_) : fasta(fasta_) {
         unsigned char magic[2] = {0, 0};
@@ -85,6 +88,7 @@ struct Fastx {
             fd = -1;
         } else {
             posix_fadvise(fd, 0, 0, POSIX_FADV_SEQUENTIAL);
+            struct stat st; if (fstat(fd, &st) == 0 && st.st_size > 0) file_bytes = (size_t)st.st_size;
         }
         buf.resize(32u << 20);
     }
@@ -153,7 +157,7 @@ void reader_thread(Fastx *fx, BatchQueue *q, size_t batch_bytes) {
     for (;;) {
         { std::unique_lock<std::mutex> lk(q->m); q->cv.wait(lk, [&] { return !q->filled[b]; }); }
         Batch &B = q->slot[b]; B.clear();
-        B.seqs.reserve(batch_bytes + (48u << 20));      // one allocation per slot, no growth copies
+        B.seqs.reserve(std::min<size_t>(batch_bytes, fx->file_bytes) + (48u << 20));   // one allocation per slot, no growth copies
         bool more = true;
         while (B.seqs.size < batch_bytes) {
             if (!fx->next(id, B.seqs)) { more = false; break; }
