@@ -5,6 +5,7 @@
 #include "mq_kernels.cuh"
 #include "mq_scan_v2.cuh"
 #include <cstdlib>
+#include <cstddef>
 
 #include <algorithm>
 #include <array>
@@ -160,9 +161,18 @@ void fill_tables(ScanTables &T, uint32_t l) {
     }
 }
 void fill_tables_v2(ScanTablesV2 &T, const ScanTables &S, uint32_t l) {
-    memcpy(T.pairF, S.pairF, sizeof(T.pairF)); memcpy(T.pairR, S.pairR, sizeof(T.pairR));
-    memcpy(T.inF, S.inF, sizeof(T.inF)); memcpy(T.outF, S.outF, sizeof(T.outF));
-    memcpy(T.inR, S.inR, sizeof(T.inR)); memcpy(T.outR, S.outR, sizeof(T.outR));
+    // v2 symbol codes are the raw bits (c>>1)&3: A=0 C=1 T=2 G=3; S is in A,C,G,T order
+    static const int v1_of[4] = {0, 1, 3, 2};
+    static_assert(offsetof(ScanTablesV2, pairR) == 128 && offsetof(ScanTablesV2, inF) == 256 && offsetof(ScanTablesV2, outF) == 288 &&
+                  offsetof(ScanTablesV2, inR) == 320 && offsetof(ScanTablesV2, outR) == 352 && offsetof(ScanTablesV2, sel) == 400,
+                  "the kernel addresses these tables by byte offset");
+    for (int i = 0; i < 4; i++) {
+        T.inF[i] = S.inF[v1_of[i]]; T.outF[i] = S.outF[v1_of[i]]; T.inR[i] = S.inR[v1_of[i]]; T.outR[i] = S.outR[v1_of[i]];
+        for (int o = 0; o < 4; o++) {
+            T.pairF[i + 4 * o] = S.pairF[v1_of[i] | (v1_of[o] << 2)];
+            T.pairR[i + 4 * o] = S.pairR[v1_of[i] | (v1_of[o] << 2)];
+        }
+    }
     T.F0 = 0; T.R0 = 0;                       // window of l phantom 'A's
     for (uint32_t i = 0; i < l; i++) { T.F0 ^= hrol(SEED_A, l - 1 - i); T.R0 ^= hrol(SEED_T, i); }
     for (uint32_t p = 0; p < 16; p++) {       // byte-permute selectors: run-start bytes first, zero fill

@@ -38,7 +38,7 @@ struct ScanTablesV2 {                           // byte offsets are used directl
     uint64_t pairF[16], pairR[16];              // @0, @128 : [in + 4*out]
     uint64_t inF[4], outF[4], inR[4], outR[4];  // @256, @288, @320, @352
     uint64_t F0, R0;                            // hash state of a window of l phantom 'A's
-    uint32_t sel[16];                           // PRMT selectors compacting the run-start bytes of a word
+    uint32_t sel[16];                           // @400: PRMT selectors compacting the run-start bytes of a word
 };
 
 // tiles of record i on the 16-byte aligned grid
@@ -59,6 +59,22 @@ __device__ __forceinline__ void v2_geometry(uint64_t gs, uint64_t ge, uint32_t n
 }
 
 struct V2Lane { uint64_t F, R; };
+
+// v2 digest of one 4-byte word.  Symbol codes are the raw bits (c>>1)&3, i.e. A=0 C=1 T=2 G=3 (the tables are
+// built in that order on the host), so no remap is needed.
+//   symw : per byte  code<<3 | nonACGT<<7   (the byte that goes into the symbol stream)
+//   run80: 0x80 in every byte that starts a homopolymer run (all bytes without HPC)
+struct V2Dig { uint32_t symw, run80; };
+__device__ __forceinline__ V2Dig v2_digest(uint32_t u, uint32_t pv, bool use_hpc) {
+    const uint32_t t = (u >> 1) & 0x03030303u;
+    const uint32_t sel = (t & 0x3u) | ((t >> 4) & 0x30u) | ((t >> 8) & 0x300u) | ((t >> 12) & 0x3000u);
+    const uint32_t diff = __byte_perm(0x47544341u /* 'A','C','T','G' */, 0u, sel) ^ u;     // 0 where the byte is A/C/G/T
+    const uint32_t bad80 = (((diff & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | diff) & 0x80808080u;
+    uint32_t run80 = 0x80808080u;
+    if (use_hpc) { const uint32_t e = u ^ pv; run80 = (((e & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | e) & 0x80808080u; }
+    V2Dig d; d.symw = (t << 3) | bad80; d.run80 = run80;
+    return d;
+}
 
 // explicit shared-state-space accessors (32-bit shared addresses): keeps ptxas from re-deriving the
 // generic->shared window base (S2R SR_CgaCtaId + LEA) inside the hot loops
@@ -217,29 +233,42 @@ __global__ void __launch_bounds__(V2_WARPS * 32) k_scan_minimizers_v2(ScanArgs a
                 uint32_t rm = 0;
                 sts8(cum_a + g, n);
                 if (live) {
-                    const bool partial = xg < own_lo || xg + 16 > own_hi;
                     const uint32_t uw[4] = {v.x, v.y, v.z, v.w};
+                    if (xg >= own_lo && xg + 16 <= own_hi) {
+                        // interior group: compact the run-start bytes of each word with one byte-permute (selector
+                        // from a 16-entry table), store all four bytes at the write cursor and advance the cursor
+                        // only past the run starts -- later stores overwrite the slack
 #pragma unroll
-                    for (int w = 0; w < 4; w++) {
-                        const uint32_t u = uw[w];
-                        uint32_t dg = digest_word(u, (u << 8) | prev, hpc);
-                        prev = u >> 24;
-                        if (partial) {
-                            const uint32_t x = xg + 4 * w;
-                            uint32_t m = 0;
-#pragma unroll
-                            for (int b = 0; b < 4; b++) if (x + b >= own_lo && x + b < own_hi) m |= 0xFFu << (8 * b);
-                            dg &= m;
-                            if (x <= own_lo && own_lo < x + 4 && tlo + own_lo == gs) dg |= D_RUN << (8 * (own_lo - x));   // record start
+                        for (int w = 0; w < 4; w++) {
+                            const uint32_t u = uw[w];
+                            const V2Dig d = v2_digest(u, (u << 8) | prev, hpc);
+                            prev = u >> 24;
+                            const uint32_t p = ((d.run80 >> 7) * 0x01020408u) >> 24;              // 4 run bits
+                            bad |= d.symw & d.run80;                                              // non-ACGT among run starts
+                            const uint32_t comp = __byte_perm(d.symw, 0u, lds32(ta + 400 + 4 * p));
+                            const uint32_t wa = sa + n;
+                            sts8(wa, comp); sts8(wa + 1, comp >> 8); sts8(wa + 2, comp >> 16); sts8(wa + 3, comp >> 24);
+                            n += __popc(p);
+                            rm |= p << (4 * w);
                         }
-                        bad |= dg & 0x04040404u & ((dg & 0x08080808u) >> 1);                       // non-ACGT among run starts
-                        const uint32_t symw = ((dg & 0x03030303u) << 3) | ((dg & 0x04040404u) << 5);
-                        rm |= ((((dg >> 3) & 0x01010101u) * 0x01020408u) >> 24) << (4 * w);
-                        // store every byte at the write cursor, advance the cursor only past run starts
+                    } else {
+                        // group cut by a record boundary (at most two per record): byte-wise
 #pragma unroll
-                        for (int b = 0; b < 4; b++) {
-                            sts8(sa + n, (symw >> (8 * b)) & 0xFFu);
-                            n += (dg >> (8 * b + 3)) & 1u;
+                        for (int w = 0; w < 4; w++) {
+                            const uint32_t u = uw[w];
+                            const V2Dig d = v2_digest(u, (u << 8) | prev, hpc);
+                            prev = u >> 24;
+#pragma unroll
+                            for (int b = 0; b < 4; b++) {
+                                const uint32_t x = xg + 4 * w + b;
+                                if (x < own_lo || x >= own_hi) continue;
+                                const bool start = (x == own_lo && tlo + own_lo == gs) || ((d.run80 >> (8 * b)) & 0x80u);
+                                if (!start) continue;
+                                const uint32_t sb = (d.symw >> (8 * b)) & 0xFFu;
+                                bad |= sb & 0x80u;
+                                sts8(sa + n, sb); n++;
+                                rm |= 1u << (4 * w + b);
+                            }
                         }
                     }
                 }
@@ -268,17 +297,20 @@ __global__ void __launch_bounds__(V2_WARPS * 32) k_scan_minimizers_v2(ScanArgs a
                 uint32_t up = __shfl_up_sync(0xffffffffu, u, 1);
                 uint32_t prevb = lane == 0 ? hcarry : (up >> 24);
                 hcarry = __shfl_sync(0xffffffffu, u, 31) >> 24;
-                uint32_t dg = digest_word(u, (u << 8) | prevb, hpc);
+                const V2Dig d = v2_digest(u, (u << 8) | prevb, hpc);
                 uint32_t m = 0;
 #pragma unroll
-                for (int b = 0; b < 4; b++) if (wa + b < ge) m |= 0xFFu << (8 * b);
-                dg &= m;
-                uint32_t mine = __popc((dg >> 3) & 0x01010101u), tot;
+                for (int b = 0; b < 4; b++) if (wa + b < ge) m |= 0x80u << (8 * b);
+                const uint32_t run = d.run80 & m;
+                uint32_t mine = __popc(run), tot;
                 uint32_t r = hcount + warp_excl_scan(mine, &tot);
 #pragma unroll
                 for (int b = 0; b < 4; b++) {
-                    const uint32_t d = (dg >> (8 * b)) & 0xFu;
-                    if (d & D_RUN) { if (r < l - 1) { sts8(ha + r, ((d & 3u) << 3) | ((d & D_N) << 5)); bad |= d & D_N; } r++; }
+                    if (run & (0x80u << (8 * b))) {
+                        const uint32_t sb = (d.symw >> (8 * b)) & 0xFFu;
+                        if (r < l - 1) { sts8(ha + r, sb); bad |= sb & 0x80u; }
+                        r++;
+                    }
                 }
                 hcount = min(hcount + tot, l - 1);
                 haddr += 128;
@@ -290,10 +322,21 @@ __global__ void __launch_bounds__(V2_WARPS * 32) k_scan_minimizers_v2(ScanArgs a
 
         // ---- context: the next l-1 symbols after my chunk, from the streams to my right -----------------
         uint32_t c = 0;
-        for (uint32_t j = lane + 1; j <= 32 && c < l - 1; j++) {
-            const uint32_t nj = lds32(nsym_a + 4 * j);
-            const uint32_t sj = ws_a + j * V2_STRIDE;
-            for (uint32_t i = 0; i < nj && c < l - 1; i++, c++) sts8(sa + n + c, lds8(sj + i));
+        if (lds32(nsym_a + 4 * (lane + 1)) >= 32u) {
+            // common case: the stream to my right alone holds the l-1 (<= 31) symbols -- copy eight words
+            const uint32_t sj = ws_a + (lane + 1) * V2_STRIDE, wa = sa + n;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const uint32_t x = lds32(sj + 4 * i);
+                sts8(wa + 4 * i, x); sts8(wa + 4 * i + 1, x >> 8); sts8(wa + 4 * i + 2, x >> 16); sts8(wa + 4 * i + 3, x >> 24);
+            }
+            c = l - 1;
+        } else {
+            for (uint32_t j = lane + 1; j <= 32 && c < l - 1; j++) {
+                const uint32_t nj = lds32(nsym_a + 4 * j);
+                const uint32_t sj = ws_a + j * V2_STRIDE;
+                for (uint32_t i = 0; i < nj && c < l - 1; i++, c++) sts8(sa + n + c, lds8(sj + i));
+            }
         }
         sts8(sa + n + c, 0); sts8(sa + n + c + 1, 0); sts8(sa + n + c + 2, 0); sts8(sa + n + c + 3, 0);
         __syncwarp();
