@@ -221,38 +221,39 @@ __global__ void __launch_bounds__(V2_WARPS * 32) k_scan_minimizers_v2(ScanArgs a
             if (c_lo > own_lo && c_lo < own_hi) prev = cp[-1];  // byte before my chunk (same record)
             else if (c_lo == own_lo && tlo + own_lo > gs) prev = cp[-1];
             else if (c_lo == own_lo) prev = (uint32_t)cp[0] ^ 0xFFu;   // record starts exactly at my chunk: force a run start
-            uint4 nxt = make_uint4(0, 0, 0, 0);
-            if (c_lo < own_hi && c_lo + 16 > own_lo) nxt = __ldg((const uint4 *)cp);
             sts32(cum_a, 0xFFFFFFFFu); sts32(cum_a + 4, 0xFFFFFFFFu); sts32(cum_a + 8, 0xFFFFFFFFu); sts32(cum_a + 12, 0xFFFFFFFFu);
+            // groups [g0, g1) of my chunk lie completely inside the record: fast path; the (at most two) groups cut
+            // by a record boundary go byte-wise; groups outside the record hold no symbol
+            const uint32_t lo_x = max(own_lo, c_lo), hi_x = min(own_hi, c_lo + Cs);
+            uint32_t g0 = gpl, g1 = gpl;
+            if (lo_x < hi_x) { g0 = (lo_x - c_lo + 15) >> 4; g1 = (hi_x - c_lo) >> 4; if (g1 < g0) g1 = g0; }
             for (uint32_t g = 0; g < gpl; g++) {
-                const uint4 v = nxt;
-                const uint32_t xg = c_lo + 16 * g;
-                const bool live = xg < own_hi && xg + 16 > own_lo;
-                const uint32_t xn = xg + 16;
-                if (g + 1 < gpl && xn < own_hi && xn + 16 > own_lo) nxt = __ldg((const uint4 *)(cp + 16 * (g + 1)));
                 uint32_t rm = 0;
                 sts8(cum_a + g, n);
-                if (live) {
+                if (g >= g0 && g < g1) {
+                    const uint4 v = __ldg((const uint4 *)(cp + 16 * g));
                     const uint32_t uw[4] = {v.x, v.y, v.z, v.w};
-                    if (xg >= own_lo && xg + 16 <= own_hi) {
-                        // interior group: compact the run-start bytes of each word with one byte-permute (selector
-                        // from a 16-entry table), store all four bytes at the write cursor and advance the cursor
-                        // only past the run starts -- later stores overwrite the slack
+                    // compact the run-start bytes of each word with one byte-permute (selector from a 16-entry
+                    // table), store all four bytes at the write cursor and advance the cursor only past the run
+                    // starts -- later stores overwrite the slack
 #pragma unroll
-                        for (int w = 0; w < 4; w++) {
-                            const uint32_t u = uw[w];
-                            const V2Dig d = v2_digest(u, (u << 8) | prev, hpc);
-                            prev = u >> 24;
-                            const uint32_t p = ((d.run80 >> 7) * 0x01020408u) >> 24;              // 4 run bits
-                            bad |= d.symw & d.run80;                                              // non-ACGT among run starts
-                            const uint32_t comp = __byte_perm(d.symw, 0u, lds32(ta + 400 + 4 * p));
-                            const uint32_t wa = sa + n;
-                            sts8(wa, comp); sts8(wa + 1, comp >> 8); sts8(wa + 2, comp >> 16); sts8(wa + 3, comp >> 24);
-                            n += __popc(p);
-                            rm |= p << (4 * w);
-                        }
-                    } else {
-                        // group cut by a record boundary (at most two per record): byte-wise
+                    for (int w = 0; w < 4; w++) {
+                        const uint32_t u = uw[w];
+                        const V2Dig d = v2_digest(u, (u << 8) | prev, hpc);
+                        prev = u >> 24;
+                        const uint32_t p = ((d.run80 >> 7) * 0x01020408u) >> 24;              // 4 run bits
+                        bad |= d.symw & d.run80;                                              // non-ACGT among run starts
+                        const uint32_t comp = __byte_perm(d.symw, 0u, lds32(ta + 400 + 4 * p));
+                        const uint32_t wa = sa + n;
+                        sts8(wa, comp); sts8(wa + 1, comp >> 8); sts8(wa + 2, comp >> 16); sts8(wa + 3, comp >> 24);
+                        n += __popc(p);
+                        rm |= p << (4 * w);
+                    }
+                } else {
+                    const uint32_t xg = c_lo + 16 * g;
+                    if (xg < own_hi && xg + 16 > own_lo) {       // cut by a record boundary: byte-wise
+                        const uint4 v = __ldg((const uint4 *)(cp + 16 * g));
+                        const uint32_t uw[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                         for (int w = 0; w < 4; w++) {
                             const uint32_t u = uw[w];
@@ -285,13 +286,13 @@ __global__ void __launch_bounds__(V2_WARPS * 32) k_scan_minimizers_v2(ScanArgs a
             continue;
         }
 
-        // ---- halo stream (slot 32): up to l-1 run-start symbols right of the tile -------------------
+        // ---- halo stream (slot 32): up to 32 (>= l-1) run-start symbols right of the tile -------------------
         uint32_t hcount = 0;
         if (tlo + TWs < ge) {
             const uint32_t ha = ws_a + 32 * V2_STRIDE;
             uint64_t haddr = tlo + TWs;
             uint32_t hcarry = a.seqs[haddr - 1];
-            while (hcount < l - 1 && haddr < ge) {
+            while (hcount < 32u && haddr < ge) {
                 const uint64_t wa = haddr + 4ull * lane;
                 uint32_t u = (wa < ge) ? __ldg((const uint32_t *)(a.seqs + wa)) : 0u;
                 uint32_t up = __shfl_up_sync(0xffffffffu, u, 1);
@@ -308,11 +309,11 @@ __global__ void __launch_bounds__(V2_WARPS * 32) k_scan_minimizers_v2(ScanArgs a
                 for (int b = 0; b < 4; b++) {
                     if (run & (0x80u << (8 * b))) {
                         const uint32_t sb = (d.symw >> (8 * b)) & 0xFFu;
-                        if (r < l - 1) { sts8(ha + r, sb); bad |= sb & 0x80u; }
+                        if (r < 32u) { sts8(ha + r, sb); if (r < l - 1) bad |= sb & 0x80u; }
                         r++;
                     }
                 }
-                hcount = min(hcount + tot, l - 1);
+                hcount = min(hcount + tot, 32u);
                 haddr += 128;
             }
         }
