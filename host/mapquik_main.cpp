@@ -30,7 +30,7 @@
 namespace {
 
 struct Opt {
-    std::string reads, reference, prefix;
+    std::string reads, reference, prefix, save_index, load_index;
     bool has_prefix = false, debug = false, low_memory = false, nosimd = false, nohpc = false, pfx = false;
     long k = -1, l = -1, c = -1, s = -1, g = -1, threads = -1, b = -1, q = -1;
     double density = -1;
@@ -220,17 +220,19 @@ int main(int argc, char **argv) {
         else if (a == "-b" || a == "--b") o.b = atol(val("b").c_str());
         else if (a == "-q" || a == "--q") o.q = atol(val("q").c_str());
         else if (a == "--gpu") o.gpu = atoi(val("gpu").c_str());
+        else if (a == "--save-index") o.save_index = val("save-index");      // extensions: the reference has no on-disk index
+        else if (a == "--load-index") o.load_index = val("load-index");
         else if (a == "-h" || a == "--help") { printf("mapquik <reads> --reference <ref> [-k -l -d -c -s -g -p --nohpc --threads --gpu]\n"); return 0; }
         else if (!a.empty() && a[0] == '-') die("unknown option " + a);
         else o.reads = a;
     }
     if (o.reads.empty()) die("Please specify an input file.");
-    if (o.reference.empty()) die("Please specify a reference file.");
+    if (o.reference.empty() && o.load_index.empty()) die("Please specify a reference file.");
     long k = 5, l = 31, c = 4, s = 11, g = 2000, b = 1, q = 200;
     double density = 0.01;
-    const bool reads_fasta = is_fasta_name(o.reads), ref_fasta = is_fasta_name(o.reference);
+    const bool reads_fasta = is_fasta_name(o.reads), ref_fasta = o.reference.empty() || is_fasta_name(o.reference);
     if (reads_fasta) { printf("Input file: %s\nFormat: FASTA\n", o.reads.c_str()); }
-    if (ref_fasta) { printf("Reference file: %s\nFormat: FASTA\n", o.reference.c_str()); }
+    if (ref_fasta && !o.reference.empty()) { printf("Reference file: %s\nFormat: FASTA\n", o.reference.c_str()); }
     if (o.k >= 0) k = o.k; else printf("Warning: Using default k value (%ld).\n", k);                                  // main.rs:207-217
     if (o.l >= 0) l = o.l; else printf("Warning: Using default l value (%ld).\n", l);
     if (o.b >= 0) b = o.b; else printf("Warning: Using default buffer size (%ldX).\n", b);
@@ -259,16 +261,38 @@ int main(int argc, char **argv) {
     // ---- reference ------------------------------------------------------------------------------------
     auto t_idx = std::chrono::steady_clock::now();
     std::vector<std::string> ref_names; std::vector<uint64_t> ref_lens;
-    for_each_batch(o.reference, ref_fasta, o.low_memory ? (64u << 20) : (512u << 20), [&](Batch &B) {
-        std::vector<uint64_t> nb(B.ids.size());
-        ck(ctx, mq_index_add(ctx, B.seqs.p, B.offs.data(), (uint32_t)B.ids.size(), (uint32_t)ref_names.size(), nb.data()), "mq_index_add");
-        for (size_t i = 0; i < B.ids.size(); i++) {
-            printf("Indexed reference %s: %llu k-min-mers.\n", B.ids[i].c_str(), (unsigned long long)nb[i]);        // closures.rs:58
-            ref_names.push_back(B.ids[i]); ref_lens.push_back(B.offs[i + 1] - B.offs[i]);
-        }
-    });
     uint64_t n_unique = 0;
-    ck(ctx, mq_index_freeze(ctx, ref_lens.data(), (uint32_t)ref_lens.size(), &n_unique, nullptr), "mq_index_freeze");
+    if (!o.load_index.empty()) {
+        // header layout of mq_index_save (include/mapquik_b200.h): magic[8] u32 version,k,l,hpc  f64 density  u64 slots,
+        // n_unique,n_keys,n_refs,names_bytes
+        struct { char magic[8]; uint32_t version, k, l, hpc; double density; uint64_t slots, n_unique, n_keys, n_refs, names_bytes; } h;
+        FILE *f = fopen(o.load_index.c_str(), "rb");
+        if (!f || fread(&h, sizeof h, 1, f) != 1) die("cannot read index file " + o.load_index);
+        fclose(f);
+        ref_lens.resize(h.n_refs);
+        std::vector<char> names(h.names_bytes + 1);
+        uint32_t n_refs = 0; uint64_t nb = 0;
+        ck(ctx, mq_index_load(ctx, o.load_index.c_str(), ref_lens.data(), (uint32_t)ref_lens.size(), &n_refs, names.data(), h.names_bytes, &nb,
+                              &n_unique), "mq_index_load");
+        const char *q = names.data(), *e = names.data() + h.names_bytes;
+        for (uint32_t i = 0; i < n_refs; i++) { ref_names.emplace_back(q < e ? q : ""); q += ref_names.back().size() + 1; }
+        printf("Loaded index %s: %u references.\n", o.load_index.c_str(), n_refs);
+    } else {
+        for_each_batch(o.reference, ref_fasta, o.low_memory ? (64u << 20) : (512u << 20), [&](Batch &B) {
+            std::vector<uint64_t> nb(B.ids.size());
+            ck(ctx, mq_index_add(ctx, B.seqs.p, B.offs.data(), (uint32_t)B.ids.size(), (uint32_t)ref_names.size(), nb.data()), "mq_index_add");
+            for (size_t i = 0; i < B.ids.size(); i++) {
+                printf("Indexed reference %s: %llu k-min-mers.\n", B.ids[i].c_str(), (unsigned long long)nb[i]);        // closures.rs:58
+                ref_names.push_back(B.ids[i]); ref_lens.push_back(B.offs[i + 1] - B.offs[i]);
+            }
+        });
+        ck(ctx, mq_index_freeze(ctx, ref_lens.data(), (uint32_t)ref_lens.size(), &n_unique, nullptr), "mq_index_freeze");
+        if (!o.save_index.empty()) {
+            std::string blob;
+            for (auto &n : ref_names) { blob += n; blob.push_back('\0'); }
+            ck(ctx, mq_index_save(ctx, o.save_index.c_str(), blob.data(), blob.size()), "mq_index_save");
+        }
+    }
     printf("Indexed %llu unique k-min-mers in %.6fs.\n", (unsigned long long)n_unique, secs(t_idx));                 // closures.rs:92
 
     // ---- reads ----------------------------------------------------------------------------------------

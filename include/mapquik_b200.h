@@ -120,9 +120,18 @@ int mq_index_freeze(mq_ctx *, const uint64_t *ref_lens, uint32_t n_refs, uint64_
 /* per-record k-min-mer counts of the frozen index (valid after freeze), nb[n_refs] */
 int mq_index_nb_mers(mq_ctx *, uint64_t *nb, uint32_t n_refs);
 
+/* ---- on-disk index (no counterpart upstream: the reference rebuilds its index on every run) ----
+ * File = header (parameters, counts) + ref_lens + per-record k-min-mer counts + an opaque blob of the caller's
+ * (the record names, e.g. NUL-separated) + the frozen table.  load needs a fresh context created with the same
+ * k / l / density / hpc; afterwards the context behaves exactly as after mq_index_freeze. */
+int mq_index_save(mq_ctx *, const char *path, const char *names_blob, uint64_t names_bytes);
+int mq_index_load(mq_ctx *, const char *path, uint64_t *ref_lens_out, uint32_t ref_cap, uint32_t *n_refs_out,
+                  char *names_out, uint64_t names_cap, uint64_t *names_bytes_out, uint64_t *n_unique_out);
+
 /* ---- mapping  (≙ find_matches, closures.rs:102) --------------------------------------------- */
 int mq_map_batch(mq_ctx *, const uint8_t *seqs, const uint64_t *offs, uint32_t n, mq_hit *out);
-/* same with everything already resident on this ctx's device (no H2D/D2H inside) */
+/* same with everything already resident on this ctx's device (no H2D/D2H inside); d_seqs must be 16-byte
+ * aligned with >= 64 readable bytes after the last record, every record < 2^31 bases */
 int mq_map_batch_device(mq_ctx *, const uint8_t *d_seqs, const uint64_t *d_offs, uint32_t n,
                         uint64_t total_bytes, mq_hit *d_out);
 

@@ -659,6 +659,7 @@ int mq_index_freeze(mq_ctx *c, const uint64_t *ref_lens, uint32_t n_refs, uint64
     }
     rec_off.push_back((uint32_t)acc);
     if (acc != c->st_n) { c->err = "internal: directory/store mismatch"; return MQ_ERR_STATE; }
+    if (c->st_n >= (1ull << 32) - 64) { c->err = "reference too large (2^32 minimizers)"; return MQ_ERR_RANGE; }
     const uint32_t n_rec = (uint32_t)rec_id.size();
     // table: power-of-two capacity >= 2 x tuples (load factor <= 0.5), one spare slot for key == EMPTY
     uint64_t cap = 1024;
@@ -705,6 +706,91 @@ int mq_index_nb_mers(mq_ctx *c, uint64_t *nb, uint32_t n_refs) {
     if (!c || !nb) return MQ_ERR_ARG;
     if (!c->frozen) return MQ_ERR_STATE;
     for (uint32_t i = 0; i < n_refs; i++) nb[i] = i < c->nb_mers.size() ? c->nb_mers[i] : 0;
+    return MQ_OK;
+}
+
+// ---- on-disk index (the reference rebuilds its index on every run) ----------------
+namespace {
+struct IndexFileHeader {
+    char magic[8];             // "MQB200IX"
+    uint32_t version, k, l, use_hpc;
+    double density;
+    uint64_t slots, n_unique, n_keys, n_refs, names_bytes;
+};
+}
+int mq_index_save(mq_ctx *c, const char *path, const char *names_blob, uint64_t names_bytes) {
+    if (!c || !path || (names_bytes && !names_blob)) return MQ_ERR_ARG;
+    if (!c->frozen) { c->err = "index not frozen"; return MQ_ERR_STATE; }
+    cudaSetDevice(c->device);
+    FILE *f = fopen(path, "wb");
+    if (!f) { c->err = std::string("cannot create ") + path; return MQ_ERR_ARG; }
+    IndexFileHeader h{};
+    memcpy(h.magic, "MQB200IX", 8);
+    h.version = 1; h.k = c->p.k; h.l = c->p.l; h.use_hpc = c->p.use_hpc; h.density = c->p.density;
+    h.slots = c->tmask + 2; h.n_unique = c->n_unique; h.n_keys = c->n_keys; h.n_refs = c->n_refs; h.names_bytes = names_bytes;
+    bool ok = fwrite(&h, sizeof h, 1, f) == 1;
+    std::vector<uint64_t> lens(c->n_refs);
+    if (c->n_refs) {
+        if (cudaMemcpy(lens.data(), c->d_ref_lens.p, (size_t)c->n_refs * 8, cudaMemcpyDeviceToHost) != cudaSuccess) { fclose(f); c->err = "D2H ref_lens"; return MQ_ERR_CUDA; }
+        ok = ok && fwrite(lens.data(), 8, c->n_refs, f) == c->n_refs;
+        std::vector<uint64_t> nb(c->n_refs, 0);
+        for (uint32_t i = 0; i < c->n_refs && i < c->nb_mers.size(); i++) nb[i] = c->nb_mers[i];
+        ok = ok && fwrite(nb.data(), 8, c->n_refs, f) == c->n_refs;
+    }
+    if (names_bytes) ok = ok && fwrite(names_blob, 1, names_bytes, f) == names_bytes;
+    const size_t CH = 64u << 20;                       // table goes out in 64 MB pieces through the pinned bounce buffer
+    int rc = ensure_pin(c, CH);
+    if (rc) { fclose(f); return rc; }
+    const size_t total = (size_t)h.slots * sizeof(Slot);
+    for (size_t off = 0; off < total && ok; off += CH) {
+        const size_t n = std::min(CH, total - off);
+        if (cudaMemcpy(c->h_pin, (const uint8_t *)c->d_table.p + off, n, cudaMemcpyDeviceToHost) != cudaSuccess) { fclose(f); c->err = "D2H table"; return MQ_ERR_CUDA; }
+        ok = fwrite(c->h_pin, 1, n, f) == n;
+    }
+    ok = (fclose(f) == 0) && ok;
+    if (!ok) { c->err = std::string("short write to ") + path; return MQ_ERR_ARG; }
+    return MQ_OK;
+}
+int mq_index_load(mq_ctx *c, const char *path, uint64_t *ref_lens_out, uint32_t ref_cap, uint32_t *n_refs_out, char *names_out,
+                  uint64_t names_cap, uint64_t *names_bytes_out, uint64_t *n_unique_out) {
+    if (!c || !path) return MQ_ERR_ARG;
+    if (c->frozen || c->st_n || !c->dir.empty()) { c->err = "load needs a fresh context"; return MQ_ERR_STATE; }
+    cudaSetDevice(c->device);
+    FILE *f = fopen(path, "rb");
+    if (!f) { c->err = std::string("cannot open ") + path; return MQ_ERR_ARG; }
+    IndexFileHeader h{};
+    if (fread(&h, sizeof h, 1, f) != 1 || memcmp(h.magic, "MQB200IX", 8) != 0 || h.version != 1) { fclose(f); c->err = "not a mapquik_b200 index file"; return MQ_ERR_ARG; }
+    if (h.k != c->p.k || h.l != c->p.l || h.use_hpc != c->p.use_hpc || h.density != c->p.density) {
+        fclose(f); c->err = "index was built with different k / l / density / hpc"; return MQ_ERR_ARG;
+    }
+    if (h.slots < 2 || ((h.slots - 1) & (h.slots - 2)) != 0) { fclose(f); c->err = "corrupt index header"; return MQ_ERR_ARG; }
+    if (n_refs_out) *n_refs_out = (uint32_t)h.n_refs;
+    if (names_bytes_out) *names_bytes_out = h.names_bytes;
+    if (n_unique_out) *n_unique_out = h.n_unique;
+    std::vector<uint64_t> lens(h.n_refs), nb(h.n_refs);
+    bool ok = true;
+    if (h.n_refs) ok = fread(lens.data(), 8, h.n_refs, f) == h.n_refs && fread(nb.data(), 8, h.n_refs, f) == h.n_refs;
+    if (ref_lens_out) { if (ref_cap < h.n_refs) { fclose(f); c->err = "ref_lens_out too small"; return MQ_ERR_ARG; } memcpy(ref_lens_out, lens.data(), h.n_refs * 8); }
+    if (h.names_bytes) {
+        if (names_out) { if (names_cap < h.names_bytes) { fclose(f); c->err = "names_out too small"; return MQ_ERR_ARG; } ok = ok && fread(names_out, 1, h.names_bytes, f) == h.names_bytes; }
+        else ok = ok && fseek(f, (long)h.names_bytes, SEEK_CUR) == 0;
+    }
+    int rc;
+    const size_t total = (size_t)h.slots * sizeof(Slot), CH = 64u << 20;
+    if ((rc = ensure(c, c->d_table, total))) { fclose(f); return rc; }
+    if ((rc = ensure(c, c->d_ref_lens, (h.n_refs + 1) * 8))) { fclose(f); return rc; }
+    if ((rc = ensure_pin(c, CH))) { fclose(f); return rc; }
+    for (size_t off = 0; off < total && ok; off += CH) {
+        const size_t n = std::min(CH, total - off);
+        ok = fread(c->h_pin, 1, n, f) == n;
+        if (ok && cudaMemcpy((uint8_t *)c->d_table.p + off, c->h_pin, n, cudaMemcpyHostToDevice) != cudaSuccess) { fclose(f); c->err = "H2D table"; return MQ_ERR_CUDA; }
+    }
+    fclose(f);
+    if (!ok) { c->err = "truncated index file"; return MQ_ERR_ARG; }
+    if (h.n_refs && cudaMemcpy(c->d_ref_lens.p, lens.data(), h.n_refs * 8, cudaMemcpyHostToDevice) != cudaSuccess) { c->err = "H2D ref_lens"; return MQ_ERR_CUDA; }
+    c->tmask = h.slots - 2; c->n_refs = (uint32_t)h.n_refs; c->n_unique = h.n_unique; c->n_keys = h.n_keys;
+    c->nb_mers.assign(nb.begin(), nb.end());
+    c->frozen = true;
     return MQ_OK;
 }
 

@@ -139,6 +139,31 @@ class Index:
         self._ref_lens = lens
         return u.value
 
+    def save(self, path):
+        """mq_index_save: frozen table + ref_map to one file."""
+        n_refs = self._ref_lens.size
+        blob = b"\0".join(self.ref_map.get(i, ("", 0))[0].encode() for i in range(n_refs)) + b"\0" if n_refs else b""
+        self._ck(self._L.mq_index_save(self._h, str(path).encode(), blob, len(blob)), "mq_index_save")
+
+    @classmethod
+    def from_file(cls, path, params=None, device=0):
+        import struct
+        with open(path, "rb") as f:
+            hdr = f.read(8 + 4 * 4 + 8 + 8 * 5)
+        magic, ver, k, l, hpc, dens, slots, n_unique, n_keys, n_refs, names_bytes = struct.unpack("<8sIIIIdQQQQQ", hdr)
+        if magic != b"MQB200IX":
+            raise MqError("not a mapquik_b200 index file")
+        p = params or Params(k=k, l=l, density=dens, use_hpc=bool(hpc))
+        ix = cls(p, device)
+        lens = np.zeros(n_refs, np.uint64); names = C.create_string_buffer(max(int(names_bytes), 1))
+        n = C.c_uint32(); nb = C.c_uint64(); nu = C.c_uint64()
+        ix._ck(ix._L.mq_index_load(ix._h, str(path).encode(), lens.ctypes.data, n_refs, C.byref(n), names, names_bytes,
+                                   C.byref(nb), C.byref(nu)), "mq_index_load")
+        parts = names.raw[:names_bytes].split(b"\0")
+        ix.ref_map = {i: (parts[i].decode() if i < len(parts) else "", int(lens[i])) for i in range(n_refs)}
+        ix._ref_lens = lens; ix.frozen = True; ix.n_unique = nu.value; ix.n_keys = n_keys
+        return ix
+
     def get_count(self):
         return self.n_unique
 

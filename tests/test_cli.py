@@ -72,3 +72,15 @@ def test_cli_reproduces_golden_paf(tmp_path, gz, args, golden):
     assert "Mapped query sequences in" in out and "Total execution time:" in out and "Maximum RSS:" in out
     if not args:
         assert "Warning: Using default k value (5)." in out and "Warning: Using default output prefix" not in out
+
+
+@pytest.mark.gpu
+def test_cli_save_and_load_index(tmp_path):
+    ref, reads = write_inputs(tmp_path)
+    idx = str(tmp_path / "scaffold.mqi")
+    r1 = subprocess.run([ensure_cli(), reads, "--reference", ref, "-p", str(tmp_path / "a"), "--save-index", idx], capture_output=True, text=True)
+    assert r1.returncode == 0, r1.stderr
+    r2 = subprocess.run([ensure_cli(), reads, "--load-index", idx, "-p", str(tmp_path / "b")], capture_output=True, text=True)
+    assert r2.returncode == 0, r2.stderr
+    assert open(str(tmp_path / "a.paf")).read() == open(str(tmp_path / "b.paf")).read() == open(os.path.join(GOLD, "config1_default.paf")).read()
+    assert "Loaded index" in r2.stdout

@@ -330,3 +330,22 @@ def test_errors_and_state():
     with pytest.raises(MqError):
         ix.add_batch(["x"], np.zeros(4, np.uint8), np.array([0, 4], np.uint64))
     ix.close()
+
+
+def test_index_save_load_roundtrip(tmp_path):
+    # the frozen table written to disk and loaded into a fresh context maps identically
+    from mapquik_b200 import MqError
+    p = Params(k=4, l=21, density=0.03)
+    g, go, names = sim.genome(81, [600000, 250000, 90000])
+    ix = Index(p); nb = ix.add_batch(names, g, go); ix.freeze()
+    rb, ro, _, _ = sim.reads(81, g, go, 1500, 8000, 2500)
+    hits = ix.map_batch(rb, ro)
+    path = tmp_path / "idx.mqi"
+    ix.save(path)
+    ix2 = Index.from_file(path)
+    assert ix2.n_unique == ix.n_unique and ix2.n_keys == ix.n_keys
+    assert ix2.ref_map == ix.ref_map and np.array_equal(ix2.nb_mers(), nb)
+    assert ix2.map_batch(rb, ro).tobytes() == hits.tobytes()
+    with pytest.raises(MqError):
+        Index.from_file(path, params=Params(k=5, l=21, density=0.03))     # parameter mismatch is refused
+    ix.close(); ix2.close()
