@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--k", type=int, default=5); ap.add_argument("--l", type=int, default=31)
     ap.add_argument("--density", type=float, default=0.01)
     ap.add_argument("--no-oracle-index", action="store_true")
+    ap.add_argument("--pinned", action="store_true", help="copy genome and reads into pinned host buffers first (full PCIe speed)")
     a = ap.parse_args()
     from mapquik_b200 import Index, Params, sim
     from oracle import pyoracle as O
@@ -50,8 +51,19 @@ def main():
         mean, sd, seed = 10000, 1500, 2
     t_gen = time.perf_counter() - t0
     rb, ro, rn, tr = sim.reads(seed, g, go, a.reads, mean, sd, 1000, 0.005, with_names=False)
+    if a.pinned:
+        import ctypes as C
+        from mapquik_b200 import capi
+        Lc = capi.lib()
+
+        def pin(arr):
+            ptr = Lc.mq_host_alloc(arr.nbytes + 64)
+            v = np.frombuffer((C.c_uint8 * arr.nbytes).from_address(ptr), dtype=arr.dtype)
+            v[:] = arr
+            return v
+        g, rb = pin(g), pin(rb)
     p = Params(k=a.k, l=a.l, density=a.density)
-    out = {"config": a.config, "genome_bp": int(go[-1]), "contigs": len(names), "reads": a.reads, "read_bp": int(ro[-1]),
+    out = {"pinned": bool(a.pinned), "config": a.config, "genome_bp": int(go[-1]), "contigs": len(names), "reads": a.reads, "read_bp": int(ro[-1]),
            "k": a.k, "l": a.l, "density": a.density, "gen_s": t_gen}
 
     ix = Index(p)
