@@ -844,11 +844,14 @@ int mq_map_batch(mq_ctx *c, const uint8_t *seqs, const uint64_t *offs, uint32_t 
         CK(cudaEventCreateWithFlags(&c->ev_copied[0], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&c->ev_copied[1], cudaEventDisableTiming));
     }
-    // sub-batch boundaries
+    // sub-batch boundaries: about an eighth of the batch, between 128 MB and 1 GB -- small enough that the first
+    // (un-overlapped) upload is short, large enough that per-sub-batch launches and scalar read-backs stay negligible
+    const uint64_t total_bytes = offs[n] - offs[0];
+    const uint64_t sub_bytes = std::min<uint64_t>(std::max<uint64_t>(total_bytes / 8, MAP_SUB_BATCH_BYTES), 1ull << 30);
     std::vector<uint32_t> cut{0};
     for (uint32_t i0 = 0; i0 < n;) {
         uint32_t i1 = i0 + 1;
-        while (i1 < n && offs[i1 + 1] - offs[i0] <= MAP_SUB_BATCH_BYTES) i1++;
+        while (i1 < n && offs[i1 + 1] - offs[i0] <= sub_bytes) i1++;
         cut.push_back(i1); i0 = i1;
     }
     const size_t ns = cut.size() - 1;
