@@ -84,3 +84,18 @@ def test_cli_save_and_load_index(tmp_path):
     assert r2.returncode == 0, r2.stderr
     assert open(str(tmp_path / "a.paf")).read() == open(str(tmp_path / "b.paf")).read() == open(os.path.join(GOLD, "config1_default.paf")).read()
     assert "Loaded index" in r2.stdout
+
+
+@pytest.mark.gpu
+def test_cli_fastq_reads(tmp_path):
+    # same reads as 4-line FASTQ (format chosen by file name like main.rs:196-206): identical PAF
+    ref, reads = write_inputs(tmp_path)
+    names, seqs = MG.read_fasta_gz(os.path.join(GOLD, "nearperfect-ecoli.100.fa.gz"))
+    fq = tmp_path / "reads.fastq"
+    with open(fq, "wb") as f:
+        for n, s in zip(names, seqs):
+            f.write(b"@" + n.encode() + b" some description\n" + s.tobytes() + b"\n+\n" + b"I" * len(s) + b"\n")
+    r = subprocess.run([ensure_cli(), str(fq), "--reference", ref, "-p", str(tmp_path / "fq")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "Format: FASTA" in r.stdout            # printed for the reference only
+    assert open(str(tmp_path / "fq.paf")).read() == open(os.path.join(GOLD, "config1_default.paf")).read()

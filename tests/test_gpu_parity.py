@@ -349,3 +349,21 @@ def test_index_save_load_roundtrip(tmp_path):
     with pytest.raises(MqError):
         Index.from_file(path, params=Params(k=5, l=21, density=0.03))     # parameter mismatch is refused
     ix.close(); ix2.close()
+
+
+def test_reads_and_reference_with_non_acgt():
+    # N runs and IUPAC codes in both the reference and the reads go through the N-aware scan path
+    p = Params()
+    g, go, names = sim.genome(91, [500000, 200000])
+    g = g.copy()
+    rng = np.random.default_rng(91)
+    for pos in rng.integers(1000, 690000, 40):
+        g[pos:pos + int(rng.integers(1, 300))] = ord("N")
+    g[rng.integers(0, 700000, 200)] = np.frombuffer(b"RYKMSWBDHV", np.uint8)[rng.integers(0, 10, 200)]
+    ix, oix = build_both(p, names, g, go)
+    rb, ro, rn, _ = sim.reads(91, g, go, 1200, 9000, 3000, contig_names=names)
+    rb = rb.copy(); rb[rng.integers(0, rb.size, 3000)] = ord("N")
+    compare_matches(ix, oix, rb, ro)
+    hits = compare_hits(ix, oix, rb, ro, rn)
+    assert hits["mapped"].mean() > 0.9
+    ix.close()
