@@ -367,3 +367,62 @@ def test_reads_and_reference_with_non_acgt():
     hits = compare_hits(ix, oix, rb, ro, rn)
     assert hits["mapped"].mean() > 0.9
     ix.close()
+
+
+def _fuzz_record(rng, n):
+    kind = rng.integers(0, 6)
+    if kind == 0:
+        return random_dna(rng, n)
+    if kind == 1:                                            # long runs
+        base = random_dna(rng, max(1, n // 6 + 1))
+        return np.repeat(base, rng.integers(1, 13, base.size))[:n]
+    if kind == 2:                                            # short tandem repeat
+        unit = random_dna(rng, int(rng.integers(1, 7)))
+        return np.tile(unit, n // unit.size + 1)[:n]
+    if kind == 3:                                            # sprinkled non-ACGT
+        x = random_dna(rng, n).copy()
+        if n:
+            x[rng.integers(0, n, max(1, n // 50))] = np.frombuffer(b"NRYacgt-", np.uint8)[rng.integers(0, 8, max(1, n // 50))]
+        return x
+    if kind == 4:                                            # one symbol
+        return np.full(n, ord("ACGTN"[int(rng.integers(0, 5))]), np.uint8)
+    x = random_dna(rng, n).copy()                            # giant run in the middle
+    if n > 10:
+        a = int(rng.integers(0, n // 2)); x[a:a + int(rng.integers(1, n - a))] = ord("T")
+    return x
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_minimizers_fuzz_tile_boundaries(seed, scan_version):
+    # record lengths around every granularity of the tiling (16-byte groups, 128-byte lane chunks, 4,096 / 8,192-base
+    # tiles), random start alignment (records are packed back to back), random l / density / HPC
+    rng = np.random.default_rng(1000 + seed)
+    lens = []
+    for _ in range(int(rng.integers(3, 40))):
+        base = int(rng.choice([0, 16, 128, 256, 4096, 8192, 12288, 3 * 4096 + 128]))
+        lens.append(max(0, base * int(rng.integers(0, 3)) + int(rng.integers(-20, 40))))
+    seqs = [_fuzz_record(rng, n) for n in lens]
+    buf, offs = concat_raw(seqs)
+    l = int(rng.integers(2, 33))
+    p = Params(k=int(rng.integers(1, 9)), l=l, density=float(rng.choice([0.005, 0.01, 0.05, 0.3, 1.0])), use_hpc=bool(rng.integers(0, 2)))
+    check_minimizers(buf, offs, p)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_hits_fuzz_small_genomes(seed):
+    rng = np.random.default_rng(2000 + seed)
+    k, l = int(rng.integers(2, 8)), int(rng.integers(8, 33))
+    p = Params(k=k, l=l, density=float(rng.choice([0.01, 0.03, 0.08])), use_hpc=bool(rng.integers(0, 2)),
+               c=int(rng.integers(0, 6)), s=int(rng.integers(0, 15)), g=int(rng.choice([50, 500, 2000, 100000])))
+    if rng.integers(0, 2):
+        g, go = repeat_genome(rng, n_contigs=int(rng.integers(1, 9)), units=int(rng.integers(5, 30)), fam=int(rng.integers(1, 5)),
+                              fam_len=int(rng.integers(500, 4000)), div=float(rng.choice([0.0, 0.002, 0.01])))
+        names = [f"c{i}" for i in range(len(go) - 1)]
+    else:
+        g, go, names = sim.genome(int(seed) + 300, [int(x) for x in rng.integers(20000, 400000, int(rng.integers(1, 6)))])
+    ix, oix = build_both(p, names, g, go)
+    rb, ro, rn, _ = sim.reads(int(seed) + 300, g, go, 600, int(rng.integers(800, 12000)), 1500, min_len=100,
+                              error_rate=float(rng.choice([0.0, 0.005, 0.03])), contig_names=names)
+    compare_matches(ix, oix, rb, ro)
+    compare_hits(ix, oix, rb, ro, rn)
+    ix.close()
