@@ -227,11 +227,14 @@ __global__ void __launch_bounds__(V2_WARPS * 32) k_scan_minimizers_v2(ScanArgs a
             const uint32_t lo_x = max(own_lo, c_lo), hi_x = min(own_hi, c_lo + Cs);
             uint32_t g0 = gpl, g1 = gpl;
             if (lo_x < hi_x) { g0 = (lo_x - c_lo + 15) >> 4; g1 = (hi_x - c_lo) >> 4; if (g1 < g0) g1 = g0; }
+            uint4 nxt = make_uint4(0, 0, 0, 0);
+            if (g0 < g1) nxt = __ldg((const uint4 *)(cp + 16 * g0));          // prefetch: one group ahead
             for (uint32_t g = 0; g < gpl; g++) {
                 uint32_t rm = 0;
                 sts8(cum_a + g, n);
                 if (g >= g0 && g < g1) {
-                    const uint4 v = __ldg((const uint4 *)(cp + 16 * g));
+                    const uint4 v = nxt;
+                    if (g + 1 < g1) nxt = __ldg((const uint4 *)(cp + 16 * (g + 1)));
                     const uint32_t uw[4] = {v.x, v.y, v.z, v.w};
                     // compact the run-start bytes of each word with one byte-permute (selector from a 16-entry
                     // table), store all four bytes at the write cursor and advance the cursor only past the run
