@@ -11,14 +11,16 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # a fresh checkout has no built artefacts (*.so are git-ignored): build them once, like __graft_entry__.build()
+    from mapquik_b200 import _build
+    import subprocess
+    if not (os.path.exists(_build.LIB) and os.path.exists(_build.HOSTLIB)):
+        _build.build_all()
+    if not os.path.exists(os.path.join(ROOT, "oracle", "libmq_oracle.so")):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-s"])
 
 
 def _have_gpu():
-    try:
-        import ctypes
-        lib = ctypes.CDLL("libcudart.so.12") if False else None  # noqa: F841  (torch is the portable probe)
-    except Exception:
-        pass
     try:
         import torch
         return torch.cuda.is_available()
