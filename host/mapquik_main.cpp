@@ -4,7 +4,7 @@
 // src/closures.rs:22-211) for the seeding->chaining path:
 //     mapquik <reads.fa|fq[.gz]> --reference <ref.fa[.gz]> [-k K] [-l L] [-d D] [-c C] [-s S] [-g G]
 //             [-p PREFIX] [--nohpc] [--threads N] [-b B] [-q Q] [--low-memory] [--nosimd]
-//             [--parallelfastx] [--debug] [--gpu ID]
+//             [--parallelfastx] [--debug] [--gpu ID] [--save-index F] [--load-index F] [--rescue k,l,d]
 // Host I/O: one reader thread parses + upper-cases records straight into pinned batch buffers while the main
 // thread maps the previous batch on the GPU and writes its PAF lines in input order (closures.rs:117-123).
 // All compute happens in the library.
@@ -30,7 +30,7 @@
 namespace {
 
 struct Opt {
-    std::string reads, reference, prefix, save_index, load_index;
+    std::string reads, reference, prefix, save_index, load_index, rescue;
     bool has_prefix = false, debug = false, low_memory = false, nosimd = false, nohpc = false, pfx = false;
     long k = -1, l = -1, c = -1, s = -1, g = -1, threads = -1, b = -1, q = -1;
     double density = -1;
@@ -222,6 +222,7 @@ int main(int argc, char **argv) {
         else if (a == "--gpu") o.gpu = atoi(val("gpu").c_str());
         else if (a == "--save-index") o.save_index = val("save-index");      // extensions: the reference has no on-disk index
         else if (a == "--load-index") o.load_index = val("load-index");
+        else if (a == "--rescue") o.rescue = val("rescue");                  // "k,l,density": second pass over the unmapped reads
         else if (a == "-h" || a == "--help") { printf("mapquik <reads> --reference <ref> [-k -l -d -c -s -g -p --nohpc --threads --gpu]\n"); return 0; }
         else if (!a.empty() && a[0] == '-') die("unknown option " + a);
         else o.reads = a;
@@ -297,13 +298,21 @@ int main(int argc, char **argv) {
 
     // ---- reads ----------------------------------------------------------------------------------------
     auto t_map = std::chrono::steady_clock::now();
+    PinnedBuf un_seqs; std::vector<uint64_t> un_offs{0}; std::vector<std::string> un_ids;      // unmapped reads (--rescue)
     {
         std::vector<mq_hit> hits; std::vector<char> line(1 << 16);
         for_each_batch(o.reads, reads_fasta, 256u << 20, [&](Batch &B) {
             hits.resize(B.ids.size());
             ck(ctx, mq_map_batch(ctx, B.seqs.p, B.offs.data(), (uint32_t)B.ids.size(), hits.data()), "mq_map_batch");
             for (size_t i = 0; i < B.ids.size(); i++) {                  // input order, closures.rs:117-123
-                if (!hits[i].mapped) continue;
+                if (!hits[i].mapped) {
+                    if (!o.rescue.empty()) {                             // keep the read for the second pass
+                        const size_t n = (size_t)(B.offs[i + 1] - B.offs[i]);
+                        un_seqs.reserve(un_seqs.size + n); memcpy(un_seqs.p + un_seqs.size, B.seqs.p + B.offs[i], n); un_seqs.size += n;
+                        un_offs.push_back(un_seqs.size); un_ids.push_back(B.ids[i]);
+                    }
+                    continue;
+                }
                 const std::string &rn = ref_names[hits[i].ref_idx];
                 if (line.size() < B.ids[i].size() + rn.size() + 256) line.resize(B.ids[i].size() + rn.size() + 256);
                 int n = mq_format_paf(line.data(), line.size(), B.ids[i].c_str(), B.offs[i + 1] - B.offs[i], rn.c_str(),
@@ -317,6 +326,44 @@ int main(int argc, char **argv) {
     fclose(paf);
     printf("Mapped query sequences in %.6fs.\n", secs(t_map));                                                      // closures.rs:211
     mq_destroy(ctx);
+
+    // ---- second pass over the unmapped reads with another (k, l, density) -------------------------------
+    // (the reference does this with a second run of the binary on the unmapped set,
+    //  experiments/chm13/run_chm13_mapquik_unmapped.sh:8-21; here both passes share one process)
+    if (!o.rescue.empty()) {
+        auto t_res = std::chrono::steady_clock::now();
+        long k2 = 0, l2 = 0; double d2 = 0;
+        if (sscanf(o.rescue.c_str(), "%ld,%ld,%lf", &k2, &l2, &d2) != 3) die("--rescue expects k,l,density");
+        if (o.reference.empty()) die("--rescue needs --reference (the second index is built from it)");
+        size_t rescued = 0;
+        std::string res_name = prefix + ".rescue.paf";
+        FILE *rp = fopen(res_name.c_str(), "w");
+        if (!rp) die("Couldn't create " + res_name);
+        if (!un_ids.empty()) {
+            mq_params p2 = p; p2.k = (uint32_t)k2; p2.l = (uint32_t)l2; p2.density = d2;
+            mq_ctx *c2 = nullptr;
+            ck(nullptr, mq_create(&c2, &p2, o.gpu), "mq_create (rescue)");
+            std::vector<std::string> names2; std::vector<uint64_t> lens2;
+            for_each_batch(o.reference, ref_fasta, o.low_memory ? (64u << 20) : (512u << 20), [&](Batch &B) {
+                ck(c2, mq_index_add(c2, B.seqs.p, B.offs.data(), (uint32_t)B.ids.size(), (uint32_t)names2.size(), nullptr), "mq_index_add (rescue)");
+                for (size_t i = 0; i < B.ids.size(); i++) { names2.push_back(B.ids[i]); lens2.push_back(B.offs[i + 1] - B.offs[i]); }
+            });
+            ck(c2, mq_index_freeze(c2, lens2.data(), (uint32_t)lens2.size(), nullptr, nullptr), "mq_index_freeze (rescue)");
+            std::vector<mq_hit> h2(un_ids.size()); std::vector<char> line(1 << 16);
+            ck(c2, mq_map_batch(c2, un_seqs.p, un_offs.data(), (uint32_t)un_ids.size(), h2.data()), "mq_map_batch (rescue)");
+            for (size_t i = 0; i < un_ids.size(); i++) {
+                if (!h2[i].mapped) continue;
+                const std::string &rn = names2[h2[i].ref_idx];
+                if (line.size() < un_ids[i].size() + rn.size() + 256) line.resize(un_ids[i].size() + rn.size() + 256);
+                int n = mq_format_paf(line.data(), line.size(), un_ids[i].c_str(), un_offs[i + 1] - un_offs[i], rn.c_str(), lens2[h2[i].ref_idx], &h2[i]);
+                if (n < 0) die("mq_format_paf failed");
+                line[n] = '\n'; fwrite(line.data(), 1, (size_t)n + 1, rp); rescued++;
+            }
+            mq_destroy(c2);
+        }
+        fclose(rp);
+        printf("Rescued %zu of %zu unmapped reads with k=%ld l=%ld d=%g in %.6fs.\n", rescued, un_ids.size(), k2, l2, d2, secs(t_res));
+    }
     printf("Total execution time: %.6fs\n", secs(t_start));                                                         // main.rs:270
     struct rusage ru; getrusage(RUSAGE_SELF, &ru);
     printf("Maximum RSS: %gGB\n", (double)ru.ru_maxrss * 1024.0 / 1024.0 / 1024.0 / 1024.0);                         // main.rs:271

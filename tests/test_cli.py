@@ -99,3 +99,33 @@ def test_cli_fastq_reads(tmp_path):
     assert r.returncode == 0, r.stderr
     assert "Format: FASTA" in r.stdout            # printed for the reference only
     assert open(str(tmp_path / "fq.paf")).read() == open(os.path.join(GOLD, "config1_default.paf")).read()
+
+
+@pytest.mark.gpu
+def test_cli_rescue_second_pass(tmp_path):
+    # unmapped reads get a second chance with another (k, l, density); the rescue PAF must equal a
+    # direct run with those parameters restricted to the reads the first pass left unmapped
+    import numpy as np
+    from mapquik_b200 import sim
+    g, go, names = sim.genome(77, [400000, 150000])
+    rb, ro, rn, _ = sim.reads(77, g, go, 400, 1500, 600, min_len=300, error_rate=0.04, contig_names=names)
+
+    def fasta(path, ids, buf, offs):
+        with open(path, "wb") as f:
+            for i, n in enumerate(ids):
+                f.write(b">" + n.encode() + b"\n" + buf[int(offs[i]):int(offs[i + 1])].tobytes() + b"\n")
+    ref, reads = str(tmp_path / "ref.fa"), str(tmp_path / "reads.fa")
+    fasta(ref, names, g, go); fasta(reads, rn, rb, ro)
+    r = subprocess.run([ensure_cli(), reads, "--reference", ref, "-p", str(tmp_path / "m"), "--rescue", "3,13,0.08"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    main = open(str(tmp_path / "m.paf")).read().splitlines()
+    resc = open(str(tmp_path / "m.rescue.paf")).read().splitlines()
+    mapped = {ln.split("\t")[0] for ln in main}
+    assert 0 < len(mapped) < 400 and len(resc) > 0 and "Rescued" in r.stdout
+    assert not ({ln.split("\t")[0] for ln in resc} & mapped)
+    r2 = subprocess.run([ensure_cli(), reads, "--reference", ref, "-p", str(tmp_path / "d"), "-k", "3", "-l", "13", "-d", "0.08"],
+                        capture_output=True, text=True)
+    assert r2.returncode == 0, r2.stderr
+    direct = [ln for ln in open(str(tmp_path / "d.paf")).read().splitlines() if ln.split("\t")[0] not in mapped]
+    assert direct == resc
