@@ -19,6 +19,7 @@
 #include <algorithm>
 #include <chrono>
 #include <condition_variable>
+#include <memory>
 #include <mutex>
 #include <thread>
 #include <cstdio>
@@ -31,7 +32,7 @@ namespace {
 
 struct Opt {
     std::string reads, reference, prefix, save_index, load_index, rescue;
-    bool has_prefix = false, debug = false, low_memory = false, nosimd = false, nohpc = false, pfx = false;
+    bool has_prefix = false, debug = false, low_memory = false, nosimd = false, nohpc = false, pfx = false, parse_only = false;
     long k = -1, l = -1, c = -1, s = -1, g = -1, threads = -1, b = -1, q = -1;
     double density = -1;
     int gpu = 0;
@@ -51,17 +52,20 @@ inline void copy_upper(uint8_t *dst, const char *src, size_t n) {
 }
 
 // growable byte buffer in pinned host memory (mq_host_alloc) so that mq_map_batch uploads at full PCIe speed
+bool g_use_pinned = true;        // --parse-only (a host-only self-test) uses plain malloc instead
 struct PinnedBuf {
     uint8_t *p = nullptr; size_t size = 0, cap = 0;
-    ~PinnedBuf() { if (p) mq_host_free(p); }
+    static uint8_t *alloc(size_t n) { return g_use_pinned ? (uint8_t *)mq_host_alloc(n) : (uint8_t *)malloc(n); }
+    static void release(uint8_t *q) { if (g_use_pinned) mq_host_free(q); else free(q); }
+    ~PinnedBuf() { if (p) release(p); }
     void reserve(size_t want) {
         if (want <= cap) return;
         size_t nc = cap ? cap : (64u << 20);
         while (nc < want) nc += nc / 2;
-        uint8_t *np = (uint8_t *)mq_host_alloc(nc);
+        uint8_t *np = alloc(nc);
         if (!np) die("pinned host allocation failed");
         if (size) memcpy(np, p, size);
-        if (p) mq_host_free(p);
+        if (p) release(p);
         p = np; cap = nc;
     }
     void append_upper(const char *src, size_t n) { reserve(size + n); copy_upper(p + size, src, n); size += n; }
@@ -75,6 +79,7 @@ struct Fastx {
     std::vector<char> buf; size_t pos = 0, len = 0; bool eof = false;
     std::string spill;            // storage for a line that straddled a refill
     size_t file_bytes = ~(size_t)0 >> 1;   // on-disk size of a plain file (bounds the batch allocation)
+    bool regular = false;                  // plain regular file with a known size (block-parallel parser)
     bool have_hdr = false; std::string hdr;   // FASTA header already consumed
     Fastx(const std::string &path, bool fasta_) : fasta(fasta_) {
         unsigned char magic[2] = {0, 0};
@@ -88,7 +93,7 @@ struct Fastx {
             fd = -1;
         } else {
             posix_fadvise(fd, 0, 0, POSIX_FADV_SEQUENTIAL);
-            struct stat st; if (fstat(fd, &st) == 0 && st.st_size > 0) file_bytes = (size_t)st.st_size;
+            struct stat st; if (fstat(fd, &st) == 0 && S_ISREG(st.st_mode)) { file_bytes = (size_t)st.st_size; regular = true; }
         }
         buf.resize(32u << 20);
     }
@@ -152,16 +157,152 @@ struct Batch {
 struct BatchQueue {          // single producer / single consumer over two slots
     std::mutex m; std::condition_variable cv; Batch slot[2]; int filled[2] = {0, 0};
 };
+// ---- block-parallel parser for plain (uncompressed) files ---------------------------------------------------
+// The file is consumed in blocks that are cut at record boundaries.  Per block: (1) worker threads index the
+// newlines of their slice, (2) one pass over the line table assembles records and a list of copy jobs,
+// (3) worker threads copy + upper-case the sequence pieces straight into the pinned batch buffer.
+int g_parse_threads = 8;
+template <class Fn> void parallel_for(int n, Fn fn) {
+    if (n <= 1) { if (n == 1) fn(0); return; }
+    std::vector<std::thread> th;
+    for (int t = 1; t < n; t++) th.emplace_back([&fn, t] { fn(t); });
+    fn(0);
+    for (auto &x : th) x.join();
+}
+struct BlockParser {
+    int fd; bool fasta; size_t block_bytes;
+    std::vector<char> raw; size_t fill = 0; bool eof = false;
+    struct Job { size_t src, len, dst; };
+    BlockParser(int fd_, bool fasta_, size_t block_bytes_, size_t file_size_) : fd(fd_), fasta(fasta_), block_bytes(block_bytes_) {
+        raw.resize(block_bytes_); file_size = file_size_;
+    }
+    size_t file_off = 0, file_size = 0;
+    void top_up() {                                   // parallel pread of the next slice of the file
+        if (eof) return;
+        const size_t want = std::min(raw.size() - fill, file_size - file_off);
+        if (want) {
+            const int T = (int)std::max<size_t>(1, std::min<size_t>((size_t)g_parse_threads, want / (8u << 20) + 1));
+            std::vector<int> bad(T, 0);
+            parallel_for(T, [&](int t) {
+                size_t a = want * (size_t)t / T, b = want * (size_t)(t + 1) / T;
+                while (a < b) {
+                    ssize_t r = pread(fd, raw.data() + fill + a, b - a, (off_t)(file_off + a));
+                    if (r <= 0) { bad[t] = 1; break; }
+                    a += (size_t)r;
+                }
+            });
+            for (int x : bad) if (x) die("read error");
+            fill += want; file_off += want;
+        }
+        if (file_off >= file_size) eof = true;
+    }
+    // fills B with the records of the next block; false when the file is exhausted
+    bool next_batch(Batch &B) {
+        B.clear();
+        static const bool timing = getenv("MQ_CLI_TIMING") != nullptr;
+        auto T0 = std::chrono::steady_clock::now();
+        auto lap = [&](const char *what) {
+            if (!timing) return;
+            auto t = std::chrono::steady_clock::now();
+            fprintf(stderr, "[parser] %-8s %.1f ms\n", what, std::chrono::duration<double, std::milli>(t - T0).count());
+            T0 = t;
+        };
+        for (;;) {
+            top_up();
+            lap("read");
+            if (fill == 0) return false;
+            // (1) newline index
+            const int T = (int)std::max<size_t>(1, std::min<size_t>((size_t)g_parse_threads, fill / (4u << 20) + 1));
+            std::vector<std::vector<uint32_t>> nlv(T);
+            parallel_for(T, [&](int t) {
+                size_t a = fill * (size_t)t / T, b = fill * (size_t)(t + 1) / T;
+                const char *p = raw.data() + a, *e = raw.data() + b;
+                auto &v = nlv[t];
+                while (p < e) { const char *q = (const char *)memchr(p, '\n', (size_t)(e - p)); if (!q) break; v.push_back((uint32_t)(q - raw.data())); p = q + 1; }
+            });
+            std::vector<uint32_t> nl;
+            { size_t tot = 0; for (auto &v : nlv) tot += v.size(); nl.reserve(tot + 1); for (auto &v : nlv) nl.insert(nl.end(), v.begin(), v.end()); }
+            lap("newlines");
+            if (eof && (nl.empty() || nl.back() != fill - 1)) nl.push_back((uint32_t)fill);     // last line without '\n'
+            // (2) records
+            std::vector<Job> jobs; size_t consumed = 0, dst = 0;
+            auto line = [&](size_t i, size_t &a, size_t &n) {
+                a = i ? (size_t)nl[i - 1] + 1 : 0; n = (size_t)nl[i] - a;
+                if (n && raw[a + n - 1] == '\r') n--;
+            };
+            if (fasta) {
+                bool open_rec = false; size_t last_hdr = 0;
+                for (size_t i = 0; i < nl.size(); i++) {
+                    size_t a, n; line(i, a, n);
+                    if (n && raw[a] == '>') {
+                        if (open_rec) B.offs.push_back(dst);
+                        B.ids.push_back(Fastx::id_of(raw.data() + a, n)); open_rec = true; last_hdr = a;
+                    } else if (open_rec && n) { jobs.push_back({a, n, dst}); dst += n; }
+                }
+                if (eof) { if (open_rec) B.offs.push_back(dst); consumed = fill; }
+                else if (B.ids.size() >= 2) {          // the last record may continue in the next block: carry it
+                    while (!jobs.empty() && jobs.back().src > last_hdr) { dst -= jobs.back().len; jobs.pop_back(); }
+                    B.ids.pop_back(); consumed = last_hdr;
+                } else { B.clear(); jobs.clear(); dst = 0; }
+            } else {
+                const size_t nrec = nl.size() / 4;
+                for (size_t r = 0; r < nrec; r++) {
+                    size_t a, n; line(4 * r, a, n);
+                    if (!n || raw[a] != '@') die("malformed FASTQ record");
+                    B.ids.push_back(Fastx::id_of(raw.data() + a, n));
+                    line(4 * r + 1, a, n);
+                    if (n) { jobs.push_back({a, n, dst}); dst += n; }
+                    B.offs.push_back(dst);
+                }
+                consumed = nrec ? (size_t)nl[4 * nrec - 1] + 1 : 0;
+                if (eof) consumed = fill;
+            }
+            if (B.ids.empty() && !eof) {                  // not even one complete record in the buffer: enlarge it
+                raw.resize(raw.size() * 2);
+                continue;
+            }
+            lap("records");
+            // (3) copy + upper-case into the pinned batch
+            B.seqs.reserve(dst + 64); B.seqs.size = dst;
+            lap("reserve");
+            if (!jobs.empty()) {
+                const int T2 = (int)std::max<size_t>(1, std::min<size_t>((size_t)g_parse_threads, dst / (4u << 20) + 1));
+                std::vector<size_t> cut(T2 + 1, jobs.size()); cut[0] = 0;
+                { size_t j = 0; for (int t = 1; t < T2; t++) { const size_t want = dst * (size_t)t / T2; while (j < jobs.size() && jobs[j].dst < want) j++; cut[t] = j; } }
+                parallel_for(T2, [&](int t) { for (size_t j = cut[t]; j < cut[t + 1]; j++) copy_upper(B.seqs.p + jobs[j].dst, raw.data() + jobs[j].src, jobs[j].len); });
+            }
+            lap("copy");
+            if (consumed < fill) memmove(raw.data(), raw.data() + consumed, fill - consumed);
+            fill -= consumed;
+            lap("carry");
+            B.last = eof && fill == 0;
+            return true;
+        }
+    }
+};
+
 void reader_thread(Fastx *fx, BatchQueue *q, size_t batch_bytes) {
     int b = 0; std::string id;
+    std::unique_ptr<BlockParser> bp;
+    if (fx->fd >= 0 && fx->regular) {                    // plain regular file: block-parallel path
+        size_t blk = std::min<size_t>(batch_bytes, fx->file_bytes + 1);
+        if (const char *e = getenv("MQ_CLI_BLOCK")) blk = (size_t)atol(e);      // tests: tiny blocks exercise the carry logic
+        bp.reset(new BlockParser(fx->fd, fx->fasta, std::max<size_t>(blk, 64), fx->file_bytes));
+    }
     for (;;) {
         { std::unique_lock<std::mutex> lk(q->m); q->cv.wait(lk, [&] { return !q->filled[b]; }); }
-        Batch &B = q->slot[b]; B.clear();
-        B.seqs.reserve(std::min<size_t>(batch_bytes, fx->file_bytes) + (48u << 20));   // one allocation per slot, no growth copies
+        Batch &B = q->slot[b];
         bool more = true;
-        while (B.seqs.size < batch_bytes) {
-            if (!fx->next(id, B.seqs)) { more = false; break; }
-            B.offs.push_back(B.seqs.size); B.ids.push_back(id);
+        if (bp) {
+            if (!bp->next_batch(B)) { B.clear(); more = false; }
+            else more = !B.last;
+        } else {
+            B.clear();
+            B.seqs.reserve(std::min<size_t>(batch_bytes, fx->file_bytes) + (48u << 20));   // one allocation per slot, no growth copies
+            while (B.seqs.size < batch_bytes) {
+                if (!fx->next(id, B.seqs)) { more = false; break; }
+                B.offs.push_back(B.seqs.size); B.ids.push_back(id);
+            }
         }
         B.last = !more;
         { std::lock_guard<std::mutex> lk(q->m); q->filled[b] = 1; }
@@ -222,12 +363,29 @@ int main(int argc, char **argv) {
         else if (a == "--gpu") o.gpu = atoi(val("gpu").c_str());
         else if (a == "--save-index") o.save_index = val("save-index");      // extensions: the reference has no on-disk index
         else if (a == "--load-index") o.load_index = val("load-index");
+        else if (a == "--parse-only") o.parse_only = true;                  // (testing) parse the reads, print a digest, exit
         else if (a == "--rescue") o.rescue = val("rescue");                  // "k,l,density": second pass over the unmapped reads
         else if (a == "-h" || a == "--help") { printf("mapquik <reads> --reference <ref> [-k -l -d -c -s -g -p --nohpc --threads --gpu]\n"); return 0; }
         else if (!a.empty() && a[0] == '-') die("unknown option " + a);
         else o.reads = a;
     }
     if (o.reads.empty()) die("Please specify an input file.");
+    if (o.threads > 0) g_parse_threads = (int)std::min<long>(o.threads, 64);
+    if (o.parse_only) {
+        g_use_pinned = false;
+        // FNV-1a over "id\n" + sequence + "\n" of every record: identical for every container format / block size
+        uint64_t h = 1469598103934665603ull, nrec = 0, nbase = 0;
+        auto mixb = [&](const uint8_t *p, size_t n) { for (size_t i = 0; i < n; i++) { h ^= p[i]; h *= 1099511628211ull; } };
+        for_each_batch(o.reads, is_fasta_name(o.reads), 256u << 20, [&](Batch &B) {
+            for (size_t i = 0; i < B.ids.size(); i++) {
+                mixb((const uint8_t *)B.ids[i].data(), B.ids[i].size()); mixb((const uint8_t *)"\n", 1);
+                mixb(B.seqs.p + B.offs[i], (size_t)(B.offs[i + 1] - B.offs[i])); mixb((const uint8_t *)"\n", 1);
+                nrec++; nbase += B.offs[i + 1] - B.offs[i];
+            }
+        });
+        printf("records %llu bases %llu digest %016llx\n", (unsigned long long)nrec, (unsigned long long)nbase, (unsigned long long)h);
+        return 0;
+    }
     if (o.reference.empty() && o.load_index.empty()) die("Please specify a reference file.");
     long k = 5, l = 31, c = 4, s = 11, g = 2000, b = 1, q = 200;
     double density = 0.01;

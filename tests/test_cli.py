@@ -129,3 +129,49 @@ def test_cli_rescue_second_pass(tmp_path):
     assert r2.returncode == 0, r2.stderr
     direct = [ln for ln in open(str(tmp_path / "d.paf")).read().splitlines() if ln.split("\t")[0] not in mapped]
     assert direct == resc
+
+
+def _digest(path, env=None, threads=None):
+    cmd = [ensure_cli(), str(path), "--parse-only"] + (["--threads", str(threads)] if threads else [])
+    e = dict(os.environ); e.update(env or {})
+    r = subprocess.run(cmd, capture_output=True, text=True, env=e)
+    assert r.returncode == 0, r.stderr
+    return r.stdout.strip()
+
+
+def test_parser_paths_agree(tmp_path):
+    # the block-parallel parser (plain files), the serial zlib reader (gz) and every block size / thread count must
+    # hand the library exactly the same records: single-line and multi-line FASTA, CRLF, no final newline, FASTQ
+    import numpy as np
+    rng = np.random.default_rng(5)
+    recs = []
+    for i in range(300):
+        n = int(rng.choice([0, 1, 59, 60, 61, 500, 5000, 40000]))
+        s = np.frombuffer(b"ACGTacgtN", np.uint8)[rng.integers(0, 9, n)].tobytes()
+        recs.append((f"r{i} desc {i}".encode(), s))
+    def fasta(width=None, eol=b"\n", final=True):
+        out = []
+        for h, s in recs:
+            out.append(b">" + h + eol)
+            if width is None:
+                out.append(s + eol)
+            else:
+                out += [s[j:j + width] + eol for j in range(0, len(s), width)] or []
+        data = b"".join(out)
+        return data if final else data[:-len(eol)]
+    fq = b"".join(b"@" + h + b"\n" + s + b"\n+\n" + (b"@" * len(s)) + b"\n" for h, s in recs)     # '@' qualities on purpose
+    files = {"a.fa": fasta(), "b.fa": fasta(60), "c.fa": fasta(60, b"\r\n"), "d.fa": fasta(None, b"\n", final=False),
+             "e.fastq": fq, "f.fastq": fq[:-1]}
+    digests = {}
+    for name, data in files.items():
+        (tmp_path / name).write_bytes(data)
+        with gzip.open(tmp_path / (name + ".gz"), "wb") as f:
+            f.write(data)
+        plain = _digest(tmp_path / name)
+        assert plain == _digest(tmp_path / (name + ".gz")), name                       # parallel == serial zlib path
+        for blk, th in (("64", 1), ("1000", 3), ("70000", 8), ("5000000", 2)):
+            assert _digest(tmp_path / name, {"MQ_CLI_BLOCK": blk}, th) == plain, (name, blk, th)
+        digests[name] = plain
+    assert len(set(digests.values())) == 1                                             # same records in every container
+    n_bases = sum(len(s) for _, s in recs)
+    assert digests["a.fa"].startswith(f"records 300 bases {n_bases} ")
