@@ -160,6 +160,8 @@ int mq_matches(mq_ctx *, const uint8_t *seqs, const uint64_t *offs, uint32_t n, 
 /* device time of the stages of the last mq_index_* / mq_map_* call, CUDA events on the ctx stream.
  * names: "h2d","scan","scan_kernel" (k_scan_minimizers alone, also inside "scan"),"gather","insert","probe","chain","d2h","total".  Returns ms or <0. */
 double mq_last_ms(mq_ctx *, const char *stage);
+/* the same stages accumulated over all calls since mq_create */
+double mq_total_ms(mq_ctx *, const char *stage);
 /* number of kernels this library launched on this ctx since creation */
 uint64_t mq_launch_count(mq_ctx *);
 void *mq_stream(mq_ctx *);                /* cudaStream_t the kernels run on */

@@ -32,7 +32,7 @@ EXPORTS = ["mq_create", "mq_destroy", "mq_strerror", "mq_last_error", "mq_abi_ve
            "mq_format_paf", "mq_minimizers", "mq_kminmers", "mq_index_get", "mq_matches", "mq_last_ms",
            "mq_launch_count", "mq_stream", "mq_sync", "mq_table_bytes", "mq_table_slots", "mq_scan_kernel_launches",
            "mq_minimizer_count", "mq_dev_alloc", "mq_dev_free", "mq_dev_upload", "mq_dev_download", "mq_dev_memset",
-           "mq_region_begin", "mq_region_end_ms", "mq_index_save", "mq_index_load"]
+           "mq_region_begin", "mq_region_end_ms", "mq_index_save", "mq_index_load", "mq_total_ms"]
 
 _lib = None
 
@@ -88,6 +88,7 @@ def lib():
     L.mq_dev_memset.restype = C.c_int; L.mq_dev_memset.argtypes = [vp, vp, C.c_int, C.c_size_t]
     L.mq_region_begin.restype = C.c_int; L.mq_region_begin.argtypes = [vp]
     L.mq_region_end_ms.restype = C.c_double; L.mq_region_end_ms.argtypes = [vp]
+    L.mq_total_ms.restype = C.c_double; L.mq_total_ms.argtypes = [vp, C.c_char_p]
     L.mq_index_save.restype = C.c_int; L.mq_index_save.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_uint64]
     L.mq_index_load.restype = C.c_int
     L.mq_index_load.argtypes = [vp, C.c_char_p, vp, C.c_uint32, C.POINTER(C.c_uint32), vp, C.c_uint64, u64p, u64p]

@@ -64,8 +64,10 @@ struct mq_ctx {
     DBuf d_seqs2[2], d_offs2[2];
     void *h_offs2[2] = {nullptr, nullptr}; size_t h_offs2_cap[2] = {0, 0};
     // timings
-    std::map<std::string, float> ms;
-    std::vector<std::pair<std::string, std::pair<cudaEvent_t, cudaEvent_t>>> pending;
+    std::map<std::string, float> ms, ms_total;
+    uint64_t timer_gen = 0;
+    struct PendingTimer { std::string name; cudaEvent_t a, b; uint64_t gen; };
+    std::vector<PendingTimer> pending;
     std::vector<cudaEvent_t> ev_pool;
 };
 
@@ -128,14 +130,17 @@ struct StageTimer {
     StageTimer(mq_ctx *c_, const char *n, cudaStream_t s_ = nullptr) : c(c_), name(n), st(s_ ? s_ : c_->stream) {
         a = get_event(c); b = get_event(c); cudaEventRecord(a, st);
     }
-    ~StageTimer() { cudaEventRecord(b, st); c->pending.push_back({name, {a, b}}); }
+    ~StageTimer() { cudaEventRecord(b, st); c->pending.push_back({name, a, b, c->timer_gen}); }
 };
-void timers_reset(mq_ctx *c) { c->ms.clear(); }
+// a new call starts a new generation: per-call figures (mq_last_ms) restart, running totals (mq_total_ms) keep
+// accumulating; nothing is synchronised here
+void timers_reset(mq_ctx *c) { c->ms.clear(); c->timer_gen++; }
 void timers_collect(mq_ctx *c) {
     for (auto &pr : c->pending) {
-        float t = 0; cudaEventSynchronize(pr.second.second); cudaEventElapsedTime(&t, pr.second.first, pr.second.second);
-        c->ms[pr.first] += t;
-        c->ev_pool.push_back(pr.second.first); c->ev_pool.push_back(pr.second.second);
+        float t = 0; cudaEventSynchronize(pr.b); cudaEventElapsedTime(&t, pr.a, pr.b);
+        if (pr.gen == c->timer_gen) c->ms[pr.name] += t;
+        c->ms_total[pr.name] += t;
+        c->ev_pool.push_back(pr.a); c->ev_pool.push_back(pr.b);
     }
     c->pending.clear();
 }
@@ -450,6 +455,12 @@ void mq_host_free(void *p) { if (p) cudaFreeHost(p); }
 void *mq_stream(mq_ctx *c) { return c ? (void *)c->stream : nullptr; }
 int mq_sync(mq_ctx *c) { if (!c) return MQ_ERR_ARG; cudaSetDevice(c->device); CK(cudaStreamSynchronize(c->stream)); timers_collect(c); return MQ_OK; }
 uint64_t mq_launch_count(mq_ctx *c) { return c ? c->launches : 0; }
+double mq_total_ms(mq_ctx *c, const char *stage) {
+    if (!c || !stage) return -1.0;
+    timers_collect(c);
+    auto it = c->ms_total.find(stage);
+    return it == c->ms_total.end() ? 0.0 : it->second;
+}
 double mq_last_ms(mq_ctx *c, const char *stage) {
     if (!c || !stage) return -1.0;
     timers_collect(c);

@@ -243,6 +243,9 @@ class Index:
     def last_ms(self, stage="total"):
         return self._L.mq_last_ms(self._h, stage.encode())
 
+    def total_ms(self, stage):
+        return self._L.mq_total_ms(self._h, stage.encode())
+
     def launch_count(self):
         return self._L.mq_launch_count(self._h)
 
