@@ -261,8 +261,8 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) k_scan_minimizers(ScanArgs a,
         const uint64_t gs = a.offs[sq], ge = a.offs[sq + 1];
         const uint64_t A = gs & ~3ull;
         const uint32_t ft = a.first_tile[sq], nt = a.first_tile[sq + 1] - ft, ti = tile - ft;
-        const uint64_t span = ge - A;
-        uint32_t Cs = (uint32_t)((span + 32ull * nt - 1) / (32ull * nt));
+        const uint32_t span = (uint32_t)(ge - A), dv = 32u * nt;
+        uint32_t Cs = (span + dv - 1) / dv;
         Cs = (Cs + 7u) & ~7u;                                   // multiple of 8 => odd word stride with the pad
         const uint32_t TWs = 32u * Cs, stride = Cs + LANE_PAD;
         const uint64_t tlo = A + (uint64_t)ti * TWs;            // aligned address of x' = 0
@@ -436,8 +436,8 @@ __device__ __forceinline__ void tile_origin(const GatherArgs &g, uint32_t tile, 
     const uint64_t am = (uint64_t)g.grid_align - 1;
     uint64_t gs = g.offs[sq], ge = g.offs[sq + 1], A = gs & ~am;
     uint32_t ft = g.first_tile[sq], nt = g.first_tile[sq + 1] - ft, ti = tile - ft;
-    uint64_t span = ge - A;
-    uint32_t Cs = (uint32_t)((span + 32ull * nt - 1) / (32ull * nt));
+    const uint32_t span = (uint32_t)(ge - A), dv = 32u * nt;
+    uint32_t Cs = (span + dv - 1) / dv;
     const uint32_t cm = g.grid_align == 16 ? 15u : 7u;
     Cs = (Cs + cm) & ~cm;
     uint64_t tlo = A + (uint64_t)ti * 32u * Cs;

@@ -52,8 +52,9 @@ __global__ void k_tiles_per_seq_v2(const uint64_t *offs, uint32_t n, uint32_t mi
 }
 
 __device__ __forceinline__ void v2_geometry(uint64_t gs, uint64_t ge, uint32_t nt, uint32_t ti, uint32_t *Cs, uint64_t *tlo) {
-    const uint64_t A = gs & ~15ull, span = ge - A;
-    uint32_t c = (uint32_t)((span + 32ull * nt - 1) / (32ull * nt));
+    const uint64_t A = gs & ~15ull;
+    const uint32_t span = (uint32_t)(ge - A), d = 32u * nt;     // records are < 2^31 bases: 32-bit division is exact
+    uint32_t c = (span + d - 1) / d;
     c = (c + 15u) & ~15u;
     *Cs = c; *tlo = A + (uint64_t)ti * 32u * c;
 }
