@@ -502,6 +502,42 @@ __device__ __forceinline__ uint64_t kminmer_hash(const uint64_t *h, uint32_t k, 
     return x;
 }
 
+// the same with k known at compile time: the window stays in registers (no local-memory array)
+template <int K> __device__ __forceinline__ uint64_t kminmer_hash_k(const uint64_t *__restrict__ g, uint32_t *rev_out) {
+    uint64_t h[K];
+#pragma unroll
+    for (int i = 0; i < K; i++) h[i] = __ldg(g + i);
+    uint32_t rev = 0; bool decided = false;
+#pragma unroll
+    for (int i = 0; i < K / 2; i++) {
+        const uint64_t a = h[i], b = h[K - 1 - i];
+        if (!decided && a != b) { rev = a > b; decided = true; }
+    }
+    uint64_t x = 0x9E3779B97F4A7C15ull ^ (uint64_t)K;
+#pragma unroll
+    for (int i = 0; i < K; i++) x = mix64(x ^ (rev ? h[K - 1 - i] : h[i]));
+    *rev_out = rev;
+    return x;
+}
+// k-min-mer hash of the window starting at g (global memory); k <= 8 takes the register path
+__device__ __forceinline__ uint64_t kminmer_hash_at(const uint64_t *__restrict__ g, uint32_t k, uint32_t *rev_out) {
+    switch (k) {
+        case 1: return kminmer_hash_k<1>(g, rev_out);
+        case 2: return kminmer_hash_k<2>(g, rev_out);
+        case 3: return kminmer_hash_k<3>(g, rev_out);
+        case 4: return kminmer_hash_k<4>(g, rev_out);
+        case 5: return kminmer_hash_k<5>(g, rev_out);
+        case 6: return kminmer_hash_k<6>(g, rev_out);
+        case 7: return kminmer_hash_k<7>(g, rev_out);
+        case 8: return kminmer_hash_k<8>(g, rev_out);
+        default: {
+            uint64_t h[MQ_MAX_K_];
+            for (uint32_t i = 0; i < k; i++) h[i] = __ldg(g + i);
+            return kminmer_hash(h, k, rev_out);
+        }
+    }
+}
+
 // records (for the index) are runs [rec_off[r], rec_off[r+1]) of the minimizer store
 __device__ __forceinline__ uint32_t find_rec(const uint32_t *rec_off, uint32_t n_rec, uint32_t j) {
     uint32_t lo = 0, hi = n_rec;
@@ -563,9 +599,7 @@ __global__ void __launch_bounds__(256) k_insert_kminmers(KminmerArgs a, Table t,
     uint32_t r = find_rec(a.rec_off, a.n_rec, j);
     uint32_t r0 = a.rec_off[r], r1 = a.rec_off[r + 1];
     if (j + a.k > r1) return;
-    uint64_t h[MQ_MAX_K_];
-    for (uint32_t i = 0; i < a.k; i++) h[i] = a.hash[j + i];
-    uint32_t rev; uint64_t key = kminmer_hash(h, a.k, &rev);
+    uint32_t rev; uint64_t key = kminmer_hash_at(a.hash + j, a.k, &rev);
     uint32_t start = a.pos[j], end = a.pos[j + a.k - 1] + a.l, off = j - r0;
     if (do_insert) table_insert(t, key, a.rec_id ? a.rec_id[r] : r, start, end, (off << 1) | rev);
     if (a.t_hash) {
@@ -639,9 +673,7 @@ __global__ void __launch_bounds__(128) k_probe_match(ProbeArgs a, Table t) {
             bool hit = false; Entry e; e.id = e.start = e.end = e.offrc = 0;
             uint32_t qstart = 0, qend = 0, qrev = 0;
             if (j < Q) {
-                uint64_t h[MQ_MAX_K_];
-                for (uint32_t i = 0; i < a.k; i++) h[i] = __ldg(a.hash + m0 + j + i);
-                uint64_t key = kminmer_hash(h, a.k, &qrev);
+                uint64_t key = kminmer_hash_at(a.hash + m0 + j, a.k, &qrev);
                 qstart = __ldg(a.pos + m0 + j); qend = __ldg(a.pos + m0 + j + a.k - 1) + a.l;
                 hit = table_get(t, key, &e);
             }
