@@ -775,7 +775,67 @@ struct ChainArgs {
     uint32_t n_reads, c, s, g;
     HitRec *hits;
     uint32_t *read_ticket;
+    uint32_t *big_list;        // reads with more than CHAIN_SMALL matches, filled by k_chain_small, drained by k_chain
+    uint32_t *big_count;
 };
+constexpr uint32_t CHAIN_SMALL = 12;
+
+// find_coords (mers.rs:131-179, wrapping usize arithmetic) + the mq_hit record
+__device__ __forceinline__ void write_hit(const ChainArgs &a, uint32_t r, bool ok, uint32_t b_ref, uint32_t b_rc, uint32_t b_mapq,
+                                          uint64_t b_qs, uint64_t b_qe, uint64_t b_rs, uint64_t b_re, uint64_t best_score) {
+    HitRec h; h.mapped = 0; h.rc = 0; h.mapq = 0; h.pad_ = 0; h.ref_idx = 0; h.q_start = h.q_end = h.r_start = h.r_end = h.score = 0;
+    if (ok && b_ref < a.n_refs) {
+        const uint64_t q_len = a.offs[r + 1] - a.offs[r], r_len = a.ref_lens[b_ref];
+        const uint64_t tail = q_len - b_qe - 1;
+        uint64_t frs, fre, exs, exe;
+        if (!b_rc) {
+            if (b_rs >= b_qs) { frs = b_rs - b_qs; exs = b_qs; } else { frs = 0; exs = b_rs; }
+            if (b_re + tail <= r_len - 1) { fre = b_re + tail; exe = tail; } else { fre = r_len - 1; exe = r_len - b_re - 1; }
+        } else {
+            if (b_re + b_qs <= r_len - 1) { fre = b_re + b_qs; exs = b_qs; } else { fre = r_len - 1; exs = r_len - b_re - 1; }
+            if (b_rs >= tail) { frs = b_rs - tail; exe = tail; } else { frs = 0; exe = b_rs; }
+        }
+        h.mapped = 1; h.rc = (uint8_t)b_rc; h.mapq = (uint8_t)b_mapq; h.ref_idx = b_ref;
+        h.q_start = b_qs - exs; h.q_end = b_qe + exe; h.r_start = frs; h.r_end = fre; h.score = best_score;
+    }
+    a.hits[r] = h;
+}
+
+// thread per read: almost every read has a handful of Matches, for which a warp per read wastes 31 lanes.
+// Reads with more than CHAIN_SMALL Matches are queued for the warp-per-read kernel below.
+__global__ void __launch_bounds__(128) k_chain_small(ChainArgs a) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= a.n_reads) return;
+    const uint32_t n = a.n_matches[r];
+    if (n > CHAIN_SMALL) { a.big_list[atomicAdd(a.big_count, 1u)] = r; return; }
+    const MatchRec *ms = a.matches + a.seq_off[r];
+    M6 m[CHAIN_SMALL];
+    for (uint32_t i = 0; i < n; i++) m[i] = load_match(ms + i);
+    uint64_t best_score = 0, second = 0; uint32_t groups = 0;
+    uint32_t b_ref = 0, b_rc = 0, b_mapq = 0; uint64_t b_qs = 0, b_qe = 0, b_rs = 0, b_re = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        const uint32_t ref = m[i].ref;
+        bool seen = false;
+        for (uint32_t q = 0; q < i; q++) seen |= m[q].ref == ref;
+        if (seen) continue;                                             // not the first Match of its reference
+        uint32_t bc = 0, bi = i, glen = 0;                              // C1: first Match with the strictly greatest count
+        for (uint32_t q = i; q < n; q++) if (m[q].ref == ref) { glen++; if (m[q].cnt > bc) { bc = m[q].cnt; bi = q; } }
+        uint32_t lenf = 0, fi = 0, li = 0; uint64_t score = 0;         // C3: keep what is compatible with the largest
+        for (uint32_t q = i; q < n; q++)
+            if (m[q].ref == ref && (glen <= 1 || compatible(m[bi], m[q], a.g))) { if (!lenf) fi = q; li = q; lenf++; score += m[q].cnt; }
+        if (!lenf) continue;
+        const uint32_t mapq = ((a.s != 0 && a.c != 0) && (lenf >= a.c || score >= a.s)) ? 60u : 0u;          // C4
+        const uint32_t rc = m[fi].rc;
+        const uint64_t qs = m[fi].qs, qe = (uint64_t)m[li].qe - 1;
+        uint64_t rs, re;
+        if (rc && lenf > 1) { rs = m[li].rs; re = (uint64_t)m[fi].re - 1; } else { rs = m[fi].rs; re = (uint64_t)m[li].re - 1; }
+        groups++;
+        if (score > best_score) { second = best_score; best_score = score; b_ref = ref; b_rc = rc; b_mapq = mapq; b_qs = qs; b_qe = qe; b_rs = rs; b_re = re; }
+        else if (score > second) second = score;
+    }
+    write_hit(a, r, groups == 1 || (groups > 1 && best_score != second), b_ref, b_rc, b_mapq, b_qs, b_qe, b_rs, b_re, best_score);
+}
+
 
 __global__ void __launch_bounds__(128) k_chain(ChainArgs a) {
     const uint32_t lane = lane_id();
@@ -783,7 +843,8 @@ __global__ void __launch_bounds__(128) k_chain(ChainArgs a) {
         uint32_t r = 0;
         if (lane == 0) r = atomicAdd(a.read_ticket, 1u);
         r = __shfl_sync(0xffffffffu, r, 0);
-        if (r >= a.n_reads) break;
+        if (a.big_list) { if (r >= *a.big_count) break; r = a.big_list[r]; }      // only the reads k_chain_small queued
+        else if (r >= a.n_reads) break;
         const uint32_t n = a.n_matches[r];
         const MatchRec *ms = a.matches + a.seq_off[r];
         // best / second-best chain score over references (mers.rs:110-129)
@@ -830,26 +891,8 @@ __global__ void __launch_bounds__(128) k_chain(ChainArgs a) {
                 b_ref = ref; b_rc = rc; b_mapq = mapq; b_qs = qs; b_qe = qe; b_rs = rs; b_re = re;
             } else if (score > second) second = score;
         }
-        if (lane == 0) {
-            HitRec h; h.mapped = 0; h.rc = 0; h.mapq = 0; h.pad_ = 0; h.ref_idx = 0; h.q_start = h.q_end = h.r_start = h.r_end = h.score = 0;
-            const bool ok = groups == 1 || (groups > 1 && best_score != second);       // tie for the max => unmapped (mers.rs:106)
-            if (ok && b_ref < a.n_refs) {
-                // find_coords, mers.rs:131-179 (usize arithmetic, wrapping)
-                const uint64_t q_len = a.offs[r + 1] - a.offs[r], r_len = a.ref_lens[b_ref];
-                const uint64_t tail = q_len - b_qe - 1;
-                uint64_t frs, fre, exs, exe;
-                if (!b_rc) {
-                    if (b_rs >= b_qs) { frs = b_rs - b_qs; exs = b_qs; } else { frs = 0; exs = b_rs; }
-                    if (b_re + tail <= r_len - 1) { fre = b_re + tail; exe = tail; } else { fre = r_len - 1; exe = r_len - b_re - 1; }
-                } else {
-                    if (b_re + b_qs <= r_len - 1) { fre = b_re + b_qs; exs = b_qs; } else { fre = r_len - 1; exs = r_len - b_re - 1; }
-                    if (b_rs >= tail) { frs = b_rs - tail; exe = tail; } else { frs = 0; exe = b_rs; }
-                }
-                h.mapped = 1; h.rc = (uint8_t)b_rc; h.mapq = (uint8_t)b_mapq; h.ref_idx = b_ref;
-                h.q_start = b_qs - exs; h.q_end = b_qe + exe; h.r_start = frs; h.r_end = fre; h.score = best_score;
-            }
-            a.hits[r] = h;
-        }
+        if (lane == 0)      // tie for the max => unmapped (mers.rs:106)
+            write_hit(a, r, groups == 1 || (groups > 1 && best_score != second), b_ref, b_rc, b_mapq, b_qs, b_qe, b_rs, b_re, best_score);
         __syncwarp();
     }
 }

@@ -48,7 +48,7 @@ struct mq_ctx {
     // per-batch workspace
     DBuf d_seqs, d_offs, d_first_tile, d_tile_seq, d_ev_hash, d_ev_meta, d_lane_cnt, d_tile_cnt, d_blocksums,
          d_scalars, d_ovf_tile, d_ovf_meta, d_ovf_hash, d_pos, d_hash, d_seq_off, d_matches, d_nmatch, d_hits,
-         d_pos_base, d_emit_len, d_misc;
+         d_pos_base, d_emit_len, d_misc, d_big_list;
     uint32_t ovf_cap = 1u << 16;
     // minimizer store (reference side)
     DBuf st_pos, st_hash; uint64_t st_n = 0;
@@ -356,6 +356,7 @@ int map_device(mq_ctx *c, const uint8_t *d_seqs, const uint64_t *d_offs, uint32_
     if ((rc = run_scan(c, d_seqs, d_offs, n, c->p.l + c->p.k - 1, nullptr, nullptr, &M))) return rc;
     if ((rc = ensure(c, c->d_matches, (M + 64) * sizeof(MatchRec)))) return rc;
     if ((rc = ensure(c, c->d_nmatch, ((size_t)n + 1) * 4))) return rc;
+    if ((rc = ensure(c, c->d_big_list, ((size_t)n + 2) * 4))) return rc;
     uint32_t *tickets = (uint32_t *)(c->d_scalars.as<uint64_t>() + SC_TICKET);
     Table t{c->d_table.as<Slot>(), c->tmask};
     {
@@ -376,9 +377,13 @@ int map_device(mq_ctx *c, const uint8_t *d_seqs, const uint64_t *d_offs, uint32_
         a.matches = c->d_matches.as<MatchRec>(); a.n_matches = c->d_nmatch.as<uint32_t>(); a.seq_off = c->d_seq_off.as<uint32_t>();
         a.offs = d_offs; a.ref_lens = c->d_ref_lens.as<uint64_t>(); a.n_refs = c->n_refs; a.n_reads = n;
         a.c = c->p.c; a.s = c->p.s; a.g = c->p.g; a.hits = d_hits; a.read_ticket = tickets + 1;
-        const uint32_t grid = std::min<uint32_t>((n + 3) / 4, (uint32_t)c->n_sm * 16);
+        // thread per read for the usual handful of Matches; reads with many Matches are queued for the warp kernel
+        a.big_list = c->d_big_list.as<uint32_t>(); a.big_count = c->d_big_list.as<uint32_t>() + n;
+        CK(cudaMemsetAsync(a.big_count, 0, 4, c->stream));
+        k_chain_small<<<(n + 127) / 128, 128, 0, c->stream>>>(a);
+        const uint32_t grid = std::min<uint32_t>((n + 3) / 4, (uint32_t)c->n_sm * 8);
         k_chain<<<grid, 128, 0, c->stream>>>(a);
-        c->launches++;
+        c->launches += 2;
         CK(cudaGetLastError());
     }
     return MQ_OK;
@@ -433,7 +438,7 @@ void mq_destroy(mq_ctx *c) {
     timers_collect(c);
     DBuf *bufs[] = {&c->d_seqs, &c->d_offs, &c->d_first_tile, &c->d_tile_seq, &c->d_ev_hash, &c->d_ev_meta, &c->d_lane_cnt,
                     &c->d_tile_cnt, &c->d_blocksums, &c->d_scalars, &c->d_ovf_tile, &c->d_ovf_meta, &c->d_ovf_hash, &c->d_pos,
-                    &c->d_hash, &c->d_seq_off, &c->d_matches, &c->d_nmatch, &c->d_hits, &c->d_pos_base, &c->d_emit_len,
+                    &c->d_hash, &c->d_seq_off, &c->d_matches, &c->d_nmatch, &c->d_hits, &c->d_pos_base, &c->d_emit_len, &c->d_big_list,
                     &c->d_misc, &c->st_pos, &c->st_hash, &c->d_table, &c->d_ref_lens};
     for (DBuf *b : bufs) dfree(*b);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
