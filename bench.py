@@ -40,6 +40,9 @@ WORKLOAD = "ecoli_4.64Mbp_x_100k_hifi_reads_10kb_99.5pct (BASELINE configs[1])"
 
 def make_workload(rank, n_reads):
     from mapquik_b200 import sim
+    if os.environ.get("OMP_NUM_THREADS") == "1" and int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        # torchrun pins OpenMP to one thread per rank; the (untimed) read simulator may use a fair share of the host
+        os.environ["OMP_NUM_THREADS"] = str(max(1, host_threads() // int(os.environ["WORLD_SIZE"])))
     g, go, names = sim.genome(SEED, [GENOME_LEN], names=["chr000913"])
     rb, ro, _, _ = sim.reads(SEED, g, go, n_reads, READ_MEAN, READ_SD, READ_MIN, READ_ERR, first=rank * n_reads,
                              with_names=False)
@@ -104,6 +107,14 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def host_threads():
+    """all host threads this process may use (torchrun exports OMP_NUM_THREADS=1, which must not shrink the CPU arm)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
 def scan_traffic(n_reads):
     """dram__bytes_read.sum + dram__bytes_write.sum of one k_scan_minimizers_v2 launch on the default
     workload, from the committed `ncu --set full` capture (profiles/scan_traffic.json); null otherwise."""
@@ -139,7 +150,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     from oracle import pyoracle as O
-    threads = O.lib().orc_max_threads()
+    threads = host_threads()
     n_sample = 25000
     g, go, names, rb, ro = make_workload(0, n_sample)
     rps, bps, t_index, dt, mapped, n_unique = cpu_oracle_run(g, go, names, rb, ro, n_sample, args.steps, args.warmup, threads)
@@ -353,8 +364,7 @@ def main():
             "clocks": clk,
         }
         if world == 1 and not args.no_cpu_baseline:
-            from oracle import pyoracle as O
-            threads = O.lib().orc_max_threads()
+            threads = host_threads()
             n_sample = min(25000, n_reads)
             rps, bps, t_index, dt, mapped, _ = cpu_oracle_run(g, go, names, rb, ro, n_sample, 2, 1, threads)
             line["cpu_baseline"] = {"value": rps, "unit": "reads/s", "cores": threads, "kind": "port",
