@@ -426,3 +426,60 @@ def test_hits_fuzz_small_genomes(seed):
     compare_matches(ix, oix, rb, ro)
     compare_hits(ix, oix, rb, ro, rn)
     ix.close()
+
+
+def test_match_quirks_on_crafted_index():
+    """The Match::check precedence quirk (match.rs:39-43) on the GPU: a forward Match extends on `offset + 1` alone,
+    across reference ids and through reverse-oriented hits.  Real sequence cannot be made to hit that on demand, so
+    the reference side is crafted: minimizer stores spliced from the read's own minimizers are imported with
+    mq_store_import, and the oracle index gets the same k-min-mers tuple by tuple."""
+    rng = np.random.default_rng(4242)
+    p = Params(k=5, l=31, density=0.02)
+    k, l = p.k, p.l
+    read = random_dna(rng, 30000)
+    ro = np.array([0, read.size], np.uint64)
+    probe = Index(p)
+    _, rpos, rh = probe.minimizers(read, ro)
+    probe.close()
+    M = len(rh)
+    assert M > 120
+    fill = lambda n: rng.integers(1, 2**62, n).astype(np.uint64)
+    recs = []            # per reference record: (hash list, position list)
+    # ref0: read minimizers [0, 20+k-1)  -> query windows 0..19 hit ref0 at offsets 0..19 (forward)
+    # ref1: 20 fillers + read minimizers [20, 45+k-1) -> windows 20..44 hit ref1 at offsets 20..44: the forward Match
+    #       of ref0 keeps extending although the reference id changes
+    # ref2: 45 fillers + reversed(read minimizers [45, 45+k)) -> window 45 hits ref2 at offset 45 in REVERSE orientation:
+    #       still extends the forward Match (strand is not compared either)
+    # ref3: reversed(read minimizers [60, 90+k-1)) -> windows 60..89 hit with decreasing offsets: a genuine rc Match
+    # ref4: 7 fillers + reversed(read minimizers [100, 100+k)) ; ref5: reversed(read minimizers [101, 101+k)) -> two rc
+    #       hits with offsets 7 and 0 on different references: an rc Match must NOT extend across references
+    recs.append(rh[0:20 + k - 1])
+    recs.append(np.concatenate([fill(20), rh[20:45 + k - 1]]))
+    recs.append(np.concatenate([fill(45), rh[45:45 + k][::-1]]))
+    recs.append(rh[60:90 + k - 1][::-1].copy())
+    recs.append(np.concatenate([fill(7), rh[100:100 + k][::-1]]))
+    recs.append(rh[101:101 + k][::-1].copy())
+    ix = Index(p)
+    oix = O.Index(oparams(p))
+    pos_all, hash_all, directory, lens = [], [], [], []
+    for rid, hs in enumerate(recs):
+        pos = (np.arange(len(hs), dtype=np.uint32) * 97 + 11)
+        pos_all.append(pos); hash_all.append(hs); directory.append((rid, 0, len(hs)))
+        lens.append(int(pos[-1]) + 5000)
+        for j in range(len(hs) - k + 1):
+            kh, rev = O.kminmer_hash(hs[j:j + k])
+            oix.add_tuple(kh, rid, int(pos[j]), int(pos[j + k - 1]) + l, j, rev)
+    pos_all = np.ascontiguousarray(np.concatenate(pos_all)); hash_all = np.ascontiguousarray(np.concatenate(hash_all))
+    ix.store_import(pos_all.ctypes.data, hash_all.ctypes.data, len(pos_all), np.array(directory, np.uint64))
+    ix.freeze({i: (f"ref{i}", lens[i]) for i in range(len(recs))})
+    oix.ref_names = [f"ref{i}" for i in range(len(recs))]; oix.ref_lens = lens
+    assert ix.n_unique == oix.count() and ix.n_keys == oix.slots()
+    compare_matches(ix, oix, read, ro)
+    compare_hits(ix, oix, read, ro, ["crafted"])
+    mo, f = ix.matches(read, ro)
+    counts = f[:, 4].tolist(); refrc = f[:, 5].tolist()
+    assert 46 in counts                                   # windows 0..45 form ONE forward Match across ref0/ref1/ref2 (the quirk)
+    assert refrc[counts.index(46)] == (0 << 1 | 0)        # filed under the head's reference id, forward
+    assert 30 in counts and refrc[counts.index(30)] == (3 << 1 | 1)      # the genuine rc Match on ref3
+    assert counts.count(1) >= 2                           # windows 100 and 101: rc hits on different references stay apart
+    ix.close()
