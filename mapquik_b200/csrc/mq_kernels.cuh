@@ -637,13 +637,6 @@ __global__ void k_index_get(Table t, const uint64_t *keys, uint64_t n, uint8_t *
 // ------------------------------------------------------------------------------------------------
 // per-read probe + Match segmentation (warp per read)
 // ------------------------------------------------------------------------------------------------
-// Transition functions of the 3-state automaton {0: closed, 1: open forward Match, 2: open rc
-// Match} are packed as 2 bits per source state: f = f(0) | f(1)<<2 | f(2)<<4.
-__device__ __forceinline__ uint32_t tf_apply(uint32_t f, uint32_t s) { return (f >> (2 * s)) & 3u; }
-__device__ __forceinline__ uint32_t tf_compose(uint32_t first, uint32_t then) {   // then(first(s))
-    return tf_apply(then, tf_apply(first, 0)) | (tf_apply(then, tf_apply(first, 1)) << 2) | (tf_apply(then, tf_apply(first, 2)) << 4);
-}
-
 struct ProbeArgs {
     const uint32_t *pos; const uint64_t *hash;     // minimizers of the batch
     const uint32_t *seq_off;                       // n+1 : minimizer range of each read
@@ -685,19 +678,20 @@ __global__ void __launch_bounds__(128) k_probe_match(ProbeArgs a, Table t) {
             // match.rs:39-43 with Rust precedence: rc Match: same ref && q.rev!=r.rc && p.off-r.off==1 ; fwd Match: r.off-p.off==1
             const bool fl = hit && p_hit && (off - p_off == 1u);
             const bool rl = hit && p_hit && (e.id == p_id) && rc && (p_off - off == 1u);
-            const uint32_t Hs = rc ? 2u : 1u;
-            uint32_t f = !hit ? 0u : (Hs | ((fl ? 1u : Hs) << 2) | ((rl ? 2u : Hs) << 4));
-            // inclusive scan of transition functions
-            uint32_t sc = f;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, sc, d); if (lane >= (uint32_t)d) sc = tf_compose(y, sc); }
-            const uint32_t s_after = tf_apply(sc, s_in);
-            uint32_t s_before = __shfl_up_sync(0xffffffffu, s_after, 1);
-            if (lane == 0) s_before = s_in;
-            const bool ext = hit && ((s_before == 1 && fl) || (s_before == 2 && rl));
-            const bool head = hit && !ext;
-            const uint32_t Hm = __ballot_sync(0xffffffffu, head), Em = __ballot_sync(0xffffffffu, ext),
-                           RCm = __ballot_sync(0xffffffffu, rc != 0);
+            // The automaton of match.rs:45-58 has three states {closed, open forward Match, open rc Match}.  Because an rc
+            // Match only extends on rc hits (rl implies rc), the state after a hit is "forward" iff the hit is forward, or
+            // it is an rc hit that extends a forward Match (offset + 1: the precedence quirk).  That is a generate /
+            // propagate carry chain over the warp's ballots: G = forward hits, P = rc hits with offset + 1.
+            const uint32_t HIT = __ballot_sync(0xffffffffu, hit), RCm = __ballot_sync(0xffffffffu, rc != 0),
+                           FL = __ballot_sync(0xffffffffu, fl), RL = __ballot_sync(0xffffffffu, rl);
+            const uint32_t G = HIT & ~RCm, P = RCm & FL;
+            const uint32_t X = ((G << 1) | (s_in == 1u ? 1u : 0u)) & P;        // P-runs whose predecessor is in the forward state
+            const uint32_t S1 = G | (P & ~(P + X));                            // the carry ripples through each such run
+            const uint32_t S2 = HIT & ~S1;
+            const uint32_t Em = ((((S1 << 1) | (s_in == 1u ? 1u : 0u)) & FL) | (((S2 << 1) | (s_in == 2u ? 1u : 0u)) & RL)) & HIT;
+            const uint32_t Hm = HIT & ~Em;
+            const bool head = (Hm >> lane) & 1u;
+            const uint32_t s_after31 = (S1 >> 31) ? 1u : ((S2 >> 31) ? 2u : 0u);
             // close the Match carried in from the previous block if lane 0 does not extend it
             if (lane == 0 && c_hit && !(Em & 1u)) {
                 MatchRec *mr = out + (n_heads - 1);
@@ -727,7 +721,7 @@ __global__ void __launch_bounds__(128) k_probe_match(ProbeArgs a, Table t) {
                 c_off = __shfl_sync(0xffffffffu, off, 31); c_qend = __shfl_sync(0xffffffffu, qend, 31);
                 c_rstart = __shfl_sync(0xffffffffu, e.start, 31); c_rend = __shfl_sync(0xffffffffu, e.end, 31);
                 c_j = j0 + 31; c_mrc = mrc31;
-                s_in = __shfl_sync(0xffffffffu, s_after, 31);
+                s_in = s_after31;
                 n_heads += __popc(Hm);
             }
         }
