@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--reads", type=int, default=100000)
     ap.add_argument("--check", type=int, default=0)
     ap.add_argument("--full-grid", action="store_true", help="all 105 combinations instead of the three 1-D sweeps")
+    ap.add_argument("--parity-all", type=int, default=0, help="for EVERY combination also build the CPU-oracle index and compare the hits of this many reads")
     a = ap.parse_args()
     from mapquik_b200 import Index, Params, sim, capi
     tot = 3.1e9 / a.scale
@@ -34,7 +35,9 @@ def main():
     else:   # the reference's figures vary one parameter around the defaults (k=5, l=31, d=0.01)
         combos = [(k, 31, 0.01) for k in ks] + [(5, l, 0.01) for l in ls if l != 31] + [(5, 31, d) for d in ds if d != 0.01]
     print("k,l,density,n_kminmers,n_unique,n_keys,table_MB,index_gpu_ms,index_e2e_s,probe_ms,probes_per_s,map_kernels_ms,"
-          "kernels_reads_per_s,e2e_reads_per_s,mapped,q60,wrong_q60")
+          "kernels_reads_per_s,e2e_reads_per_s,mapped,q60,wrong_q60" + (",parity" if a.parity_all else ""))
+    if a.parity_all:
+        from oracle import pyoracle as O
     for k, l, d in combos:
         ix = Index(Params(k=k, l=l, density=d))
         t0 = time.perf_counter()
@@ -57,7 +60,17 @@ def main():
         nq = max(int(n_min), 1)          # minimizers of the timed map pass ~ index probes
         print(f"{k},{l},{d},{int(nb.sum())},{ix.n_unique},{ix.n_keys},{ix.table_bytes() / 1e6:.0f},{gpu_ms:.2f},{t_idx:.3f},"
               f"{st['probe']:.3f},{nq / (st['probe'] / 1e3):.3e},{kern:.2f},{a.reads / (kern / 1e3):.3e},{a.reads / t_map:.3e},"
-              f"{int(hits['mapped'].sum())},{int((hits['mapq'] == 60).sum())},{int(((hits['mapq'] == 60) & ~ok).sum())}", flush=True)
+              f"{int(hits['mapped'].sum())},{int((hits['mapq'] == 60).sum())},{int(((hits['mapq'] == 60) & ~ok).sum())}", end="", flush=True)
+        if a.parity_all:
+            oix = O.Index(O.params(k, l, d), int(nb.sum()) + 1024)
+            onb = oix.add_batch(names, g, go, threads=os.cpu_count())
+            n = min(a.parity_all, a.reads)
+            oh = oix.map_batch(rb[:int(ro[n])], ro[:n + 1], threads=os.cpu_count())
+            good = bool(np.array_equal(nb, onb) and oix.count() == ix.n_unique and oix.slots() == ix.n_keys and
+                        oh.tobytes() == hits[:n].tobytes())
+            print(f",{'ok' if good else 'MISMATCH'}", end="")
+            del oix
+        print(flush=True)
         ix.close()
     if a.check:
         from oracle import pyoracle as O
