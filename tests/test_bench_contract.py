@@ -1,0 +1,49 @@
+"""bench.py contract, CPU side: the reference arm runs without a GPU and prints one JSON line with the keys the
+driver reads; the GPU arm's line is checked on the B200 (-m gpu)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+COMMON = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+          "dtype", "data", "config", "e2e", "cpu_baseline"}
+
+
+def run_bench(*args, env=None):
+    e = dict(os.environ); e.update(env or {})
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *args], capture_output=True, text=True, env=e, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, r.stdout
+    return json.loads(lines[0])
+
+
+def test_reference_arm_line():
+    d = run_bench("--impl", "reference", "--steps", "1", "--warmup", "1", env={"OMP_NUM_THREADS": "1"})
+    assert COMMON <= set(d) and d["impl"] == "reference"
+    assert d["unit"] == "reads/s" and d["higher_is_better"] is True and d["vs_baseline"] is None and d["dtype"] == "u64"
+    assert "workload" in d["config"] and "model" not in d["config"]
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["value"] > 0 and d["mapped_reads"] == 25000
+
+
+def test_reference_arm_other_ranks_stay_silent():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"], capture_output=True,
+                       text=True, cwd=ROOT, env={**os.environ, "RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
+    assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+@pytest.mark.gpu
+def test_gpu_arm_line():
+    d = run_bench("--steps", "3", "--warmup", "3", "--reads", "20000")
+    assert COMMON | {"roofline", "gpu_launches", "clocks"} <= set(d) and "impl" not in d
+    assert d["n_gpus"] == 1 and d["scaling"] == "weak" and d["data"] == "synthetic"
+    rf = d["roofline"]
+    assert rf["bound"] == "hbm" and rf["unit"] == "GB/s" and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9
+    assert d["gpu_launches"] > 0 and d["e2e"]["h2d_bytes_per_step"] > 20000 * 1000 and d["e2e"]["d2h_bytes_per_step"] == 20000 * 48
+    assert d["e2e"]["value"] < d["value"]                       # the PCIe copies are inside the e2e region
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
