@@ -1023,8 +1023,11 @@ int mq_matches(mq_ctx *c, const uint8_t *seqs, const uint64_t *offs, uint32_t n,
     if (n_total) *n_total = tot;
     if (fields6 && tot) {
         if (cap < tot) { c->err = "output capacity too small"; return MQ_ERR_ARG; }
+        // only the first nm[i] records of a read's region are written by the kernel: copy exactly those
         std::vector<MatchRec> all(so[n]);
-        if (so[n]) CK(cudaMemcpyAsync(all.data(), c->d_matches.p, (size_t)so[n] * sizeof(MatchRec), cudaMemcpyDeviceToHost, c->stream));
+        for (uint32_t i = 0; i < n; i++)
+            if (nm[i]) CK(cudaMemcpyAsync(all.data() + so[i], c->d_matches.as<MatchRec>() + so[i], (size_t)nm[i] * sizeof(MatchRec),
+                                          cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
         uint64_t w = 0;
         for (uint32_t i = 0; i < n; i++) for (uint32_t j = 0; j < nm[i]; j++, w++) {
