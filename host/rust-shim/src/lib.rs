@@ -1,0 +1,84 @@
+//! FFI declarations of include/mapquik_b200.h plus a thin safe wrapper shaped like the reference's own types
+//! (`Index` / `ReadOnlyIndex`, src/index.rs) so that src/closures.rs changes by a few lines only.
+//! NOT compiled in the build image (no Rust toolchain); kept next to the C ABI it mirrors.
+use std::ffi::CStr;
+use std::os::raw::{c_char, c_int};
+
+#[repr(C)]
+pub struct MqParams { pub k: u32, pub l: u32, pub density: f64, pub use_hpc: u32, pub c: u32, pub s: u32, pub g: u32 }
+
+#[repr(C)]
+#[derive(Clone, Copy, Default, Debug)]
+pub struct MqHit {
+    pub mapped: u8, pub rc: u8, pub mapq: u8, pub pad_: u8, pub ref_idx: u32,
+    pub q_start: u64, pub q_end: u64, pub r_start: u64, pub r_end: u64, pub score: u64,
+}
+
+pub enum MqCtx {}
+
+extern "C" {
+    pub fn mq_create(out: *mut *mut MqCtx, p: *const MqParams, device: c_int) -> c_int;
+    pub fn mq_destroy(c: *mut MqCtx);
+    pub fn mq_strerror(code: c_int) -> *const c_char;
+    pub fn mq_last_error(c: *const MqCtx) -> *const c_char;
+    pub fn mq_index_add(c: *mut MqCtx, seqs: *const u8, offs: *const u64, n: u32, first_ref_idx: u32, nb_mers_out: *mut u64) -> c_int;
+    pub fn mq_index_freeze(c: *mut MqCtx, ref_lens: *const u64, n_refs: u32, n_unique: *mut u64, n_keys: *mut u64) -> c_int;
+    pub fn mq_map_batch(c: *mut MqCtx, seqs: *const u8, offs: *const u64, n: u32, out: *mut MqHit) -> c_int;
+}
+
+fn check(c: *const MqCtx, rc: c_int, what: &str) {
+    if rc != 0 {
+        // the reference aborts on every error (panic = "abort", Cargo.toml:49); keep that convention
+        let msg = unsafe { CStr::from_ptr(mq_strerror(rc)) }.to_string_lossy().into_owned();
+        let detail = if c.is_null() { String::new() } else { unsafe { CStr::from_ptr(mq_last_error(c)) }.to_string_lossy().into_owned() };
+        panic!("{}: {} ({})", what, msg, detail);
+    }
+}
+
+/// Stands in for `Index` (src/index.rs:73-105) while the reference is being read ...
+pub struct GpuIndex { ctx: *mut MqCtx, ref_lens: Vec<u64> }
+/// ... and for `ReadOnlyIndex` (src/index.rs:108-128) afterwards.
+pub struct GpuReadOnlyIndex { ctx: *mut MqCtx }
+unsafe impl Send for GpuIndex {}
+unsafe impl Send for GpuReadOnlyIndex {}
+
+impl GpuIndex {
+    /// ≙ Index::new() (closures.rs:24); `params` carries k, l, density, use_hpc, c, s, g of `Params` (main.rs:33-47)
+    pub fn new(params: MqParams, device: i32) -> Self {
+        let mut ctx: *mut MqCtx = std::ptr::null_mut();
+        check(std::ptr::null(), unsafe { mq_create(&mut ctx, &params, device) }, "mq_create");
+        GpuIndex { ctx, ref_lens: Vec::new() }
+    }
+    /// ≙ mers::ref_extract for a batch of upper-cased records (closures.rs:48,63); returns the k-min-mer count of each
+    pub fn ref_extract_batch(&mut self, seqs: &[u8], offs: &[u64]) -> Vec<u64> {
+        let n = (offs.len() - 1) as u32;
+        let mut nb = vec![0u64; n as usize];
+        let first = self.ref_lens.len() as u32;
+        check(self.ctx, unsafe { mq_index_add(self.ctx, seqs.as_ptr(), offs.as_ptr(), n, first, nb.as_mut_ptr()) }, "mq_index_add");
+        for w in offs.windows(2) { self.ref_lens.push(w[1] - w[0]); }
+        nb
+    }
+    /// ≙ mers_index.get_count() + ReadOnlyIndex::new(mers_index.index) (closures.rs:92,94)
+    pub fn freeze(self) -> (GpuReadOnlyIndex, u64) {
+        let mut n_unique = 0u64;
+        check(self.ctx, unsafe { mq_index_freeze(self.ctx, self.ref_lens.as_ptr(), self.ref_lens.len() as u32, &mut n_unique, std::ptr::null_mut()) },
+              "mq_index_freeze");
+        let ctx = self.ctx;
+        std::mem::forget(self);
+        (GpuReadOnlyIndex { ctx }, n_unique)
+    }
+}
+impl Drop for GpuIndex { fn drop(&mut self) { unsafe { mq_destroy(self.ctx) } } }
+
+impl GpuReadOnlyIndex {
+    /// ≙ mers::find_matches for a batch of upper-cased reads (closures.rs:102,106): one MqHit per read, input order.
+    /// The caller formats `q_id, q_len, q_start, q_end, ±, r_id, r_len, r_start, r_end, score, r_len, mapq` (mers.rs:181)
+    /// for every hit with `mapped != 0`.
+    pub fn find_matches_batch(&self, seqs: &[u8], offs: &[u64]) -> Vec<MqHit> {
+        let n = (offs.len() - 1) as u32;
+        let mut hits = vec![MqHit::default(); n as usize];
+        check(self.ctx, unsafe { mq_map_batch(self.ctx, seqs.as_ptr(), offs.as_ptr(), n, hits.as_mut_ptr()) }, "mq_map_batch");
+        hits
+    }
+}
+impl Drop for GpuReadOnlyIndex { fn drop(&mut self) { unsafe { mq_destroy(self.ctx) } } }
