@@ -483,3 +483,29 @@ def test_match_quirks_on_crafted_index():
     assert 30 in counts and refrc[counts.index(30)] == (3 << 1 | 1)      # the genuine rc Match on ref3
     assert counts.count(1) >= 2                           # windows 100 and 101: rc hits on different references stay apart
     ix.close()
+
+
+def test_segment_partition_tiny_and_odd_contigs():
+    # the multi-GPU index build on awkward references: contigs shorter than l+k-1, shorter than the rank count, one
+    # base, homopolymers -- cut into 8 ranges exactly like mapquik_b200.shard does -- must equal the single-shot index
+    from mapquik_b200 import shard
+    rng = np.random.default_rng(77)
+    p = Params()
+    contigs = [random_dna(rng, n) for n in (5, 1, 34, 35, 36, 200, 1000, 4097, 50000)]
+    contigs.append(np.full(3000, ord("A"), np.uint8))
+    contigs.append(np.concatenate([random_dna(rng, 700), np.full(900, ord("C"), np.uint8), random_dna(rng, 800)]))
+    buf, offs = concat_raw(contigs)
+    names = [f"c{i}" for i in range(len(contigs))]
+    whole = Index(p); nb = whole.add_batch(names, buf, offs); whole.freeze()
+    world = 8
+    part = Index(p)
+    for rank in range(world):
+        for r, seq in enumerate(contigs):
+            s, own, data = shard.segment_for_rank(seq, rank, world, p.l)
+            part.add_segment(r, names[r], len(seq), s, own, data if len(data) else np.zeros(1, np.uint8))
+    part.freeze()
+    assert whole.n_unique == part.n_unique and whole.n_keys == part.n_keys
+    assert np.array_equal(nb, part.nb_mers())
+    rb, ro, _, _ = sim.reads(77, buf, offs, 300, 3000, 1000, min_len=200)
+    assert whole.map_batch(rb, ro).tobytes() == part.map_batch(rb, ro).tobytes()
+    whole.close(); part.close()
