@@ -17,6 +17,7 @@
 //   * raw positions are recovered only for the ~1.5 % of l-mers that are selected, from per-group run
 //     masks (find-n-th-set-bit), instead of being tracked per base.
 #pragma once
+#include <cstddef>
 #include "mq_kernels.cuh"
 
 namespace mq {
@@ -39,7 +40,10 @@ struct ScanTablesV2 {                           // byte offsets are used directl
     uint64_t inF[4], outF[4], inR[4], outR[4];  // @256, @288, @320, @352
     uint64_t F0, R0;                            // hash state of a window of l phantom 'A's
     uint32_t sel[16];                           // @400: PRMT selectors compacting the run-start bytes of a word
+    uint32_t opq[4];                            // @464: 0x80000000, 2, bound_hi, shared address of this struct -- read back
+                                                //       through volatile loads so they stay in registers (see v2_step)
 };
+static_assert(offsetof(ScanTablesV2, opq) == 464 && sizeof(ScanTablesV2) == 480, "the kernel addresses these fields by byte offset");
 
 // tiles of record i on the 16-byte aligned grid
 __global__ void k_tiles_per_seq_v2(const uint64_t *offs, uint32_t n, uint32_t min_len, uint32_t *tiles) {
@@ -61,20 +65,73 @@ __device__ __forceinline__ void v2_geometry(uint64_t gs, uint64_t ge, uint32_t n
 
 struct V2Lane { uint64_t F, R; };
 
+// How the two 64-bit rotate-by-one + xor updates of a hash step are issued.  The integer ALU pipe (LOP3/SHF/compare,
+// one warp-instruction per two clocks per scheduler) is what bounds this kernel, while the FMA pipe (IMAD*) idles:
+//   0  leave it to the compiler (64-bit shifts/ors)
+//   1  funnel shifts (4 SHF + 4 LOP3, all ALU pipe)
+//   2  both rotations through IMAD.WIDE: x * 2^31 = {x << 31, x >> 1}, x * 2 = {x << 1, x >> 31}; the halves are
+//      recombined inside the xor (LOP3 (a|b)^c), so a step is 4 IMAD.WIDE (FMA pipe) + 4 LOP3 (ALU pipe)
+//   3  forward strand through IMAD.WIDE, reverse strand through funnel shifts
+//   4  reverse strand through IMAD.WIDE, forward strand through funnel shifts
+#ifndef MQ_V2_ROT
+#define MQ_V2_ROT 1
+#endif
+__device__ __forceinline__ void mulwide(uint32_t x, uint32_t k, uint32_t &lo, uint32_t &hi) {
+    asm("{ .reg .b64 w; mul.wide.u32 w, %2, %3; mov.b64 {%0, %1}, w; }" : "=r"(lo), "=r"(hi) : "r"(x), "r"(k));
+}
+struct V2H { uint32_t flo, fhi, rlo, rhi; };
+__device__ __forceinline__ void v2_step(V2H &h, uint64_t tf, uint64_t tr, uint32_t k31, uint32_t k2) {
+    const uint32_t tfl = (uint32_t)tf, tfh = (uint32_t)(tf >> 32), trl = (uint32_t)tr, trh = (uint32_t)(tr >> 32);
+    (void)k31; (void)k2; (void)tfl; (void)tfh; (void)trl; (void)trh;
+#if MQ_V2_ROT == 0
+    const uint64_t F = ror1(((uint64_t)h.fhi << 32) | h.flo) ^ tf, R = rol1(((uint64_t)h.rhi << 32) | h.rlo) ^ tr;
+    h.flo = (uint32_t)F; h.fhi = (uint32_t)(F >> 32); h.rlo = (uint32_t)R; h.rhi = (uint32_t)(R >> 32);
+#else
+#if MQ_V2_ROT == 2 || MQ_V2_ROT == 3
+    {   // F = ror1(F) ^ tf
+        uint32_t l31, l1, h31, h1;
+        mulwide(h.flo, k31, l31, l1); mulwide(h.fhi, k31, h31, h1);      // {x << 31, x >> 1}
+        h.flo = (l1 | h31) ^ tfl; h.fhi = (h1 | l31) ^ tfh;
+    }
+#else
+    { const uint32_t lo = h.flo, hi = h.fhi; h.flo = __funnelshift_r(lo, hi, 1) ^ tfl; h.fhi = __funnelshift_r(hi, lo, 1) ^ tfh; }
+#endif
+#if MQ_V2_ROT == 2 || MQ_V2_ROT == 4
+    {   // R = rol1(R) ^ tr
+        uint32_t ls, lc, hs, hc;
+        mulwide(h.rlo, k2, ls, lc); mulwide(h.rhi, k2, hs, hc);          // {x << 1, x >> 31}
+        h.rlo = (ls | hc) ^ trl; h.rhi = (hs | lc) ^ trh;
+    }
+#else
+    { const uint32_t lo = h.rlo, hi = h.rhi; h.rlo = __funnelshift_l(hi, lo, 1) ^ trl; h.rhi = __funnelshift_l(lo, hi, 1) ^ trh; }
+#endif
+#endif
+}
+
 // v2 digest of one 4-byte word.  Symbol codes are the raw bits (c>>1)&3, i.e. A=0 C=1 T=2 G=3 (the tables are
 // built in that order on the host), so no remap is needed.
 //   symw : per byte  code<<3 | nonACGT<<7   (the byte that goes into the symbol stream)
 //   run80: 0x80 in every byte that starts a homopolymer run (all bytes without HPC)
 struct V2Dig { uint32_t symw, run80; };
+// 0 in every byte of u that is 'A', 'C', 'G' or 'T':  bits 1..2 are the code; the other six bits must read 0x41, or
+// 0x50 when the code is 2 ('T' = 0x54) -- m marks code-2 bytes, m*0x0F + 0x41.. is the expected pattern
+__device__ __forceinline__ uint32_t v2_acgt_diff(uint32_t u) {
+    const uint32_t m = (u >> 2) & ~(u >> 1) & 0x01010101u;
+    return (u & 0xF9F9F9F9u) ^ (m * 0x0Fu + 0x41414141u);
+}
+__device__ __forceinline__ uint32_t v2_run80(uint32_t u, uint32_t pv, bool use_hpc) {
+    if (!use_hpc) return 0x80808080u;
+    const uint32_t e = u ^ pv;
+    return (((e & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | e) & 0x80808080u;
+}
 __device__ __forceinline__ V2Dig v2_digest(uint32_t u, uint32_t pv, bool use_hpc) {
-    const uint32_t t = (u >> 1) & 0x03030303u;
-    const uint32_t sel = (t & 0x3u) | ((t >> 4) & 0x30u) | ((t >> 8) & 0x300u) | ((t >> 12) & 0x3000u);
-    const uint32_t diff = __byte_perm(0x47544341u /* 'A','C','T','G' */, 0u, sel) ^ u;     // 0 where the byte is A/C/G/T
+    const uint32_t diff = v2_acgt_diff(u);
     const uint32_t bad80 = (((diff & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | diff) & 0x80808080u;
-    uint32_t run80 = 0x80808080u;
-    if (use_hpc) { const uint32_t e = u ^ pv; run80 = (((e & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | e) & 0x80808080u; }
-    V2Dig d; d.symw = (t << 3) | bad80; d.run80 = run80;
+    V2Dig d; d.symw = ((u << 2) & 0x18181818u) | bad80; d.run80 = v2_run80(u, pv, use_hpc);
     return d;
+}
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t r; asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel)); return r;
 }
 
 // explicit shared-state-space accessors (32-bit shared addresses): keeps ptxas from re-deriving the
@@ -119,14 +176,19 @@ __device__ __forceinline__ uint32_t select16(uint32_t m, uint32_t k) {
     c = m & 1u;                   if (k >= c) { pos += 1; }
     return pos;
 }
-// raw offset (inside the lane chunk) of the symbol with ordinal o: group = #(cum[g] <= o) - 1
+// raw offset (inside the lane chunk) of the symbol with ordinal o: group = #(cum[g] <= o) - 1.
+// cum[] holds the symbol count before each 16-byte group; unused entries hold a sentinel no ordinal reaches.  With
+// chunks of <= 128 bytes every value is < 0x80 (a chunk with fewer than 8 groups has <= 112 symbols), so "byte <= o"
+// is one SWAR subtraction: bit 7 of (0x80|o) - byte.
+constexpr uint32_t V2_CUM_FILL = V2_CS_MAX <= 128 ? 0x7F7F7F7Fu : 0xFFFFFFFFu;
 __device__ __forceinline__ uint32_t v2_raw_offset(uint32_t runm_a, uint32_t cum_a, uint32_t gpl, uint32_t o) {
     uint32_t g = 0;
+    const uint32_t ob = o * 0x01010101u;
 #pragma unroll
-    for (int w = 0; w < 4; w++) {
+    for (int w = 0; w < V2_GPL_MAX / 4; w++) {
         const uint32_t cw = lds32(cum_a + 4 * w);
-        // bytes of cw that are <= o (only the first gpl entries are meaningful; later ones hold 0xFF)
-        g += __popc(__vcmpleu4(cw, o * 0x01010101u) & 0x01010101u);
+        if (V2_CS_MAX <= 128) g += __popc(((ob | 0x80808080u) - cw) & 0x80808080u);
+        else g += __popc(__vcmpleu4(cw, ob) & 0x01010101u);
     }
     g -= 1;
     const uint32_t rm = lds16(runm_a + 2 * g), base = lds8(cum_a + g);
@@ -161,9 +223,85 @@ __device__ __noinline__ void v2_flush(uint32_t nc, uint32_t j0, uint32_t ch_a, u
     *nloc = j;
 }
 
+// Stage + compact one lane chunk: groups [g0, g1) lie completely inside the record (fast path, one PRMT compaction per
+// word); the (at most two) groups cut by a record boundary go byte-wise; groups outside the record hold no symbol.
+// FAST leaves the non-ACGT flag (bit 7) out of the symbol bytes and only reports whether the chunk holds ANY byte other
+// than A/C/G/T (bad != 0) -- the caller then stages the tile again with FAST = false, which flags every symbol.
+template <bool FAST>
+__device__ __forceinline__ void v2_stage(const ScanArgs &a, uint64_t tlo, uint64_t gs, uint32_t c_lo, uint32_t gpl, uint32_t own_lo,
+                                         uint32_t own_hi, uint32_t sa, uint32_t cum_a, uint32_t runm_a, uint32_t ta, bool hpc,
+                                         uint32_t &n_out, uint32_t &bad_out) {
+    const uint32_t Cs = gpl << 4;
+    uint32_t n = 0, bad = 0;
+    const uint8_t *cp = a.seqs + tlo + c_lo;
+    uint32_t prev = 0;
+    if (c_lo > own_lo && c_lo < own_hi) prev = cp[-1];  // byte before my chunk (same record)
+    else if (c_lo == own_lo && tlo + own_lo > gs) prev = cp[-1];
+    else if (c_lo == own_lo) prev = (uint32_t)cp[0] ^ 0xFFu;   // record starts exactly at my chunk: force a run start
+    sts32(cum_a, V2_CUM_FILL); sts32(cum_a + 4, V2_CUM_FILL); sts32(cum_a + 8, V2_CUM_FILL); sts32(cum_a + 12, V2_CUM_FILL);
+    const uint32_t lo_x = max(own_lo, c_lo), hi_x = min(own_hi, c_lo + Cs);
+    uint32_t g0 = gpl, g1 = gpl;
+    if (lo_x < hi_x) { g0 = (lo_x - c_lo + 15) >> 4; g1 = (hi_x - c_lo) >> 4; if (g1 < g0) g1 = g0; }
+    uint4 nxt = make_uint4(0, 0, 0, 0);
+    if (g0 < g1) nxt = __ldg((const uint4 *)(cp + 16 * g0));          // prefetch: one group ahead
+    for (uint32_t g = 0; g < gpl; g++) {
+        uint32_t rm = 0;
+        sts8(cum_a + g, n);
+        if (g >= g0 && g < g1) {
+            const uint4 v = nxt;
+            if (g + 1 < g1) nxt = __ldg((const uint4 *)(cp + 16 * (g + 1)));
+            const uint32_t uw[4] = {v.x, v.y, v.z, v.w};
+            // compact the run-start bytes of each word with one byte-permute (selector from a 16-entry
+            // table), store all four bytes at the write cursor and advance the cursor only past the run
+            // starts -- later stores overwrite the slack
+#pragma unroll
+            for (int w = 0; w < 4; w++) {
+                const uint32_t u = uw[w];
+                const uint32_t run80 = v2_run80(u, (u << 8) | prev, hpc);
+                prev = u >> 24;
+                uint32_t symw;
+                if (FAST) { symw = (u << 2) & 0x18181818u; bad |= v2_acgt_diff(u); }
+                else { const V2Dig d = v2_digest(u, 0u, false); symw = d.symw; bad |= d.symw & run80; }
+                const uint32_t p4 = ((run80 >> 7) * 0x04081020u) >> 24;            // 4 * (the four run bits)
+                const uint32_t comp = prmt(symw, 0u, lds32(ta + 400 + p4));
+                const uint32_t wa = sa + n;
+                sts8(wa, comp); sts8(wa + 1, comp >> 8); sts8(wa + 2, comp >> 16); sts8(wa + 3, comp >> 24);
+                n += __popc(p4);
+                rm |= w ? (p4 << (4 * w - 2)) : (p4 >> 2);
+            }
+        } else {
+            const uint32_t xg = c_lo + 16 * g;
+            if (xg < own_hi && xg + 16 > own_lo) {       // cut by a record boundary: byte-wise
+                const uint4 v = __ldg((const uint4 *)(cp + 16 * g));
+                const uint32_t uw[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int w = 0; w < 4; w++) {
+                    const uint32_t u = uw[w];
+                    const V2Dig d = v2_digest(u, (u << 8) | prev, hpc);
+                    prev = u >> 24;
+#pragma unroll
+                    for (int b = 0; b < 4; b++) {
+                        const uint32_t x = xg + 4 * w + b;
+                        if (x < own_lo || x >= own_hi) continue;
+                        const bool start = (x == own_lo && tlo + own_lo == gs) || ((d.run80 >> (8 * b)) & 0x80u);
+                        if (!start) continue;
+                        const uint32_t sb = (d.symw >> (8 * b)) & 0xFFu;
+                        bad |= sb & 0x80u;
+                        sts8(sa + n, FAST ? (sb & 0x7Fu) : sb); n++;
+                        rm |= 1u << (4 * w + b);
+                    }
+                }
+            }
+        }
+        sts16(runm_a + 2 * g, rm);
+    }
+    n_out = n; bad_out = bad;
+}
+
 #define V2_CANDIDATE(ORD)                                                                                     \
-    if (min((uint32_t)(F >> 32), (uint32_t)(R >> 32)) <= bound_hi) {                                          \
-        sts64(ch_a + 8 * nc, F < R ? F : R); sts8(co_a + nc, (uint32_t)(ORD)); nc++;                          \
+    if (min(H.fhi, H.rhi) <= bound_hi) {                                                                      \
+        const uint64_t F_ = ((uint64_t)H.fhi << 32) | H.flo, R_ = ((uint64_t)H.rhi << 32) | H.rlo;            \
+        sts64(ch_a + 8 * nc, F_ < R_ ? F_ : R_); sts8(co_a + nc, (uint32_t)(ORD)); nc++;                      \
         if (nc == V2_CAND) { v2_flush(nc, nloc, ch_a, co_a, runm_a, cum_a, gpl, c_lo, xlo, xlim, lane, ev_a, tile, a, bound, &nloc); nc = 0; } \
     }
 
@@ -172,6 +310,8 @@ __global__ void __launch_bounds__(V2_WARPS * 32) k_scan_minimizers_v2(ScanArgs a
     __shared__ __align__(128) ScanTablesV2 T;
     __shared__ uint32_t ev_cnt[V2_WARPS];
     for (uint32_t i = threadIdx.x; i < sizeof(ScanTablesV2) / 4; i += blockDim.x) ((uint32_t *)&T)[i] = ((const uint32_t *)&Tin)[i];
+    __syncthreads();
+    if (threadIdx.x == 0) { T.opq[0] = 0x80000000u; T.opq[1] = 2u; T.opq[2] = (uint32_t)(a.bound >> 32); T.opq[3] = smem_addr(&T); }
     __syncthreads();
     const uint32_t lane = lane_id(), wid = threadIdx.x >> 5;
     uint8_t *WS = smem_raw + (size_t)wid * V2_WARP_BYTES;
@@ -182,11 +322,14 @@ __global__ void __launch_bounds__(V2_WARPS * 32) k_scan_minimizers_v2(ScanArgs a
     const uint32_t cum_a = ws_a + V2_OFF_CUM + lane * 16;
     const uint32_t ch_a = ws_a + V2_OFF_CH + lane * V2_CH_STRIDE;
     const uint32_t co_a = ws_a + V2_OFF_CO + lane * 16;
-    const uint32_t ta = smem_addr(&T);                               // pairF @0, pairR @128, single-symbol tables @256..
+    // pairF @0, pairR @128, single-symbol tables @256..; these four scalars come back through volatile shared loads so
+    // that ptxas keeps them in registers instead of re-deriving them (S2UR/ULEA/LDCU) inside the hot loop
+    const uint32_t ta = lds32(smem_addr(&T) + 464 + 12);
+    const uint32_t k31 = lds32(ta + 464), k2 = lds32(ta + 464 + 4);
+    const uint32_t bound_hi = lds32(ta + 464 + 8);
     const uint32_t ev_a = smem_addr(&ev_cnt[wid]);
     const uint32_t l = a.l;
     const bool hpc = a.use_hpc != 0;
-    const uint32_t bound_hi = (uint32_t)(a.bound >> 32);
     const uint64_t bound = a.bound;
 
     for (;;) {
@@ -215,70 +358,11 @@ __global__ void __launch_bounds__(V2_WARPS * 32) k_scan_minimizers_v2(ScanArgs a
 
         // ---- stage + compact my chunk: one byte per homopolymer-run start ---------------------------
         const uint32_t c_lo = lane * Cs;                       // x' of my first byte
-        uint32_t n = 0, bad = 0;
-        {
-            const uint8_t *cp = a.seqs + tlo + c_lo;
-            uint32_t prev = 0;
-            if (c_lo > own_lo && c_lo < own_hi) prev = cp[-1];  // byte before my chunk (same record)
-            else if (c_lo == own_lo && tlo + own_lo > gs) prev = cp[-1];
-            else if (c_lo == own_lo) prev = (uint32_t)cp[0] ^ 0xFFu;   // record starts exactly at my chunk: force a run start
-            sts32(cum_a, 0xFFFFFFFFu); sts32(cum_a + 4, 0xFFFFFFFFu); sts32(cum_a + 8, 0xFFFFFFFFu); sts32(cum_a + 12, 0xFFFFFFFFu);
-            // groups [g0, g1) of my chunk lie completely inside the record: fast path; the (at most two) groups cut
-            // by a record boundary go byte-wise; groups outside the record hold no symbol
-            const uint32_t lo_x = max(own_lo, c_lo), hi_x = min(own_hi, c_lo + Cs);
-            uint32_t g0 = gpl, g1 = gpl;
-            if (lo_x < hi_x) { g0 = (lo_x - c_lo + 15) >> 4; g1 = (hi_x - c_lo) >> 4; if (g1 < g0) g1 = g0; }
-            uint4 nxt = make_uint4(0, 0, 0, 0);
-            if (g0 < g1) nxt = __ldg((const uint4 *)(cp + 16 * g0));          // prefetch: one group ahead
-            for (uint32_t g = 0; g < gpl; g++) {
-                uint32_t rm = 0;
-                sts8(cum_a + g, n);
-                if (g >= g0 && g < g1) {
-                    const uint4 v = nxt;
-                    if (g + 1 < g1) nxt = __ldg((const uint4 *)(cp + 16 * (g + 1)));
-                    const uint32_t uw[4] = {v.x, v.y, v.z, v.w};
-                    // compact the run-start bytes of each word with one byte-permute (selector from a 16-entry
-                    // table), store all four bytes at the write cursor and advance the cursor only past the run
-                    // starts -- later stores overwrite the slack
-#pragma unroll
-                    for (int w = 0; w < 4; w++) {
-                        const uint32_t u = uw[w];
-                        const V2Dig d = v2_digest(u, (u << 8) | prev, hpc);
-                        prev = u >> 24;
-                        const uint32_t p = ((d.run80 >> 7) * 0x01020408u) >> 24;              // 4 run bits
-                        bad |= d.symw & d.run80;                                              // non-ACGT among run starts
-                        const uint32_t comp = __byte_perm(d.symw, 0u, lds32(ta + 400 + 4 * p));
-                        const uint32_t wa = sa + n;
-                        sts8(wa, comp); sts8(wa + 1, comp >> 8); sts8(wa + 2, comp >> 16); sts8(wa + 3, comp >> 24);
-                        n += __popc(p);
-                        rm |= p << (4 * w);
-                    }
-                } else {
-                    const uint32_t xg = c_lo + 16 * g;
-                    if (xg < own_hi && xg + 16 > own_lo) {       // cut by a record boundary: byte-wise
-                        const uint4 v = __ldg((const uint4 *)(cp + 16 * g));
-                        const uint32_t uw[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                        for (int w = 0; w < 4; w++) {
-                            const uint32_t u = uw[w];
-                            const V2Dig d = v2_digest(u, (u << 8) | prev, hpc);
-                            prev = u >> 24;
-#pragma unroll
-                            for (int b = 0; b < 4; b++) {
-                                const uint32_t x = xg + 4 * w + b;
-                                if (x < own_lo || x >= own_hi) continue;
-                                const bool start = (x == own_lo && tlo + own_lo == gs) || ((d.run80 >> (8 * b)) & 0x80u);
-                                if (!start) continue;
-                                const uint32_t sb = (d.symw >> (8 * b)) & 0xFFu;
-                                bad |= sb & 0x80u;
-                                sts8(sa + n, sb); n++;
-                                rm |= 1u << (4 * w + b);
-                            }
-                        }
-                    }
-                }
-                sts16(runm_a + 2 * g, rm);
-            }
+        uint32_t n, bad;
+        v2_stage<true>(a, tlo, gs, c_lo, gpl, own_lo, own_hi, sa, cum_a, runm_a, ta, hpc, n, bad);
+        if (__any_sync(0xffffffffu, bad != 0)) {               // some byte is not A/C/G/T: stage again with per-symbol flags
+            __syncwarp();
+            v2_stage<false>(a, tlo, gs, c_lo, gpl, own_lo, own_hi, sa, cum_a, runm_a, ta, hpc, n, bad);
         }
         sts32(nsym_a + 4 * lane, n);
         if (!__any_sync(0xffffffffu, n != 0)) {
@@ -351,29 +435,33 @@ __global__ void __launch_bounds__(V2_WARPS * 32) k_scan_minimizers_v2(ScanArgs a
         const int lim = (int)(n + c);                           // symbols available in my logical stream
         int o = lim - 1;
         const int o2 = max(-1, min((int)n - 1, lim - (int)l));  // first ordinal whose window is complete and mine
+        V2H H;
         if (anyN) {
             for (; o > o2; o--) v2_step_generic(st, sa, o, lim, l, ta);
+            H.flo = (uint32_t)st.F; H.fhi = (uint32_t)(st.F >> 32); H.rlo = (uint32_t)st.R; H.rhi = (uint32_t)(st.R >> 32);
         } else {
             // o > o2 == lim-l (or -1): the outgoing ordinal o+l lies beyond the stream, i.e. it is a phantom
             // 'A' (code 0) -- the pair-table row for out == 0 is the whole step
+            H.flo = (uint32_t)st.F; H.fhi = (uint32_t)(st.F >> 32); H.rlo = (uint32_t)st.R; H.rhi = (uint32_t)(st.R >> 32);
             for (; o > o2; o--) {
                 const uint32_t off = lds8(sa + o);
-                st.F = ror1(st.F) ^ lds64(ta + off); st.R = rol1(st.R) ^ lds64(ta + 128 + off);
+                v2_step(H, lds64(ta + off), lds64(ta + 128 + off), k31, k2);
             }
         }
 
         // ---- phase 2: scan of my own symbols; selected l-mers are parked, positions resolved after --------
-        uint64_t F = st.F, R = st.R;
         uint32_t nc = 0;
         if (anyN) {
             for (; o >= 0; o--) {
-                st.F = F; st.R = R; v2_step_generic(st, sa, o, lim, l, ta); F = st.F; R = st.R;
+                st.F = ((uint64_t)H.fhi << 32) | H.flo; st.R = ((uint64_t)H.rhi << 32) | H.rlo;
+                v2_step_generic(st, sa, o, lim, l, ta);
+                H.flo = (uint32_t)st.F; H.fhi = (uint32_t)(st.F >> 32); H.rlo = (uint32_t)st.R; H.rhi = (uint32_t)(st.R >> 32);
                 V2_CANDIDATE(o)
             }
         } else {
             for (; o >= 0 && ((o + 1) & 3); o--) {                // bring o+1 to a multiple of 4
                 const uint32_t off = lds8(sa + o) | (lds8(sa + o + (int)l) << 2);
-                F = ror1(F) ^ lds64(ta + off); R = rol1(R) ^ lds64(ta + 128 + off);
+                v2_step(H, lds64(ta + off), lds64(ta + 128 + off), k31, k2);
                 V2_CANDIDATE(o)
             }
             const uint32_t lw4 = (l >> 2) * 4, ls = 8 * (l & 3);
@@ -390,10 +478,10 @@ __global__ void __launch_bounds__(V2_WARPS * 32) k_scan_minimizers_v2(ScanArgs a
                 const uint64_t tf1 = lds64(ta + o1b), tr1 = lds64(ta + 128 + o1b);
                 const uint64_t tf0 = lds64(ta + o0b), tr0 = lds64(ta + 128 + o0b);
                 if (w > 0) { inw = lds32(sa + 4 * w - 4); ow0 = lds32(sa + 4 * w - 4 + lw4); ow1 = lds32(sa + 4 * w + lw4); }
-                F = ror1(F) ^ tf3; R = rol1(R) ^ tr3; V2_CANDIDATE(4 * w + 3)
-                F = ror1(F) ^ tf2; R = rol1(R) ^ tr2; V2_CANDIDATE(4 * w + 2)
-                F = ror1(F) ^ tf1; R = rol1(R) ^ tr1; V2_CANDIDATE(4 * w + 1)
-                F = ror1(F) ^ tf0; R = rol1(R) ^ tr0; V2_CANDIDATE(4 * w)
+                v2_step(H, tf3, tr3, k31, k2); V2_CANDIDATE(4 * w + 3)
+                v2_step(H, tf2, tr2, k31, k2); V2_CANDIDATE(4 * w + 2)
+                v2_step(H, tf1, tr1, k31, k2); V2_CANDIDATE(4 * w + 1)
+                v2_step(H, tf0, tr0, k31, k2); V2_CANDIDATE(4 * w)
             }
         }
         if (nc) v2_flush(nc, nloc, ch_a, co_a, runm_a, cum_a, gpl, c_lo, xlo, xlim, lane, ev_a, tile, a, bound, &nloc);
