@@ -30,7 +30,7 @@ def _stale(target, sources):
 
 
 def build_cuda(force=False, verbose=False):
-    srcs = [os.path.join(CSRC, "mq_lib.cu"), os.path.join(CSRC, "mq_kernels.cuh"), os.path.join(CSRC, "mq_scan_v2.cuh"),
+    srcs = [os.path.join(CSRC, "mq_lib.cu"), os.path.join(CSRC, "mq_kernels.cuh"), os.path.join(CSRC, "mq_scan_v2.cuh"), os.path.join(CSRC, "mq_scan_v3.cuh"),
             os.path.join(PKG, "..", "include", "mapquik_b200.h")]
     if force or _stale(LIB, srcs):
         cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, srcs[0]]

@@ -4,6 +4,7 @@
 #include "../../include/mapquik_b200.h"
 #include "mq_kernels.cuh"
 #include "mq_scan_v2.cuh"
+#include "mq_scan_v3.cuh"
 #include <cstdlib>
 #include <cstddef>
 
@@ -38,8 +39,10 @@ struct mq_ctx {
     uint64_t bound = 0;
     ScanTables tab{};
     ScanTablesV2 tab2{};
+    ScanTablesV3 tab3{};
     int v2_ctas_per_sm = 0;
     bool scan_v1 = false;          // MQ_SCAN_V1=1 selects the first-generation scan kernel (A/B, debugging)
+    bool scan_v2 = false;          // MQ_SCAN_V2=1 selects the second-generation one (contiguous lane streams)
     std::string err;
     uint64_t launches = 0, scan_kernel_launches = 0;
     int n_sm = 148;
@@ -262,15 +265,20 @@ int run_scan(mq_ctx *c, const uint8_t *d_seqs, const uint64_t *d_offs, uint32_t 
                     k_scan_minimizers<<<grid, SCAN_WARPS * 32, SCAN_WARPS * TILE_SMEM, c->stream>>>(a, c->tab);
                 } else {
                     const uint32_t ctas_needed = (n_tiles + V2_WARPS - 1) / V2_WARPS;
-                    const size_t smem = (size_t)V2_WARPS * V2_WARP_BYTES;
+                    size_t smem = (size_t)V2_WARPS * (c->scan_v2 ? V2_WARP_BYTES : V3_WARP_BYTES);
+                    { const char *e = getenv("MQ_SCAN_PAD"); if (e) smem += (size_t)atoi(e); }   // occupancy experiments
                     if (c->v2_ctas_per_sm == 0) {      // persistent grid = every CTA the chip can hold
                         int nb = 0;
-                        if (smem > 48 * 1024) cudaFuncSetAttribute(k_scan_minimizers_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_scan_minimizers_v2, V2_WARPS * 32, smem) != cudaSuccess || nb < 1) nb = 1;
+                        const void *kern = c->scan_v2 ? (const void *)k_scan_minimizers_v2 : (const void *)k_scan_minimizers_v3;
+                        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+                        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, V2_WARPS * 32, smem) != cudaSuccess || nb < 1) nb = 1;
                         c->v2_ctas_per_sm = nb;
+                        if (getenv("MQ_DEBUG")) fprintf(stderr, "[mq] scan kernel: %d CTAs/SM x %d warps, %zu B dynamic smem per CTA\n", nb, V2_WARPS, smem);
                     }
                     const uint32_t grid = std::min<uint32_t>(ctas_needed, (uint32_t)(c->n_sm * c->v2_ctas_per_sm));
-                    k_scan_minimizers_v2<<<grid, V2_WARPS * 32, smem, c->stream>>>(a, c->tab2);
+                    if (c->scan_v2) k_scan_minimizers_v2<<<grid, V2_WARPS * 32, smem, c->stream>>>(a, c->tab2);
+                    else k_scan_minimizers_v3<<<grid, V2_WARPS * 32, smem, c->stream>>>(a, c->tab3);
                 }
             }
             c->launches += 2;
@@ -420,7 +428,9 @@ int mq_create(mq_ctx **out, const mq_params *p, int device) {
     c->p = *p; c->device = device; c->bound = hash_bound(p->density);
     fill_tables(c->tab, p->l);
     fill_tables_v2(c->tab2, c->tab, p->l);
+    fill_tables_v3(c->tab3, c->tab2);
     { const char *e = getenv("MQ_SCAN_V1"); c->scan_v1 = e && e[0] == '1'; }
+    { const char *e = getenv("MQ_SCAN_V2"); c->scan_v2 = e && e[0] == '1'; }
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->n_sm = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return MQ_ERR_CUDA; }

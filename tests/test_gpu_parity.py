@@ -22,10 +22,11 @@ def oracle_minimizers(seqs, offs, p):
         np.concatenate(hs) if hs else np.zeros(0, np.uint64)
 
 
-@pytest.fixture(params=["v2", "v1"])
+@pytest.fixture(params=["v3", "v2", "v1"])
 def scan_version(request, monkeypatch):
-    """both generations of the S1 kernel stay under test (MQ_SCAN_V1 is read at mq_create)"""
+    """all generations of the S1 kernel stay under test (MQ_SCAN_V1 / MQ_SCAN_V2 are read at mq_create)"""
     monkeypatch.setenv("MQ_SCAN_V1", "1" if request.param == "v1" else "0")
+    monkeypatch.setenv("MQ_SCAN_V2", "1" if request.param == "v2" else "0")
     return request.param
 
 
