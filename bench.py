@@ -116,7 +116,7 @@ def host_threads():
 
 
 def scan_traffic(n_reads):
-    """dram__bytes_read.sum + dram__bytes_write.sum of one k_scan_minimizers_v2 launch on the default
+    """dram__bytes_read.sum + dram__bytes_write.sum of one k_scan_minimizers_v3 launch on the default
     workload, from the committed `ncu --set full` capture (profiles/scan_traffic.json); null otherwise."""
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "scan_traffic.json")))
@@ -355,7 +355,7 @@ def main():
                     "d2h_bytes_per_step": int(n_reads * 48), "gbp_per_s": bases_total * args.steps / (t_e2e / 1e3) / 1e9,
                     "stage_ms_last_step": e2e_stage},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "k_scan_minimizers_v2", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "k_scan_minimizers_v3", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if peak else None, "traffic": scan_traffic(n_reads), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(algo_bytes), "avg_launch_ms": scan_avg_ms,
                          "launches": int(scan_launches),

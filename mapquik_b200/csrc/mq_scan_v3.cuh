@@ -32,11 +32,12 @@ struct ScanTablesV3 {                           // same size and scalar offsets 
     uint64_t inF[4], outF[4], inR[4], outR[4];  // @256, @288, @320, @352
     uint64_t F0, R0;
     uint32_t sel[16];                           // @400
-    uint32_t opq[4];                            // @464
+    uint32_t opq[8];                            // @464: 2^31, 2, bound_hi, &T, 15 << 30, 1, 4, -- (see MQ_V3_FMA)
 };
-static_assert(sizeof(ScanTablesV3) == sizeof(ScanTablesV2) && offsetof(ScanTablesV3, sel) == 400 && offsetof(ScanTablesV3, opq) == 464, "layout");
+static_assert(sizeof(ScanTablesV3) == sizeof(ScanTablesV2) + 16 && offsetof(ScanTablesV3, sel) == 400 && offsetof(ScanTablesV3, opq) == 464, "layout");
 inline void fill_tables_v3(ScanTablesV3 &T, const ScanTablesV2 &S) {
-    memcpy(&T, &S, sizeof(T));
+    memset(&T, 0, sizeof(T));
+    memcpy(&T, &S, sizeof(S));
     if (MQ_V3_LDS128) for (int i = 0; i < 16; i++) { T.pair[2 * i] = S.pairF[i]; T.pair[2 * i + 1] = S.pairR[i]; }
 }
 __device__ __forceinline__ uint4 lds128(uint32_t a) {
@@ -50,6 +51,36 @@ __device__ __forceinline__ uint4 v3_tab(uint32_t ta, uint32_t off) {
 }
 __device__ __forceinline__ void v3_step(V2H &h, uint4 t, uint32_t k31, uint32_t k2) {
     v2_step(h, ((uint64_t)t.y << 32) | t.x, ((uint64_t)t.w << 32) | t.z, k31, k2);
+}
+// MQ_V3_FMA = 1: additions / small multiplies whose result the integer ALU pipe would otherwise produce are issued as
+// IMAD / IMAD.HI with multipliers read from shared memory (opaque to ptxas, which would strength-reduce literal
+// multipliers back into shifts and adds): the ALU pipe is this kernel's bound, the FMA pipe is mostly idle.
+#ifndef MQ_V3_FMA
+#define MQ_V3_FMA 0
+#endif
+struct V3K { uint32_t c0, one, four; };          // 15 << 30, 1, 4
+__device__ __forceinline__ uint32_t fma_add(uint32_t x, uint32_t c, const V3K &k) {           // x + c
+#if MQ_V3_FMA
+    uint32_t r; asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(k.one), "r"(c)); return r;
+#else
+    (void)k; return x + c;
+#endif
+}
+// 0 in every byte of u that is 'A', 'C', 'G' or 'T' (see v2_acgt_diff): m4 marks code-2 bytes at bit 2, and
+// hi32(m4 * (15 << 30)) = (m4 * 15) >> 2 = 0x0F in those bytes, so the expected pattern is one IMAD.HI
+__device__ __forceinline__ uint32_t v3_acgt_diff(uint32_t u, const V3K &k) {
+#if MQ_V3_FMA
+    const uint32_t m4 = u & ~(u << 1) & 0x04040404u;
+    uint32_t e; asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(e) : "r"(m4), "r"(k.c0), "r"(0x41414141u));
+    return (u & 0xF9F9F9F9u) ^ e;
+#else
+    (void)k; return v2_acgt_diff(u);
+#endif
+}
+__device__ __forceinline__ uint32_t v3_run80(uint32_t u, uint32_t pv, bool use_hpc, const V3K &k) {
+    if (!use_hpc) return 0x80808080u;
+    const uint32_t e = u ^ pv;
+    return (fma_add(e & 0x7F7F7F7Fu, 0x7F7F7F7Fu, k) | e) & 0x80808080u;
 }
 // symbol byte: code << V3_SH (code: A=0 C=1 T=2 G=3), bit 7 = not A/C/G/T
 __device__ __forceinline__ uint32_t v3_symw(uint32_t u) { return (u << (V3_SH - 1)) & (0x03030303u << V3_SH); }
@@ -75,9 +106,19 @@ __device__ __forceinline__ uint32_t v3_baddr(uint32_t sb, uint32_t o) { return s
 // append cursor of a lane stream: P holds the bytes of the incomplete word (zero above them), n8 = 8 * symbols so far,
 // wp = address of the incomplete word
 struct V3Pend { uint32_t P, n8, wp; };
+#ifndef MQ_V3_PUSH_MAD
+#define MQ_V3_PUSH_MAD 0
+#endif
 __device__ __forceinline__ void v3_push(V3Pend &q, uint32_t comp, uint32_t c8) {       // comp: c8/8 bytes, zero above
     const uint32_t f8 = q.n8 & 24u;
-    const uint32_t lo = q.P | (comp << f8), hi = __funnelshift_l(comp, 0u, f8);        // (hi:lo) = comp << f8 | P
+#if MQ_V3_PUSH_MAD
+    uint32_t lo, hi;                                                                    // (hi:lo) = comp * 2^f8 + P
+    asm("{ .reg .b64 w, p; mov.b64 p, {%3, %4}; mad.wide.u32 w, %2, %5, p; mov.b64 {%0, %1}, w; }"
+        : "=r"(lo), "=r"(hi) : "r"(comp), "r"(q.P), "r"(0u), "r"(1u << f8));
+#else
+    (void)f8;                                                                           // the funnel shifter takes n8 mod 32
+    const uint32_t lo = q.P | __funnelshift_l(0u, comp, q.n8), hi = __funnelshift_l(comp, 0u, q.n8);   // (hi:lo) = comp << f8 | P
+#endif
     const uint32_t n8n = q.n8 + c8;
     if ((n8n ^ q.n8) & 32u) { sts32(q.wp, lo); q.wp += 128u; q.P = hi; } else q.P = lo;
     q.n8 = n8n;
@@ -116,7 +157,7 @@ __device__ __noinline__ uint32_t v3_flush(uint32_t top, uint32_t cpz, uint32_t j
 template <bool FAST>
 __device__ __forceinline__ void v3_stage(const ScanArgs &a, uint64_t tlo, uint64_t gs, uint32_t c_lo, uint32_t gpl, uint32_t own_lo,
                                          uint32_t own_hi, uint32_t sb, uint32_t cum_l, uint32_t runm_l, uint32_t ta, bool hpc,
-                                         V3Pend &q, uint32_t &bad_out) {
+                                         const V3K &kk, V3Pend &q, uint32_t &bad_out) {
     const uint32_t Cs = gpl << 4;
     uint32_t bad = 0;
     q.P = 0; q.n8 = 0; q.wp = sb;
@@ -143,15 +184,17 @@ __device__ __forceinline__ void v3_stage(const ScanArgs &a, uint64_t tlo, uint64
 #pragma unroll
             for (int w = 0; w < 4; w++) {
                 const uint32_t u = uw[w];
-                const uint32_t run80 = v2_run80(u, (u << 8) | prev, hpc);
+                const uint32_t run80 = v3_run80(u, (u << 8) | prev, hpc, kk);
                 prev = u >> 24;
                 uint32_t symw = v3_symw(u);
-                if (FAST) bad |= v2_acgt_diff(u);
+                if (FAST) bad |= v3_acgt_diff(u, kk);
                 else { symw |= v3_bad80(u); bad |= symw & run80; }
-                const uint32_t p4 = ((run80 >> 7) * 0x04081020u) >> 24;            // 4 * (the four run bits)
-                const uint32_t comp = prmt(symw, 0u, lds32(ta + 400 + p4));       // run-start bytes first, zero fill
-                v3_push(q, comp, __popc(p4) << 3);
-                rm |= w ? (p4 << (4 * w - 2)) : (p4 >> 2);
+                // run80 has bit 7 of byte i set for a run start: * 0x00204081 moves them to bits 28..31 (no two partial
+                // products meet, so nothing carries)
+                const uint32_t p = (run80 * 0x00204081u) >> 28;                    // the four run bits
+                const uint32_t comp = prmt(symw, 0u, lds32(p * 4u + (ta + 400)));   // run-start bytes first, zero fill
+                v3_push(q, comp, __popc(p) << 3);
+                rm |= p << (4 * w);
             }
         } else {
             const uint32_t xg = c_lo + 16 * g;
@@ -194,13 +237,16 @@ __device__ __forceinline__ void v3_step_generic(V2Lane &s, uint32_t sb, int o, i
     s.F = ror1(s.F) ^ tf; s.R = rol1(s.R) ^ tr;
 }
 
-// park: three stores down the column; flush when the next candidate would reach the rows the scan still reads
-#define V3_CANDIDATE(ORD)                                                                                     \
+// park: three stores down the column; flush when the next candidate would reach the rows the scan still reads.
+// cq is the cursor minus ck = (l/4)*128 + 384, so that inside the word loop the test is simply cq <= wa (rows up to
+// wa + (l/4)*128 + 128 are still read, and a candidate needs three rows).
+#define V3_CANDIDATE(ORD, LIVE)                                                                               \
     if (min(H.fhi, H.rhi) <= bound_hi) {                                                                      \
         const bool fmin = (((uint64_t)H.fhi << 32) | H.flo) < (((uint64_t)H.rhi << 32) | H.rlo);              \
+        const uint32_t cpz = fma_add(cq, ck, kk);                                                             \
         sts32(cpz, fmin ? H.flo : H.rlo); sts32(cpz - 128u, fmin ? H.fhi : H.rhi); sts32(cpz - 256u, (uint32_t)(ORD)); \
-        cpz -= 384u;                                                                                          \
-        if (cpz <= live_a) { nloc = v3_flush(ctop, cpz, nloc, runm_l, cum_l, c_lo, xlo, xlim, lane, ev_a, tile, a, bound); cpz = ctop; } \
+        cq = fma_add(cq, 0u - 384u, kk);                                                                      \
+        if (cq <= (LIVE)) { nloc = v3_flush(ctop, cq + ck, nloc, runm_l, cum_l, c_lo, xlo, xlim, lane, ev_a, tile, a, bound); cq = ctop - ck; } \
     }
 
 __global__ void __launch_bounds__(V2_WARPS * 32, 32 / V2_WARPS) k_scan_minimizers_v3(const __grid_constant__ ScanArgs a, const __grid_constant__ ScanTablesV3 Tin) {
@@ -209,7 +255,10 @@ __global__ void __launch_bounds__(V2_WARPS * 32, 32 / V2_WARPS) k_scan_minimizer
     __shared__ uint32_t ev_cnt[V2_WARPS];
     for (uint32_t i = threadIdx.x; i < sizeof(ScanTablesV3) / 4; i += blockDim.x) ((uint32_t *)&T)[i] = ((const uint32_t *)&Tin)[i];
     __syncthreads();
-    if (threadIdx.x == 0) { T.opq[0] = 0x80000000u; T.opq[1] = 2u; T.opq[2] = (uint32_t)(a.bound >> 32); T.opq[3] = smem_addr(&T); }
+    if (threadIdx.x == 0) {
+        T.opq[0] = 0x80000000u; T.opq[1] = 2u; T.opq[2] = (uint32_t)(a.bound >> 32); T.opq[3] = smem_addr(&T);
+        T.opq[4] = 15u << 30; T.opq[5] = 1u; T.opq[6] = 4u;
+    }
     __syncthreads();
     const uint32_t lane = lane_id(), wid = threadIdx.x >> 5;
     const uint32_t ws_a = smem_addr(smem_raw + (size_t)wid * V3_WARP_BYTES);
@@ -224,6 +273,7 @@ __global__ void __launch_bounds__(V2_WARPS * 32, 32 / V2_WARPS) k_scan_minimizer
     // scalars read back through volatile shared loads so that ptxas keeps them in registers (see mq_scan_v2.cuh)
     const uint32_t ta = lds32(smem_addr(&T) + 464 + 12);
     const uint32_t k31 = lds32(ta + 464), k2 = lds32(ta + 464 + 4);
+    V3K kk; kk.c0 = lds32(ta + 464 + 16); kk.one = lds32(ta + 464 + 20); kk.four = lds32(ta + 464 + 24);
     const uint32_t bound_hi = lds32(ta + 464 + 8);
     const uint32_t ev_a = smem_addr(&ev_cnt[wid]);
     const uint32_t l = a.l;
@@ -257,10 +307,10 @@ __global__ void __launch_bounds__(V2_WARPS * 32, 32 / V2_WARPS) k_scan_minimizer
         // ---- stage + compact my chunk: one byte per homopolymer-run start ---------------------------
         const uint32_t c_lo = lane * Cs;                       // x' of my first byte
         V3Pend q; uint32_t bad;
-        v3_stage<true>(a, tlo, gs, c_lo, gpl, own_lo, own_hi, sb, cum_l, runm_l, ta, hpc, q, bad);
+        v3_stage<true>(a, tlo, gs, c_lo, gpl, own_lo, own_hi, sb, cum_l, runm_l, ta, hpc, kk, q, bad);
         if (__any_sync(0xffffffffu, bad != 0)) {               // some byte is not A/C/G/T: stage again with per-symbol flags
             __syncwarp();
-            v3_stage<false>(a, tlo, gs, c_lo, gpl, own_lo, own_hi, sb, cum_l, runm_l, ta, hpc, q, bad);
+            v3_stage<false>(a, tlo, gs, c_lo, gpl, own_lo, own_hi, sb, cum_l, runm_l, ta, hpc, kk, q, bad);
         }
         const uint32_t n = q.n8 >> 3;
         // my incomplete word is published in the top row of my column (free until candidates are parked), NOT in
@@ -386,22 +436,23 @@ __global__ void __launch_bounds__(V2_WARPS * 32, 32 / V2_WARPS) k_scan_minimizer
         }
 
         // ---- phase 2: scan of my own symbols; selected l-mers are parked, positions resolved after --------
-        uint32_t cpz = ctop;
-        uint32_t live_a = sb + 128u * ((uint32_t)lim >> 2) + 256u;   // a candidate's three rows must stay above the rows still read
+        const uint32_t lr = (l >> 2) * 128u, ck = lr + 384u;
+        uint32_t cq = ctop - ck;
+        const uint32_t live0 = sb + 128u * ((uint32_t)lim >> 2) + 256u - ck;   // outside the word loop: everything up to row lim/4 is live
         if (anyN) {
             for (; o >= 0; o--) {
                 st.F = ((uint64_t)H.fhi << 32) | H.flo; st.R = ((uint64_t)H.rhi << 32) | H.rlo;
                 v3_step_generic(st, sb, o, lim, l, ta);
                 H.flo = (uint32_t)st.F; H.fhi = (uint32_t)(st.F >> 32); H.rlo = (uint32_t)st.R; H.rhi = (uint32_t)(st.R >> 32);
-                V3_CANDIDATE(o)
+                V3_CANDIDATE(o, live0)
             }
         } else {
             for (; o >= 0 && ((o + 1) & 3); o--) {                // bring o+1 to a multiple of 4
                 const uint32_t off = lds8(v3_baddr(sb, (uint32_t)o)) | (lds8(v3_baddr(sb, (uint32_t)o + l)) << 2);
                 v3_step(H, v3_tab(ta, off), k31, k2);
-                V3_CANDIDATE(o)
+                V3_CANDIDATE(o, live0)
             }
-            const uint32_t lr = (l >> 2) * 128u, ls = 8 * (l & 3);
+            const uint32_t ls = 8 * (l & 3);
             int w = ((o + 1) >> 2) - 1;
             // software pipeline: the three stream words of the next iteration are loaded one iteration ahead,
             // and the four table loads of an iteration are issued before its four dependent hash steps
@@ -410,17 +461,16 @@ __global__ void __launch_bounds__(V2_WARPS * 32, 32 / V2_WARPS) k_scan_minimizer
             if (w >= 0) { inw = lds32(wa); ow0 = lds32(wa + lr); ow1 = lds32(wa + lr + 128); }
             for (; w >= 0; w--) {
                 const uint32_t comb = inw | (__funnelshift_r(ow0, ow1, ls) << 2);   // per byte: in*16 + out*64 (no N in this tile)
-                const uint4 t3 = v3_tab(ta, (comb >> 24)), t2 = v3_tab(ta, ((comb >> 16) & 0xFFu));
-                const uint4 t1 = v3_tab(ta, ((comb >> 8) & 0xFFu)), t0 = v3_tab(ta, (comb & 0xFFu));
+                const uint4 t3 = v3_tab(ta, prmt(comb, 0u, 0x4443u)), t2 = v3_tab(ta, prmt(comb, 0u, 0x4442u));
+                const uint4 t1 = v3_tab(ta, prmt(comb, 0u, 0x4441u)), t0 = v3_tab(ta, prmt(comb, 0u, 0x4440u));
                 if (w > 0) { wa -= 128; inw = lds32(wa); ow0 = lds32(wa + lr); ow1 = lds32(wa + lr + 128); }
-                live_a = wa + lr + 384u;                                 // rows <= wa + lr + 128 are still read
-                v3_step(H, t3, k31, k2); V3_CANDIDATE(4 * w + 3)
-                v3_step(H, t2, k31, k2); V3_CANDIDATE(4 * w + 2)
-                v3_step(H, t1, k31, k2); V3_CANDIDATE(4 * w + 1)
-                v3_step(H, t0, k31, k2); V3_CANDIDATE(4 * w)
+                v3_step(H, t3, k31, k2); V3_CANDIDATE(4 * w + 3, wa)
+                v3_step(H, t2, k31, k2); V3_CANDIDATE(4 * w + 2, wa)
+                v3_step(H, t1, k31, k2); V3_CANDIDATE(4 * w + 1, wa)
+                v3_step(H, t0, k31, k2); V3_CANDIDATE(4 * w, wa)
             }
         }
-        if (cpz != ctop) nloc = v3_flush(ctop, cpz, nloc, runm_l, cum_l, c_lo, xlo, xlim, lane, ev_a, tile, a, bound);
+        if (cq != ctop - ck) nloc = v3_flush(ctop, cq + ck, nloc, runm_l, cum_l, c_lo, xlo, xlim, lane, ev_a, tile, a, bound);
         __syncwarp();
         a.lane_cnt[(uint64_t)tile * 32 + lane] = (uint16_t)nloc;
         if (lane == 0) a.tile_cnt[tile] = lds32(ev_a);

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Small end-to-end run meant to be executed under compute-sanitizer (memcheck / racecheck / initcheck):
-adversarial minimizer inputs, index build, segment build, mapping, both scan kernel generations."""
+adversarial minimizer inputs, index build, segment build, mapping, all scan kernel generations."""
 import os
 import sys
 
@@ -14,8 +14,9 @@ def main():
     from mapquik_b200 import Index, Params, sim
     import test_gpu_parity as T
     rng = np.random.default_rng(7)
-    for v1 in ("0", "1"):
-        os.environ["MQ_SCAN_V1"] = v1
+    for gen in ("v3", "v2", "v1"):
+        os.environ["MQ_SCAN_V1"] = "1" if gen == "v1" else "0"
+        os.environ["MQ_SCAN_V2"] = "1" if gen == "v2" else "0"
         buf, offs = T.concat_raw(T.adversarial_seqs(rng))
         for p in (Params(), Params(l=16, density=0.2, use_hpc=False), Params(l=5, density=1.0)):
             T.check_minimizers(buf, offs, p)
