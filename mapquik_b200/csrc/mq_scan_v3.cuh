@@ -244,7 +244,7 @@ __device__ __forceinline__ void v3_step_generic(V2Lane &s, uint32_t sb, int o, i
     if (min(H.fhi, H.rhi) <= bound_hi) {                                                                      \
         const bool fmin = (((uint64_t)H.fhi << 32) | H.flo) < (((uint64_t)H.rhi << 32) | H.rlo);              \
         const uint32_t cpz = fma_add(cq, ck, kk);                                                             \
-        sts32(cpz, fmin ? H.flo : H.rlo); sts32(cpz - 128u, fmin ? H.fhi : H.rhi); sts32(cpz - 256u, (uint32_t)(ORD)); \
+        sts32(cpz, fmin ? H.flo : H.rlo); sts32(cpz - 128u, min(H.fhi, H.rhi)); sts32(cpz - 256u, (uint32_t)(ORD)); \
         cq = fma_add(cq, 0u - 384u, kk);                                                                      \
         if (cq <= (LIVE)) { nloc = v3_flush(ctop, cq + ck, nloc, runm_l, cum_l, c_lo, xlo, xlim, lane, ev_a, tile, a, bound); cq = ctop - ck; } \
     }
