@@ -58,6 +58,17 @@ def adversarial_seqs(rng):
     w = random_dna(rng, 9000).copy(); w[-2000:] = ord("G"); seqs.append(w)   # record ends in a long run
     v = random_dna(rng, 9000).copy(); v[:3000] = ord("C"); seqs.append(v)    # record starts with a long run
     seqs.append(np.frombuffer(b"acgtnACGT" * 500, np.uint8))                # lower case is NOT folded at the ABI
+    # islands of a few symbols between runs longer than a lane chunk: most lanes of a tile hold no symbol at all, the
+    # context of a lane comes from several sparse streams further right (v3: ballot walk over non-empty streams)
+    parts = []
+    for i in range(120):
+        parts.append(np.full(int(rng.integers(100, 700)), ord("ACGTN"[i % 5]), np.uint8))
+        parts.append(random_dna(rng, int(rng.integers(1, 40))))
+    seqs.append(np.concatenate(parts))
+    # IUPAC / garbage bytes, including ones that share their low bits with A, C, G, T (E, P, R, V, 0xC1, ...)
+    q = random_dna(rng, 6000).copy()
+    q[rng.integers(0, 6000, 300)] = np.frombuffer(b"EPRVBDHKMSWYU*-\xc1\xc3\xc7\xd4\x01\x00", np.uint8)[rng.integers(0, 21, 300)]
+    seqs.append(q)
     return seqs
 
 
