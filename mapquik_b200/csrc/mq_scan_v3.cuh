@@ -141,12 +141,13 @@ __device__ __forceinline__ uint32_t v3_raw_offset(uint32_t runm_l, uint32_t cum_
 // resolve and emit the candidates parked in rows (cpz, top] of the lane's column, oldest first
 __device__ __noinline__ uint32_t v3_flush(uint32_t top, uint32_t cpz, uint32_t j0, uint32_t runm_l, uint32_t cum_l,
                                           uint32_t c_lo, uint32_t xlo, uint32_t xlim, uint32_t lane, uint32_t ev_a, uint32_t tile,
-                                          const ScanArgs &a, uint64_t bound) {
+                                          const ScanArgs &a, uint64_t bound, int o2) {
     uint32_t j = j0;
     for (uint32_t p = top; p > cpz; p -= 384u) {
         const uint64_t h = ((uint64_t)lds32(p - 128u) << 32) | lds32(p);
         if (h >= bound) continue;                      // parked on the hi-word pre-filter only: exact test here
         const uint32_t o = lds32(p - 256u);
+        if ((int)o > o2) continue;                     // a context symbol, or a window the record end leaves incomplete
         const uint32_t x = c_lo + v3_raw_offset(runm_l, cum_l, o);
         if (x - xlo < xlim - xlo) { v2_emit(x, h, lane, j, ev_a, tile, a); j++; }
     }
@@ -246,7 +247,7 @@ __device__ __forceinline__ void v3_step_generic(V2Lane &s, uint32_t sb, int o, i
         const uint32_t cpz = fma_add(cq, ck, kk);                                                             \
         sts32(cpz, fmin ? H.flo : H.rlo); sts32(cpz - 128u, min(H.fhi, H.rhi)); sts32(cpz - 256u, (uint32_t)(ORD)); \
         cq = fma_add(cq, 0u - 384u, kk);                                                                      \
-        if (cq <= (LIVE)) { nloc = v3_flush(ctop, cq + ck, nloc, runm_l, cum_l, c_lo, xlo, xlim, lane, ev_a, tile, a, bound); cq = ctop - ck; } \
+        if (cq <= (LIVE)) { nloc = v3_flush(ctop, cq + ck, nloc, runm_l, cum_l, c_lo, xlo, xlim, lane, ev_a, tile, a, bound, o2); cq = ctop - ck; } \
     }
 
 __global__ void __launch_bounds__(V2_WARPS * 32, 32 / V2_WARPS) k_scan_minimizers_v3(const __grid_constant__ ScanArgs a, const __grid_constant__ ScanTablesV3 Tin) {
@@ -380,6 +381,7 @@ __global__ void __launch_bounds__(V2_WARPS * 32, 32 / V2_WARPS) k_scan_minimizer
                     P = __funnelshift_l(x, 0u, sh0);
                 }
                 sts32(wp0 + 128 * 8, P);
+                sts32(wp0 + 128 * 9, 0u);
             } else {
                 // record end or short streams: walk the non-empty streams to my right (the halo last), word by word
                 uint32_t need = l - 1, rest = lane < 31 ? nz >> (lane + 1) : 0u, jb = lane + 1;
@@ -399,68 +401,50 @@ __global__ void __launch_bounds__(V2_WARPS * 32, 32 / V2_WARPS) k_scan_minimizer
                     need -= take; c += take;
                 }
                 sts32(q.wp, q.P);                               // the incomplete word, zero above its bytes
-                for (uint32_t za = q.wp + 128; za <= wp0 + 128 * 8; za += 128) sts32(za, 0u);
+                for (uint32_t za = q.wp + 128; za <= wp0 + 128 * 9; za += 128) sts32(za, 0u);
             }
         }
         __syncwarp();
 
-        // ---- phase 1: warm-up over context and record-final symbols, no emission ----------------------
+        // ---- phase 1 + 2: one pass down my column, row by row ------------------------------------------
+        // Rows above the one holding my last own symbol are warm-up: the outgoing symbol of those steps lies beyond the
+        // stream, i.e. it is a phantom 'A' (code 0), and the pair-table row for out == 0 is the whole step.  Zero bytes
+        // behind the context are phantom 'A's entering a window of phantom 'A's, which leaves the state unchanged, so
+        // whole rows are stepped.  From that row down every step may park a candidate; the up to three context symbols
+        // sharing the row, and windows a record end leaves incomplete, are dropped at resolve time (ordinal > o2).
         V2Lane st; st.F = T.F0; st.R = T.R0;
         const int lim = (int)(n + c);                           // symbols available in my logical stream
-        int o = lim - 1;
         const int o2 = max(-1, min((int)n - 1, lim - (int)l));  // first ordinal whose window is complete and mine
         V2H H;
-        if (anyN) {
-            for (; o > o2; o--) v3_step_generic(st, sb, o, lim, l, ta);
-            H.flo = (uint32_t)st.F; H.fhi = (uint32_t)(st.F >> 32); H.rlo = (uint32_t)st.R; H.rhi = (uint32_t)(st.R >> 32);
-        } else {
-            // the outgoing symbol of every warm-up step lies beyond the stream, i.e. it is a phantom 'A' (code 0): the
-            // pair-table row for out == 0 is the whole step.  The zero bytes behind the context are phantom 'A's
-            // entering a window of phantom 'A's, which leaves the state unchanged, so whole words are stepped.
-            H.flo = (uint32_t)st.F; H.fhi = (uint32_t)(st.F >> 32); H.rlo = (uint32_t)st.R; H.rhi = (uint32_t)(st.R >> 32);
-            if (n != 0) {
-                uint32_t ra = wp0 + 128u * ((l + 2) >> 2);      // one row past the last context word
-                uint32_t hi = lds32(ra);
-                for (; ra > wp0; ra -= 128u) {
-                    const uint32_t lo = lds32(ra - 128u);
-                    const uint32_t x = __funnelshift_r(lo, hi, sh0);
-                    hi = lo;
-                    v3_step(H, v3_tab(ta, (x >> 24)), k31, k2);
-                    v3_step(H, v3_tab(ta, ((x >> 16) & 0xFFu)), k31, k2);
-                    v3_step(H, v3_tab(ta, ((x >> 8) & 0xFFu)), k31, k2);
-                    v3_step(H, v3_tab(ta, (x & 0xFFu)), k31, k2);
-                }
-            }
-            for (o = (int)n - 1; o > o2; o--)                    // record end: my last symbols have no complete window
-                v3_step(H, v3_tab(ta, lds8(v3_baddr(sb, (uint32_t)o))), k31, k2);
-        }
-
-        // ---- phase 2: scan of my own symbols; selected l-mers are parked, positions resolved after --------
+        H.flo = (uint32_t)st.F; H.fhi = (uint32_t)(st.F >> 32); H.rlo = (uint32_t)st.R; H.rhi = (uint32_t)(st.R >> 32);
         const uint32_t lr = (l >> 2) * 128u, ck = lr + 384u;
         uint32_t cq = ctop - ck;
-        const uint32_t live0 = sb + 128u * ((uint32_t)lim >> 2) + 256u - ck;   // outside the word loop: everything up to row lim/4 is live
         if (anyN) {
+            const uint32_t live0 = sb + 128u * ((uint32_t)lim >> 2) + 256u - ck;   // everything up to row lim/4 stays live
+            int o = lim - 1;
+            for (; o > o2; o--) v3_step_generic(st, sb, o, lim, l, ta);
             for (; o >= 0; o--) {
-                st.F = ((uint64_t)H.fhi << 32) | H.flo; st.R = ((uint64_t)H.rhi << 32) | H.rlo;
                 v3_step_generic(st, sb, o, lim, l, ta);
                 H.flo = (uint32_t)st.F; H.fhi = (uint32_t)(st.F >> 32); H.rlo = (uint32_t)st.R; H.rhi = (uint32_t)(st.R >> 32);
                 V3_CANDIDATE(o, live0)
             }
-        } else {
-            for (; o >= 0 && ((o + 1) & 3); o--) {                // bring o+1 to a multiple of 4
-                const uint32_t off = lds8(v3_baddr(sb, (uint32_t)o)) | (lds8(v3_baddr(sb, (uint32_t)o + l)) << 2);
-                v3_step(H, v3_tab(ta, off), k31, k2);
-                V3_CANDIDATE(o, live0)
+        } else if (n != 0) {
+            int w = (lim - 1) >> 2;
+            const int wm = (int)(n - 1) >> 2;
+            uint32_t wa = sb + 128u * (uint32_t)w;
+            for (; w > wm; w--, wa -= 128u) {
+                const uint32_t x = lds32(wa);
+                v3_step(H, v3_tab(ta, (x >> 24)), k31, k2);
+                v3_step(H, v3_tab(ta, ((x >> 16) & 0xFFu)), k31, k2);
+                v3_step(H, v3_tab(ta, ((x >> 8) & 0xFFu)), k31, k2);
+                v3_step(H, v3_tab(ta, (x & 0xFFu)), k31, k2);
             }
             const uint32_t ls = 8 * (l & 3);
-            int w = ((o + 1) >> 2) - 1;
             // software pipeline: the three stream words of the next iteration are loaded one iteration ahead,
-            // and the four table loads of an iteration are issued before its four dependent hash steps
-            uint32_t inw = 0, ow0 = 0, ow1 = 0;
-            uint32_t wa = sb + 128u * (uint32_t)(w < 0 ? 0 : w);
-            if (w >= 0) { inw = lds32(wa); ow0 = lds32(wa + lr); ow1 = lds32(wa + lr + 128); }
+            // and the table rows of an iteration are issued before its four dependent hash steps
+            uint32_t inw = lds32(wa), ow0 = lds32(wa + lr), ow1 = lds32(wa + lr + 128);
             for (; w >= 0; w--) {
-                const uint32_t comb = inw | (__funnelshift_r(ow0, ow1, ls) << 2);   // per byte: in*16 + out*64 (no N in this tile)
+                const uint32_t comb = inw | (__funnelshift_r(ow0, ow1, ls) << 2);   // per byte: in + out * 4, pre-scaled (no N in this tile)
                 const uint4 t3 = v3_tab(ta, prmt(comb, 0u, 0x4443u)), t2 = v3_tab(ta, prmt(comb, 0u, 0x4442u));
                 const uint4 t1 = v3_tab(ta, prmt(comb, 0u, 0x4441u)), t0 = v3_tab(ta, prmt(comb, 0u, 0x4440u));
                 if (w > 0) { wa -= 128; inw = lds32(wa); ow0 = lds32(wa + lr); ow1 = lds32(wa + lr + 128); }
@@ -470,7 +454,7 @@ __global__ void __launch_bounds__(V2_WARPS * 32, 32 / V2_WARPS) k_scan_minimizer
                 v3_step(H, t0, k31, k2); V3_CANDIDATE(4 * w, wa)
             }
         }
-        if (cq != ctop - ck) nloc = v3_flush(ctop, cq + ck, nloc, runm_l, cum_l, c_lo, xlo, xlim, lane, ev_a, tile, a, bound);
+        if (cq != ctop - ck) nloc = v3_flush(ctop, cq + ck, nloc, runm_l, cum_l, c_lo, xlo, xlim, lane, ev_a, tile, a, bound, o2);
         __syncwarp();
         a.lane_cnt[(uint64_t)tile * 32 + lane] = (uint16_t)nloc;
         if (lane == 0) a.tile_cnt[tile] = lds32(ev_a);
