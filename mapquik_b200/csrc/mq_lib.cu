@@ -269,7 +269,7 @@ int run_scan(mq_ctx *c, const uint8_t *d_seqs, const uint64_t *d_offs, uint32_t 
                     { const char *e = getenv("MQ_SCAN_PAD"); if (e) smem += (size_t)atoi(e); }   // occupancy experiments
                     if (c->v2_ctas_per_sm == 0) {      // persistent grid = every CTA the chip can hold
                         int nb = 0;
-                        const void *kern = c->scan_v2 ? (const void *)k_scan_minimizers_v2 : (const void *)k_scan_minimizers_v3;
+                        const void *kern = c->scan_v2 ? (const void *)k_scan_minimizers_v2 : (c->p.use_hpc ? (const void *)k_scan_minimizers_v3<true> : (const void *)k_scan_minimizers_v3<false>);
                         if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                         cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
                         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, V2_WARPS * 32, smem) != cudaSuccess || nb < 1) nb = 1;
@@ -278,7 +278,8 @@ int run_scan(mq_ctx *c, const uint8_t *d_seqs, const uint64_t *d_offs, uint32_t 
                     }
                     const uint32_t grid = std::min<uint32_t>(ctas_needed, (uint32_t)(c->n_sm * c->v2_ctas_per_sm));
                     if (c->scan_v2) k_scan_minimizers_v2<<<grid, V2_WARPS * 32, smem, c->stream>>>(a, c->tab2);
-                    else k_scan_minimizers_v3<<<grid, V2_WARPS * 32, smem, c->stream>>>(a, c->tab3);
+                    else if (c->p.use_hpc) k_scan_minimizers_v3<true><<<grid, V2_WARPS * 32, smem, c->stream>>>(a, c->tab3);
+                    else k_scan_minimizers_v3<false><<<grid, V2_WARPS * 32, smem, c->stream>>>(a, c->tab3);
                 }
             }
             c->launches += 2;

@@ -250,6 +250,8 @@ __device__ __forceinline__ void v3_step_generic(V2Lane &s, uint32_t sb, int o, i
         if (cq <= (LIVE)) { nloc = v3_flush(ctop, cq + ck, nloc, runm_l, cum_l, c_lo, xlo, xlim, lane, ev_a, tile, a, bound, o2); cq = ctop - ck; } \
     }
 
+// HPC is a compile-time flag (two instantiations): the run-start digest then has no per-word branch
+template <bool HPC>
 __global__ void __launch_bounds__(V2_WARPS * 32, 32 / V2_WARPS) k_scan_minimizers_v3(const __grid_constant__ ScanArgs a, const __grid_constant__ ScanTablesV3 Tin) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __shared__ __align__(256) ScanTablesV3 T;
@@ -278,7 +280,7 @@ __global__ void __launch_bounds__(V2_WARPS * 32, 32 / V2_WARPS) k_scan_minimizer
     const uint32_t bound_hi = lds32(ta + 464 + 8);
     const uint32_t ev_a = smem_addr(&ev_cnt[wid]);
     const uint32_t l = a.l;
-    const bool hpc = a.use_hpc != 0;
+    constexpr bool hpc = HPC;
     const uint64_t bound = a.bound;
 
     for (;;) {

@@ -25,11 +25,23 @@ template <int OP> __device__ __forceinline__ void op(uint32_t &a, uint32_t &b, u
     if (OP == 11) { asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a) : "r"(b), "r"(k));         // 2 ALU + 1 wide
                     asm volatile("shf.l.wrap.b32 %0, %0, %1, 1;" : "+r"(a) : "r"(b));
                     uint64_t w; asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(w) : "r"(b), "r"(k)); b = (uint32_t)(w >> 32) ^ (uint32_t)w; }
+    if (OP == 13) { asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a) : "r"(b), "r"(k));         // 2 ALU: LOP3 + SHF
+                    asm volatile("shf.l.wrap.b32 %0, %0, %1, 1;" : "+r"(b) : "r"(a)); }
+    if (OP == 14) { asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a) : "r"(b), "r"(k));         // 2 ALU + 1 IMAD
+                    asm volatile("shf.l.wrap.b32 %0, %0, %1, 1;" : "+r"(a) : "r"(b));
+                    asm volatile("mad.lo.u32 %0, %0, %2, %1;" : "+r"(b) : "r"(a), "r"(k)); }
+    if (OP == 15) { asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a) : "r"(b), "r"(k));         // 1 ALU + 1 IMAD.HI
+                    asm volatile("mad.hi.u32 %0, %0, %2, %1;" : "+r"(b) : "r"(a), "r"(k)); }
+    if (OP == 16) { asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a) : "r"(b), "r"(k));         // 3 ALU + 1 IMAD
+                    asm volatile("shf.l.wrap.b32 %0, %0, %1, 1;" : "+r"(a) : "r"(b));
+                    asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a) : "r"(b), "r"(k));
+                    asm volatile("mad.lo.u32 %0, %0, %2, %1;" : "+r"(b) : "r"(a), "r"(k)); }
     if (OP == 12) { uint64_t w; asm volatile("mad.wide.u32 %0, %1, %2, %3;" : "=l"(w) : "r"(a), "r"(k), "l"(((uint64_t)b << 32) | a)); a = (uint32_t)w; b = (uint32_t)(w >> 32); }
 }
 static const char *NAMES[] = {"LOP3", "SHF.L.W", "IMAD", "IMAD.WIDE.U32", "IMAD.HI.U32", "PRMT", "VIMNMX", "POPC", "IADD",
-                              "LOP3 + (IMAD.WIDE+LOP3)", "LOP3 + IMAD", "LOP3+SHF + (IMAD.WIDE+LOP3)", "IMAD.WIDE (mad)"};
-static const int NINSTR[] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 3, 2, 4, 1};
+                              "LOP3 + (IMAD.WIDE+LOP3)", "LOP3 + IMAD", "LOP3+SHF + (IMAD.WIDE+LOP3)", "IMAD.WIDE (mad)",
+                              "LOP3 + SHF", "LOP3+SHF + IMAD", "LOP3 + IMAD.HI", "LOP3+SHF+LOP3 + IMAD"};
+static const int NINSTR[] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 3, 2, 4, 1, 2, 3, 2, 4};
 
 template <int OP> __global__ void k(uint32_t *out, uint32_t k0, long long *cyc) {
     uint32_t a[ILP], b[ILP];
@@ -46,16 +58,23 @@ template <int OP> __global__ void k(uint32_t *out, uint32_t k0, long long *cyc) 
     if (threadIdx.x == 0 && blockIdx.x == 0) *cyc = t1 - t0;
 }
 
+static int g_threads = 1024;
 template <int OP> void run(uint32_t *d, long long *dc) {
-    const int threads = 1024, blocks = 148 * 2;
+    const int threads = g_threads, blocks = 148 * 2;
     k<OP><<<blocks, threads>>>(d, 0x80000000u, dc);
     cudaDeviceSynchronize();
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0);
     k<OP><<<blocks, threads>>>(d, 0x80000000u, dc);
+    cudaEventRecord(e1);
     cudaDeviceSynchronize();
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
     long long c; cudaMemcpy(&c, dc, 8, cudaMemcpyDeviceToHost);
     // per SM: 2 blocks x 32 warps resident; warp-instrs per SM = 64 * ITER * ILP * NINSTR
-    double wi = 64.0 * ITER * ILP * NINSTR[OP];
-    printf("%-32s %6.3f warp-instr/clk/SM  (%lld clk)\n", NAMES[OP], wi / (double)c, c);
+    double wi = 2.0 * (threads / 32) * ITER * ILP * NINSTR[OP];
+    // clock64() of one CTA and, independently, CUDA events around the whole launch (148 SMs, 2 CTAs each)
+    printf("%-32s %6.3f warp-instr/clk64/SM  (%lld clk64)   %7.1f G warp-instr/s chip-wide by events (%.3f ms)\n", NAMES[OP], wi / (double)c, c,
+           wi * 148.0 / (ms * 1e-3) / 1e9, ms);
 }
 
 int main() {
@@ -63,6 +82,7 @@ int main() {
     cudaMalloc(&d, 148 * 2 * 1024 * 4); cudaMalloc(&dc, 8);
     run<0>(d, dc); run<1>(d, dc); run<2>(d, dc); run<3>(d, dc); run<4>(d, dc); run<5>(d, dc); run<6>(d, dc);
     run<7>(d, dc); run<8>(d, dc); run<9>(d, dc); run<10>(d, dc); run<11>(d, dc); run<12>(d, dc);
+    run<13>(d, dc); run<14>(d, dc); run<15>(d, dc); run<16>(d, dc);
     cudaError_t e = cudaGetLastError();
     printf("status: %s\n", cudaGetErrorString(e));
     return 0;
