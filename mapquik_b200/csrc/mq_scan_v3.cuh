@@ -52,6 +52,22 @@ __device__ __forceinline__ uint4 v3_tab(uint32_t ta, uint32_t off) {
 __device__ __forceinline__ void v3_step(V2H &h, uint4 t, uint32_t k31, uint32_t k2) {
     v2_step(h, ((uint64_t)t.y << 32) | t.x, ((uint64_t)t.w << 32) | t.z, k31, k2);
 }
+// MQ_V3_PROBE_ALU / MQ_V3_PROBE_FMA (default 0): N extra LOP3 / IMAD instructions per hash step of the hot loop, on an
+// accumulator of their own.  Only for the "which pipe binds" experiment in profiles/README.md: the slope of kernel time
+// against N tells whether ALU-pipe slots, FMA-pipe slots or plain issue slots are the scarce resource.
+#ifndef MQ_V3_PROBE_ALU
+#define MQ_V3_PROBE_ALU 0
+#endif
+#ifndef MQ_V3_PROBE_FMA
+#define MQ_V3_PROBE_FMA 0
+#endif
+#if MQ_V3_PROBE_ALU || MQ_V3_PROBE_FMA
+#define V3_PROBE(T4)                                                                                          \
+    { _Pragma("unroll") for (int i_ = 0; i_ < MQ_V3_PROBE_ALU; i_++) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(probe_acc) : "r"((T4).y), "r"((T4).z)); \
+      _Pragma("unroll") for (int i_ = 0; i_ < MQ_V3_PROBE_FMA; i_++) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(probe_acc) : "r"((T4).y), "r"((T4).z)); }
+#else
+#define V3_PROBE(T4)
+#endif
 // MQ_V3_FMA = 1: additions / small multiplies whose result the integer ALU pipe would otherwise produce are issued as
 // IMAD / IMAD.HI with multipliers read from shared memory (opaque to ptxas, which would strength-reduce literal
 // multipliers back into shifts and adds): the ALU pipe is this kernel's bound, the FMA pipe is mostly idle.
@@ -442,6 +458,7 @@ __global__ void __launch_bounds__(V2_WARPS * 32, 32 / V2_WARPS) k_scan_minimizer
                 v3_step(H, v3_tab(ta, (x & 0xFFu)), k31, k2);
             }
             const uint32_t ls = 8 * (l & 3);
+            uint32_t probe_acc = lane; (void)probe_acc;
             // software pipeline: the three stream words of the next iteration are loaded one iteration ahead,
             // and the table rows of an iteration are issued before its four dependent hash steps
             uint32_t inw = lds32(wa), ow0 = lds32(wa + lr), ow1 = lds32(wa + lr + 128);
@@ -450,11 +467,14 @@ __global__ void __launch_bounds__(V2_WARPS * 32, 32 / V2_WARPS) k_scan_minimizer
                 const uint4 t3 = v3_tab(ta, prmt(comb, 0u, 0x4443u)), t2 = v3_tab(ta, prmt(comb, 0u, 0x4442u));
                 const uint4 t1 = v3_tab(ta, prmt(comb, 0u, 0x4441u)), t0 = v3_tab(ta, prmt(comb, 0u, 0x4440u));
                 if (w > 0) { wa -= 128; inw = lds32(wa); ow0 = lds32(wa + lr); ow1 = lds32(wa + lr + 128); }
-                v3_step(H, t3, k31, k2); V3_CANDIDATE(4 * w + 3, wa)
-                v3_step(H, t2, k31, k2); V3_CANDIDATE(4 * w + 2, wa)
-                v3_step(H, t1, k31, k2); V3_CANDIDATE(4 * w + 1, wa)
-                v3_step(H, t0, k31, k2); V3_CANDIDATE(4 * w, wa)
+                v3_step(H, t3, k31, k2); V3_PROBE(t3) V3_CANDIDATE(4 * w + 3, wa)
+                v3_step(H, t2, k31, k2); V3_PROBE(t2) V3_CANDIDATE(4 * w + 2, wa)
+                v3_step(H, t1, k31, k2); V3_PROBE(t1) V3_CANDIDATE(4 * w + 1, wa)
+                v3_step(H, t0, k31, k2); V3_PROBE(t0) V3_CANDIDATE(4 * w, wa)
             }
+#if MQ_V3_PROBE_ALU || MQ_V3_PROBE_FMA
+            if (probe_acc == 0x9E3779B9u && l == 77u) a.tile_cnt[tile] = probe_acc;   // never true (l <= 32): keeps the probe instructions
+#endif
         }
         if (cq != ctop - ck) nloc = v3_flush(ctop, cq + ck, nloc, runm_l, cum_l, c_lo, xlo, xlim, lane, ev_a, tile, a, bound, o2);
         __syncwarp();
