@@ -73,7 +73,10 @@ def adversarial_seqs(rng):
 
 
 @pytest.mark.parametrize("l,density,hpc", [(31, 0.01, True), (16, 0.01, True), (31, 0.05, False), (5, 0.3, True),
-                                           (32, 0.02, True), (2, 0.5, True), (25, 1.0, True)])
+                                           (32, 0.02, True), (2, 0.5, True), (25, 1.0, True),
+                                           # full 128-symbol lane streams with the longest window: the least spare rows
+                                           # for parked candidates (v3), first sparse, then every l-mer selected
+                                           (32, 0.05, False), (32, 1.0, False)])
 def test_minimizers_adversarial(l, density, hpc, scan_version):
     rng = np.random.default_rng(7)
     buf, offs = concat_raw(adversarial_seqs(rng))
