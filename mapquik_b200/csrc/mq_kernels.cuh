@@ -797,37 +797,54 @@ __device__ __forceinline__ void write_hit(const ChainArgs &a, uint32_t r, bool o
 
 // thread per read: almost every read has a handful of Matches, for which a warp per read wastes 31 lanes.
 // Reads with more than CHAIN_SMALL Matches are queued for the warp-per-read kernel below.
+// The body is instantiated for a compile-time bound NMAX on the number of Matches: for 1..4 (nearly every read) all loops
+// unroll and the Matches stay in registers; a runtime-indexed array would live in local memory, and its dependent
+// loads were what this kernel spent its time on (long-scoreboard stalls, 10 % issue utilisation).
+template <int NMAX>
+__device__ __forceinline__ void chain_thread(const ChainArgs &a, uint32_t r, uint32_t n, const MatchRec *ms) {
+    M6 m[NMAX];
+#pragma unroll
+    for (int i = 0; i < NMAX; i++) if (i < (int)n) m[i] = load_match(ms + i); else { m[i] = M6{}; m[i].ref = 0xFFFFFFFFu; }
+    uint64_t best_score = 0, second = 0; uint32_t groups = 0;
+    uint32_t b_ref = 0, b_rc = 0, b_mapq = 0; uint64_t b_qs = 0, b_qe = 0, b_rs = 0, b_re = 0;
+#pragma unroll
+    for (int i = 0; i < NMAX; i++) {
+        if (i >= (int)n) break;
+        const uint32_t ref = m[i].ref;
+        bool seen = false;
+#pragma unroll
+        for (int q = 0; q < i; q++) seen |= m[q].ref == ref;
+        if (seen) continue;                                             // not the first Match of its reference
+        uint32_t bc = 0, glen = 0; M6 mb = m[i];                        // C1: first Match with the strictly greatest count
+#pragma unroll
+        for (int q = i; q < NMAX; q++) if (q < (int)n && m[q].ref == ref) { glen++; if (m[q].cnt > bc) { bc = m[q].cnt; mb = m[q]; } }
+        uint32_t lenf = 0; uint64_t score = 0; M6 mf = m[i], ml = m[i]; // C3: keep what is compatible with the largest
+#pragma unroll
+        for (int q = i; q < NMAX; q++)
+            if (q < (int)n && m[q].ref == ref && (glen <= 1 || compatible(mb, m[q], a.g))) { if (!lenf) mf = m[q]; ml = m[q]; lenf++; score += m[q].cnt; }
+        if (!lenf) continue;
+        const uint32_t mapq = ((a.s != 0 && a.c != 0) && (lenf >= a.c || score >= a.s)) ? 60u : 0u;          // C4
+        const uint32_t rc = mf.rc;
+        const uint64_t qs = mf.qs, qe = (uint64_t)ml.qe - 1;
+        uint64_t rs, re;
+        if (rc && lenf > 1) { rs = ml.rs; re = (uint64_t)mf.re - 1; } else { rs = mf.rs; re = (uint64_t)ml.re - 1; }
+        groups++;
+        if (score > best_score) { second = best_score; best_score = score; b_ref = ref; b_rc = rc; b_mapq = mapq; b_qs = qs; b_qe = qe; b_rs = rs; b_re = re; }
+        else if (score > second) second = score;
+    }
+    write_hit(a, r, groups == 1 || (groups > 1 && best_score != second), b_ref, b_rc, b_mapq, b_qs, b_qe, b_rs, b_re, best_score);
+}
+
 __global__ void __launch_bounds__(128) k_chain_small(ChainArgs a) {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= a.n_reads) return;
     const uint32_t n = a.n_matches[r];
     if (n > CHAIN_SMALL) { a.big_list[atomicAdd(a.big_count, 1u)] = r; return; }
     const MatchRec *ms = a.matches + a.seq_off[r];
-    M6 m[CHAIN_SMALL];
-    for (uint32_t i = 0; i < n; i++) m[i] = load_match(ms + i);
-    uint64_t best_score = 0, second = 0; uint32_t groups = 0;
-    uint32_t b_ref = 0, b_rc = 0, b_mapq = 0; uint64_t b_qs = 0, b_qe = 0, b_rs = 0, b_re = 0;
-    for (uint32_t i = 0; i < n; i++) {
-        const uint32_t ref = m[i].ref;
-        bool seen = false;
-        for (uint32_t q = 0; q < i; q++) seen |= m[q].ref == ref;
-        if (seen) continue;                                             // not the first Match of its reference
-        uint32_t bc = 0, bi = i, glen = 0;                              // C1: first Match with the strictly greatest count
-        for (uint32_t q = i; q < n; q++) if (m[q].ref == ref) { glen++; if (m[q].cnt > bc) { bc = m[q].cnt; bi = q; } }
-        uint32_t lenf = 0, fi = 0, li = 0; uint64_t score = 0;         // C3: keep what is compatible with the largest
-        for (uint32_t q = i; q < n; q++)
-            if (m[q].ref == ref && (glen <= 1 || compatible(m[bi], m[q], a.g))) { if (!lenf) fi = q; li = q; lenf++; score += m[q].cnt; }
-        if (!lenf) continue;
-        const uint32_t mapq = ((a.s != 0 && a.c != 0) && (lenf >= a.c || score >= a.s)) ? 60u : 0u;          // C4
-        const uint32_t rc = m[fi].rc;
-        const uint64_t qs = m[fi].qs, qe = (uint64_t)m[li].qe - 1;
-        uint64_t rs, re;
-        if (rc && lenf > 1) { rs = m[li].rs; re = (uint64_t)m[fi].re - 1; } else { rs = m[fi].rs; re = (uint64_t)m[li].re - 1; }
-        groups++;
-        if (score > best_score) { second = best_score; best_score = score; b_ref = ref; b_rc = rc; b_mapq = mapq; b_qs = qs; b_qe = qe; b_rs = rs; b_re = re; }
-        else if (score > second) second = score;
-    }
-    write_hit(a, r, groups == 1 || (groups > 1 && best_score != second), b_ref, b_rc, b_mapq, b_qs, b_qe, b_rs, b_re, best_score);
+    if (n <= 1) chain_thread<1>(a, r, n, ms);
+    else if (n == 2) chain_thread<2>(a, r, n, ms);
+    else if (n <= 4) chain_thread<4>(a, r, n, ms);
+    else chain_thread<CHAIN_SMALL>(a, r, n, ms);
 }
 
 
