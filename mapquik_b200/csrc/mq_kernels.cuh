@@ -443,25 +443,46 @@ __device__ __forceinline__ void tile_origin(const GatherArgs &g, uint32_t tile, 
     uint64_t tlo = A + (uint64_t)ti * 32u * Cs;
     *x0_to_pos = (int64_t)tlo - (int64_t)gs + (g.pos_base ? (int64_t)g.pos_base[sq] : 0);
 }
+// A warp handles one tile (typically ~50 events), so the kernel lives on memory-level parallelism: the loads are
+// arranged in two dependency levels -- everything addressable from the tile id first, then the record geometry and the
+// first 64 events together -- instead of one dependent load after another.
 __global__ void __launch_bounds__(256) k_gather_minimizers(GatherArgs g) {
-    uint32_t tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint32_t tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (tile >= g.n_tiles) return;
-    uint32_t lane = lane_id();
-    uint32_t base = g.tile_base[tile];
-    uint32_t total = g.tile_base[tile + 1] - base;
+    const uint32_t lane = lane_id();
+    // level 1
+    const uint32_t base = __ldg(g.tile_base + tile), next = __ldg(g.tile_base + tile + 1);
+    const uint32_t n = __ldg(g.lane_cnt + (uint64_t)tile * 32 + lane);
+    const uint32_t sq = __ldg(g.tile_seq + tile);
+    const uint32_t total = next - base;
     if (total == 0) return;
-    uint32_t n = g.lane_cnt[(uint64_t)tile * 32 + lane], tot;
-    uint32_t ex = warp_excl_scan(n, &tot);
-    int64_t org; tile_origin(g, tile, &org);
-    uint32_t staged = total < EV_CAP ? total : EV_CAP;
+    // level 2: geometry of the record and the first two rounds of events
+    const uint32_t staged = total < EV_CAP ? total : EV_CAP;
+    const uint64_t eb = (uint64_t)tile * EV_CAP;
+    uint32_t meta0 = 0, meta1 = 0; uint64_t h0 = 0, h1 = 0;
+    if (lane < staged) { meta0 = g.ev_meta[eb + lane]; h0 = g.ev_hash[eb + lane]; }
+    if (lane + 32 < staged) { meta1 = g.ev_meta[eb + lane + 32]; h1 = g.ev_hash[eb + lane + 32]; }
+    const uint64_t am = (uint64_t)g.grid_align - 1;
+    const uint64_t gs = __ldg(g.offs + sq), ge = __ldg(g.offs + sq + 1), A = gs & ~am;
+    const uint32_t ft = __ldg(g.first_tile + sq), nt = __ldg(g.first_tile + sq + 1) - ft, ti = tile - ft;
+    const int64_t pb = g.pos_base ? (int64_t)__ldg(g.pos_base + sq) : 0;
+    uint32_t tot;
+    const uint32_t ex = warp_excl_scan(n, &tot);
+    const uint32_t span = (uint32_t)(ge - A), dv = 32u * nt;
+    uint32_t Cs = (span + dv - 1) / dv;
+    const uint32_t cm = g.grid_align == 16 ? 15u : 7u;
+    Cs = (Cs + cm) & ~cm;
+    const int64_t org = (int64_t)(A + (uint64_t)ti * 32u * Cs) - (int64_t)gs + pb;
     for (uint32_t s0 = 0; s0 < staged; s0 += 32) {
-        uint32_t s = s0 + lane;
-        uint32_t meta = 0; uint64_t h = 0;
-        if (s < staged) { meta = g.ev_meta[(uint64_t)tile * EV_CAP + s]; h = g.ev_hash[(uint64_t)tile * EV_CAP + s]; }
-        uint32_t ln = (meta >> 14) & 31, j = meta >> 19;
-        uint32_t e = __shfl_sync(0xffffffffu, ex, ln), c = __shfl_sync(0xffffffffu, n, ln);
+        const uint32_t s = s0 + lane;
+        uint32_t meta; uint64_t h;
+        if (s0 == 0) { meta = meta0; h = h0; }
+        else if (s0 == 32) { meta = meta1; h = h1; }
+        else { meta = 0; h = 0; if (s < staged) { meta = g.ev_meta[eb + s]; h = g.ev_hash[eb + s]; } }
+        const uint32_t ln = (meta >> 14) & 31, j = meta >> 19;
+        const uint32_t e = __shfl_sync(0xffffffffu, ex, ln), c = __shfl_sync(0xffffffffu, n, ln);
         if (s < staged) {
-            uint32_t rank = e + c - 1 - j;
+            const uint32_t rank = e + c - 1 - j;
             g.out_pos[base + rank] = (uint32_t)((int64_t)(meta & 0x3FFF) + org);
             g.out_hash[base + rank] = h;
         }
