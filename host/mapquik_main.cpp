@@ -60,8 +60,9 @@ struct PinnedBuf {
     ~PinnedBuf() { if (p) release(p); }
     void reserve(size_t want) {
         if (want <= cap) return;
-        size_t nc = cap ? cap : (64u << 20);
-        while (nc < want) nc += nc / 2;
+        // pinning costs ~0.5 s per GB (cudaHostAlloc), so a slot is sized to what it must hold, not to a growth schedule
+        size_t nc = cap ? std::max(want, cap + cap / 2) : want;
+        nc = (nc + (1u << 20) - 1) & ~(size_t)((1u << 20) - 1);
         uint8_t *np = alloc(nc);
         if (!np) die("pinned host allocation failed");
         if (size) memcpy(np, p, size);
@@ -161,7 +162,7 @@ struct BatchQueue {          // single producer / single consumer over two slots
 // The file is consumed in blocks that are cut at record boundaries.  Per block: (1) worker threads index the
 // newlines of their slice, (2) one pass over the line table assembles records and a list of copy jobs,
 // (3) worker threads copy + upper-case the sequence pieces straight into the pinned batch buffer.
-int g_parse_threads = 8;
+int g_parse_threads = (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
 template <class Fn> void parallel_for(int n, Fn fn) {
     if (n <= 1) { if (n == 1) fn(0); return; }
     std::vector<std::thread> th;
@@ -263,7 +264,7 @@ struct BlockParser {
             }
             lap("records");
             // (3) copy + upper-case into the pinned batch
-            B.seqs.reserve(dst + 64); B.seqs.size = dst;
+            B.seqs.reserve(std::max(dst, raw.size()) + 64); B.seqs.size = dst;     // sequence bytes never exceed the block: one allocation per slot
             lap("reserve");
             if (!jobs.empty()) {
                 const int T2 = (int)std::max<size_t>(1, std::min<size_t>((size_t)g_parse_threads, dst / (4u << 20) + 1));
@@ -437,7 +438,7 @@ int main(int argc, char **argv) {
         for (uint32_t i = 0; i < n_refs; i++) { ref_names.emplace_back(q < e ? q : ""); q += ref_names.back().size() + 1; }
         printf("Loaded index %s: %u references.\n", o.load_index.c_str(), n_refs);
     } else {
-        for_each_batch(o.reference, ref_fasta, o.low_memory ? (64u << 20) : (512u << 20), [&](Batch &B) {
+        for_each_batch(o.reference, ref_fasta, o.low_memory ? (64u << 20) : (128u << 20), [&](Batch &B) {
             std::vector<uint64_t> nb(B.ids.size());
             ck(ctx, mq_index_add(ctx, B.seqs.p, B.offs.data(), (uint32_t)B.ids.size(), (uint32_t)ref_names.size(), nb.data()), "mq_index_add");
             for (size_t i = 0; i < B.ids.size(); i++) {
@@ -459,7 +460,9 @@ int main(int argc, char **argv) {
     PinnedBuf un_seqs; std::vector<uint64_t> un_offs{0}; std::vector<std::string> un_ids;      // unmapped reads (--rescue)
     {
         std::vector<mq_hit> hits; std::vector<char> line(1 << 16);
-        for_each_batch(o.reads, reads_fasta, 256u << 20, [&](Batch &B) {
+        // 64 MB batches: two pinned slots cost ~70 ms to allocate (256 MB ones cost 0.33 s, more than parsing 1 GB), and the
+        // GPU side of a batch (H2D 1.3 ms + kernels) hides behind the parser either way
+        for_each_batch(o.reads, reads_fasta, 64u << 20, [&](Batch &B) {
             hits.resize(B.ids.size());
             ck(ctx, mq_map_batch(ctx, B.seqs.p, B.offs.data(), (uint32_t)B.ids.size(), hits.data()), "mq_map_batch");
             for (size_t i = 0; i < B.ids.size(); i++) {                  // input order, closures.rs:117-123
@@ -502,7 +505,7 @@ int main(int argc, char **argv) {
             mq_ctx *c2 = nullptr;
             ck(nullptr, mq_create(&c2, &p2, o.gpu), "mq_create (rescue)");
             std::vector<std::string> names2; std::vector<uint64_t> lens2;
-            for_each_batch(o.reference, ref_fasta, o.low_memory ? (64u << 20) : (512u << 20), [&](Batch &B) {
+            for_each_batch(o.reference, ref_fasta, o.low_memory ? (64u << 20) : (128u << 20), [&](Batch &B) {
                 ck(c2, mq_index_add(c2, B.seqs.p, B.offs.data(), (uint32_t)B.ids.size(), (uint32_t)names2.size(), nullptr), "mq_index_add (rescue)");
                 for (size_t i = 0; i < B.ids.size(); i++) { names2.push_back(B.ids[i]); lens2.push_back(B.offs[i + 1] - B.offs[i]); }
             });

@@ -43,6 +43,8 @@ def main():
     got = open(os.path.join(d, "out.paf")).read().splitlines()
     out = {"reads": n_reads, "read_bp": int(ro[-1]), "cli_wall_s": wall, "paf_identical": got == exp, "paf_lines": len(got),
            "stdout_tail": r.stdout.splitlines()[-5:], "reads_per_s_cli": n_reads / wall, "gbp_per_s_cli": float(ro[-1]) / wall / 1e9}
+    if os.environ.get("MQ_CLI_TIMING"):
+        out["timing_lines"] = [ln for ln in r.stderr.splitlines() if ln.startswith("[")]
     print(json.dumps(out))
     for f in os.listdir(d):
         os.unlink(os.path.join(d, f))
