@@ -12,6 +12,7 @@
 
 #include <fcntl.h>
 #include <sys/resource.h>
+#include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
 #include <zlib.h>
@@ -171,31 +172,25 @@ template <class Fn> void parallel_for(int n, Fn fn) {
     for (auto &x : th) x.join();
 }
 struct BlockParser {
+    // The file is mapped once; a block is a window [pos, pos + block_bytes) of the mapping that next_batch() advances
+    // past the records it consumed -- no read() copy and no carry-over of an incomplete trailing record.
     int fd; bool fasta; size_t block_bytes;
-    std::vector<char> raw; size_t fill = 0; bool eof = false;
+    const char *base = nullptr; size_t file_size = 0, pos = 0;
+    const char *raw = nullptr; size_t fill = 0; bool eof = false;
     struct Job { size_t src, len, dst; };
-    BlockParser(int fd_, bool fasta_, size_t block_bytes_, size_t file_size_) : fd(fd_), fasta(fasta_), block_bytes(block_bytes_) {
-        raw.resize(block_bytes_); file_size = file_size_;
-    }
-    size_t file_off = 0, file_size = 0;
-    void top_up() {                                   // parallel pread of the next slice of the file
-        if (eof) return;
-        const size_t want = std::min(raw.size() - fill, file_size - file_off);
-        if (want) {
-            const int T = (int)std::max<size_t>(1, std::min<size_t>((size_t)g_parse_threads, want / (8u << 20) + 1));
-            std::vector<int> bad(T, 0);
-            parallel_for(T, [&](int t) {
-                size_t a = want * (size_t)t / T, b = want * (size_t)(t + 1) / T;
-                while (a < b) {
-                    ssize_t r = pread(fd, raw.data() + fill + a, b - a, (off_t)(file_off + a));
-                    if (r <= 0) { bad[t] = 1; break; }
-                    a += (size_t)r;
-                }
-            });
-            for (int x : bad) if (x) die("read error");
-            fill += want; file_off += want;
+    BlockParser(int fd_, bool fasta_, size_t block_bytes_, size_t file_size_) : fd(fd_), fasta(fasta_), block_bytes(block_bytes_), file_size(file_size_) {
+        if (file_size) {
+            void *m = mmap(nullptr, file_size, PROT_READ, MAP_PRIVATE, fd, 0);
+            if (m == MAP_FAILED) die("mmap failed");
+            base = (const char *)m;
+            madvise(m, file_size, MADV_SEQUENTIAL);
         }
-        if (file_off >= file_size) eof = true;
+    }
+    ~BlockParser() { if (base) munmap((void *)base, file_size); }
+    void top_up() {                                   // position the window
+        fill = std::min(block_bytes, file_size - pos);
+        raw = base + pos;
+        eof = pos + fill >= file_size;
     }
     // fills B with the records of the next block; false when the file is exhausted
     bool next_batch(Batch &B) {
@@ -210,16 +205,15 @@ struct BlockParser {
         };
         for (;;) {
             top_up();
-            lap("read");
             if (fill == 0) return false;
             // (1) newline index
             const int T = (int)std::max<size_t>(1, std::min<size_t>((size_t)g_parse_threads, fill / (4u << 20) + 1));
             std::vector<std::vector<uint32_t>> nlv(T);
             parallel_for(T, [&](int t) {
                 size_t a = fill * (size_t)t / T, b = fill * (size_t)(t + 1) / T;
-                const char *p = raw.data() + a, *e = raw.data() + b;
+                const char *p = raw + a, *e = raw + b;
                 auto &v = nlv[t];
-                while (p < e) { const char *q = (const char *)memchr(p, '\n', (size_t)(e - p)); if (!q) break; v.push_back((uint32_t)(q - raw.data())); p = q + 1; }
+                while (p < e) { const char *q = (const char *)memchr(p, '\n', (size_t)(e - p)); if (!q) break; v.push_back((uint32_t)(q - raw)); p = q + 1; }
             });
             std::vector<uint32_t> nl;
             { size_t tot = 0; for (auto &v : nlv) tot += v.size(); nl.reserve(tot + 1); for (auto &v : nlv) nl.insert(nl.end(), v.begin(), v.end()); }
@@ -237,7 +231,7 @@ struct BlockParser {
                     size_t a, n; line(i, a, n);
                     if (n && raw[a] == '>') {
                         if (open_rec) B.offs.push_back(dst);
-                        B.ids.push_back(Fastx::id_of(raw.data() + a, n)); open_rec = true; last_hdr = a;
+                        B.ids.push_back(Fastx::id_of(raw + a, n)); open_rec = true; last_hdr = a;
                     } else if (open_rec && n) { jobs.push_back({a, n, dst}); dst += n; }
                 }
                 if (eof) { if (open_rec) B.offs.push_back(dst); consumed = fill; }
@@ -250,7 +244,7 @@ struct BlockParser {
                 for (size_t r = 0; r < nrec; r++) {
                     size_t a, n; line(4 * r, a, n);
                     if (!n || raw[a] != '@') die("malformed FASTQ record");
-                    B.ids.push_back(Fastx::id_of(raw.data() + a, n));
+                    B.ids.push_back(Fastx::id_of(raw + a, n));
                     line(4 * r + 1, a, n);
                     if (n) { jobs.push_back({a, n, dst}); dst += n; }
                     B.offs.push_back(dst);
@@ -258,25 +252,28 @@ struct BlockParser {
                 consumed = nrec ? (size_t)nl[4 * nrec - 1] + 1 : 0;
                 if (eof) consumed = fill;
             }
-            if (B.ids.empty() && !eof) {                  // not even one complete record in the buffer: enlarge it
-                raw.resize(raw.size() * 2);
+            if (B.ids.empty() && !eof) {                  // not even one complete record in the window: enlarge it
+                if (block_bytes >= (size_t)3 << 30) die("record larger than 3 GB");      // line offsets are 32-bit
+                block_bytes *= 2;
                 continue;
             }
             lap("records");
             // (3) copy + upper-case into the pinned batch
-            B.seqs.reserve(std::max(dst, raw.size()) + 64); B.seqs.size = dst;     // sequence bytes never exceed the block: one allocation per slot
+            B.seqs.reserve(std::max(dst, block_bytes) + 64); B.seqs.size = dst;     // sequence bytes never exceed the block: one allocation per slot
             lap("reserve");
             if (!jobs.empty()) {
                 const int T2 = (int)std::max<size_t>(1, std::min<size_t>((size_t)g_parse_threads, dst / (4u << 20) + 1));
                 std::vector<size_t> cut(T2 + 1, jobs.size()); cut[0] = 0;
                 { size_t j = 0; for (int t = 1; t < T2; t++) { const size_t want = dst * (size_t)t / T2; while (j < jobs.size() && jobs[j].dst < want) j++; cut[t] = j; } }
-                parallel_for(T2, [&](int t) { for (size_t j = cut[t]; j < cut[t + 1]; j++) copy_upper(B.seqs.p + jobs[j].dst, raw.data() + jobs[j].src, jobs[j].len); });
+                parallel_for(T2, [&](int t) { for (size_t j = cut[t]; j < cut[t + 1]; j++) copy_upper(B.seqs.p + jobs[j].dst, raw + jobs[j].src, jobs[j].len); });
             }
             lap("copy");
-            if (consumed < fill) memmove(raw.data(), raw.data() + consumed, fill - consumed);
-            fill -= consumed;
-            lap("carry");
-            B.last = eof && fill == 0;
+            {   // the consumed part of the mapping is not needed again: drop it from this process's resident set
+                const size_t pg = 4096, a0 = pos & ~(pg - 1), a1 = (pos + consumed) & ~(pg - 1);
+                if (a1 > a0) madvise((void *)(base + a0), a1 - a0, MADV_DONTNEED);
+            }
+            pos += consumed;
+            B.last = eof && consumed == fill;
             return true;
         }
     }
