@@ -307,7 +307,7 @@ int run_scan(mq_ctx *c, const uint8_t *d_seqs, const uint64_t *d_offs, uint32_t 
         g.tile_base = c->d_tile_cnt.as<uint32_t>();
         g.tile_seq = c->d_tile_seq.as<uint32_t>(); g.first_tile = c->d_first_tile.as<uint32_t>(); g.offs = d_offs;
         g.pos_base = d_pos_base; g.n_tiles = n_tiles; g.grid_align = c->scan_v1 ? 4u : 16u; g.out_pos = c->d_pos.as<uint32_t>(); g.out_hash = c->d_hash.as<uint64_t>();
-        k_gather_minimizers<<<(n_tiles + 7) / 8, 256, 0, c->stream>>>(g);
+        k_gather_minimizers<<<(n_tiles + 8 * GATHER_TPW - 1) / (8 * GATHER_TPW), 256, 0, c->stream>>>(g);
         c->launches++;
         if (n_ovf) {
             k_gather_overflow<<<(n_ovf + 255) / 256, 256, 0, c->stream>>>(g, c->d_ovf_tile.as<uint32_t>(), c->d_ovf_meta.as<uint32_t>(),
