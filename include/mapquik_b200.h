@@ -28,9 +28,17 @@
  * never throws or aborts across the boundary.  There is NO CPU fallback: without a usable CUDA
  * device every entry point that computes returns MQ_ERR_CUDA.
  *
- * Threading: one host thread per mq_ctx at a time.  One mq_ctx drives one GPU (one process per
- * GPU; the multi-GPU index exchange is an all-gather of the minimizer store, see
- * mq_store_* below and DESIGN.md section 6).
+ * Threading: one host thread per mq_ctx at a time.  mq_create gives a context that drives one GPU; mq_create_multi one
+ * that fans every call out to several GPUs of this process (closures.rs:85,183 fan out over threads at the same two
+ * places): the reference is partitioned by base range, the per-GPU minimizer stores are exchanged GPU to GPU and every
+ * GPU freezes the whole index; reads are sharded with no communication.  One process per GPU works too: mq_store_*
+ * below is what the ranks all-gather before mq_index_freeze.
+ *
+ * Packed input: every entry point that takes upper-cased ASCII has a twin that takes the same sequences as 2-bit
+ * codes (mq_packed).  The reference makes one pass over every record before the hot path sees it
+ * (`to_ascii_uppercase`, closures.rs:63,106); a caller of this library makes that pass with mq_pack / mq_pack_at
+ * instead and ships a quarter of the bytes to the GPU.  Results are identical by construction: codes + exception
+ * intervals are exactly the ASCII bytes.
  */
 #ifndef MAPQUIK_B200_H
 #define MAPQUIK_B200_H
@@ -75,8 +83,38 @@ typedef struct {
 
 typedef struct mq_ctx mq_ctx;
 
+/* ---- packed sequences --------------------------------------------------------------------------
+ * Base i of a sequence array: code (words[i >> 4] >> 2*(i & 15)) & 3 with code = (byte >> 1) & 3 (A=0 C=1 T=2 G=3).
+ * flags: bit (i >> 6) & 31 of flags[i >> 11] is set iff the 64-base block of i holds a byte other than A/C/G/T; exc lists
+ * those bytes as sorted, disjoint intervals.  offs[] of the packed entry points index bases exactly as the ASCII ones
+ * index bytes.  words needs mq_packed_words(n) entries (256 bytes of zeroed slack), flags mq_packed_flag_words(n). */
+typedef struct { uint64_t start; uint32_t len; uint32_t byte; } mq_exc;      /* bases [start, start+len) are `byte` */
+typedef struct {
+    const uint32_t *words;
+    const uint32_t *flags;
+    const mq_exc   *exc;
+    uint64_t        n_exc;
+    uint64_t        n_bases;
+} mq_packed;
+uint64_t mq_packed_words(uint64_t n_bases);
+uint64_t mq_packed_flag_words(uint64_t n_bases);
+/* Pack a whole array with n_threads host threads (<= 0: all cores).  fold_case != 0 upper-cases first
+ * (closures.rs:63,106).  Returns MQ_ERR_RANGE with *n_exc = the count needed when exc_cap is too small. */
+int mq_pack(const uint8_t *ascii, uint64_t n_bases, uint32_t *words, uint32_t *flags, mq_exc *exc, uint64_t exc_cap,
+            uint64_t *n_exc, int n_threads, int fold_case);
+/* Pack n_bases bytes to base positions [at_base, at_base + n_bases) of a ZEROED destination.  Safe to call concurrently
+ * for disjoint ranges (shared edge words are OR-ed in atomically) -- a FASTX parser's copy jobs call this instead of
+ * their upper-casing memcpy.  exc receives this range's intervals (absolute positions); the caller concatenates the
+ * lists of all ranges in position order. */
+int mq_pack_at(const uint8_t *ascii, uint64_t n_bases, uint64_t at_base, uint32_t *words, uint32_t *flags, mq_exc *exc,
+               uint64_t exc_cap, uint64_t *n_exc, int fold_case);
+int mq_unpack(const uint32_t *words, const mq_exc *exc, uint64_t n_exc, uint64_t first, uint64_t n, uint8_t *ascii);
+
 /* ---- lifecycle ------------------------------------------------------------------------------- */
 int  mq_create(mq_ctx **out, const mq_params *p, int device);
+/* One context over n_devices GPUs of this process.  Entry points marked [multi] accept it. */
+int  mq_create_multi(mq_ctx **out, const mq_params *p, const int *devices, int n_devices);
+int  mq_device_count(const mq_ctx *);
 void mq_destroy(mq_ctx *);
 const char *mq_strerror(int code);
 const char *mq_last_error(const mq_ctx *);       /* detail of the last failure on this ctx */
@@ -92,7 +130,9 @@ void  mq_host_free(void *);
  * nb_mers_out[i] (may be NULL) = number of k-min-mers the record emitted ("Indexed reference {}:
  * {} k-min-mers.", closures.rs:58). */
 int mq_index_add(mq_ctx *, const uint8_t *seqs, const uint64_t *offs, uint32_t n,
-                 uint32_t first_ref_idx, uint64_t *nb_mers_out);
+                 uint32_t first_ref_idx, uint64_t *nb_mers_out);                                  /* [multi] */
+int mq_index_add_packed(mq_ctx *, const mq_packed *seqs, const uint64_t *offs, uint32_t n,
+                        uint32_t first_ref_idx, uint64_t *nb_mers_out);                           /* [multi] */
 
 /* Scan one contiguous piece [seg_start, seg_start+own_len) of reference record `ref_idx` whose
  * total length is ref_len (multi-GPU partitioning by reference chunk).  `bytes` must start at
@@ -109,6 +149,10 @@ int mq_store_info(mq_ctx *, uint64_t *n_minimizers, uint32_t *n_segments);
 int mq_store_export(mq_ctx *, void **d_pos_u32, void **d_hash_u64, uint64_t *dir_u64x3 /* n_segments*3 */);
 int mq_store_import(mq_ctx *, const void *d_pos_u32, const void *d_hash_u64, uint64_t n_minimizers,
                     const uint64_t *dir_u64x3, uint32_t n_segments);
+/* In-place variant for collectives: reserve room for the union (this rank's own entries stay at the front), let
+ * ncclAllGather / ncclBroadcast write every rank's share into the returned arrays, then commit the merged directory. */
+int mq_store_reserve(mq_ctx *, uint64_t n_minimizers, void **d_pos_u32, void **d_hash_u64);
+int mq_store_commit(mq_ctx *, uint64_t n_minimizers, const uint64_t *dir_u64x3, uint32_t n_segments);
 
 /* ≙ get_count + ReadOnlyIndex::new (closures.rs:92,94).  ref_lens[n_refs] are the record lengths
  * (the ref_map of closures.rs:29,49).  Builds the table from the store: k-min-mers are formed per
@@ -116,7 +160,7 @@ int mq_store_import(mq_ctx *, const void *d_pos_u32, const void *d_hash_u64, uin
  * rule.  n_unique (may be NULL) = get_count(); n_keys (may be NULL) = distinct keys incl.
  * tombstones. */
 int mq_index_freeze(mq_ctx *, const uint64_t *ref_lens, uint32_t n_refs, uint64_t *n_unique,
-                    uint64_t *n_keys);
+                    uint64_t *n_keys);                                                            /* [multi] */
 /* per-record k-min-mer counts of the frozen index (valid after freeze), nb[n_refs] */
 int mq_index_nb_mers(mq_ctx *, uint64_t *nb, uint32_t n_refs);
 
@@ -129,11 +173,14 @@ int mq_index_load(mq_ctx *, const char *path, uint64_t *ref_lens_out, uint32_t r
                   char *names_out, uint64_t names_cap, uint64_t *names_bytes_out, uint64_t *n_unique_out);
 
 /* ---- mapping  (≙ find_matches, closures.rs:102) --------------------------------------------- */
-int mq_map_batch(mq_ctx *, const uint8_t *seqs, const uint64_t *offs, uint32_t n, mq_hit *out);
-/* same with everything already resident on this ctx's device (no H2D/D2H inside); d_seqs must be 16-byte
- * aligned with >= 64 readable bytes after the last record, every record < 2^31 bases */
-int mq_map_batch_device(mq_ctx *, const uint8_t *d_seqs, const uint64_t *d_offs, uint32_t n,
-                        uint64_t total_bytes, mq_hit *d_out);
+int mq_map_batch(mq_ctx *, const uint8_t *seqs, const uint64_t *offs, uint32_t n, mq_hit *out);            /* [multi] */
+int mq_map_batch_packed(mq_ctx *, const mq_packed *seqs, const uint64_t *offs, uint32_t n, mq_hit *out);  /* [multi] */
+/* The same with the sequences (and the hits) resident on this ctx's device: no sequence H2D / hit D2H inside.  offs is
+ * a HOST array (the per-sub-batch tile tables are derived from it on the host).  d_seqs / d_seqs->words must be 16-byte
+ * aligned with >= 256 readable bytes after the last record; for the packed variant words, flags and exc are device
+ * pointers.  Every record < 2^31 bases. */
+int mq_map_batch_device(mq_ctx *, const uint8_t *d_seqs, const uint64_t *offs, uint32_t n, mq_hit *d_out);
+int mq_map_batch_packed_device(mq_ctx *, const mq_packed *d_seqs, const uint64_t *offs, uint32_t n, mq_hit *d_out);
 
 /* mers.rs:181: 12-column PAF line, no trailing newline.  Returns its length, or <0 if cap is too
  * small.  Pure host formatting. */
@@ -145,6 +192,8 @@ int mq_format_paf(char *buf, size_t cap, const char *q_id, uint64_t q_len, const
  * size (total returned in *n_total). */
 int mq_minimizers(mq_ctx *, const uint8_t *seqs, const uint64_t *offs, uint32_t n,
                   uint64_t *seq_off, uint32_t *pos, uint64_t *hash, uint64_t cap, uint64_t *n_total);
+int mq_minimizers_packed(mq_ctx *, const mq_packed *seqs, const uint64_t *offs, uint32_t n,
+                         uint64_t *seq_off, uint32_t *pos, uint64_t *hash, uint64_t cap, uint64_t *n_total);
 /* S1+S2: k-min-mer tuples of a batch (start,end,offset<<1|rev as u32; hash u64) */
 int mq_kminmers(mq_ctx *, const uint8_t *seqs, const uint64_t *offs, uint32_t n, uint64_t *seq_off,
                 uint32_t *start, uint32_t *end, uint32_t *offrev, uint64_t *hash, uint64_t cap,
@@ -158,7 +207,8 @@ int mq_matches(mq_ctx *, const uint8_t *seqs, const uint64_t *offs, uint32_t n, 
                uint32_t *fields6, uint64_t cap, uint64_t *n_total);
 
 /* device time of the stages of the last mq_index_* / mq_map_* call, CUDA events on the ctx stream.
- * names: "h2d","scan","scan_kernel" (k_scan_minimizers alone, also inside "scan"),"gather","insert","probe","chain","d2h","total".  Returns ms or <0. */
+ * names: "h2d","scan","scan_kernel" (k_scan_minimizers alone, also inside "scan"),"gather","insert","exchange","probe","chain","d2h","total".
+ * Returns ms or <0; for a multi-GPU context the maximum over its devices. */
 double mq_last_ms(mq_ctx *, const char *stage);
 /* the same stages accumulated over all calls since mq_create */
 double mq_total_ms(mq_ctx *, const char *stage);

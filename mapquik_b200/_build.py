@@ -1,7 +1,7 @@
 """In-tree builds of the native pieces (nvcc cross-compiles sm_100a without a GPU).
 
-  libmapquik_b200.so  CUDA kernels + C ABI (include/mapquik_b200.h)   csrc/mq_lib.cu
-  libmq_host.so       host-only helpers: simulator, FASTX reader       csrc/mq_sim.cpp, csrc/mq_fastx.cpp
+  libmapquik_b200.so  CUDA kernels + C ABI (include/mapquik_b200.h)   csrc/mq_lib.cu, csrc/mq_pack.cpp
+  libmq_host.so       host-only helper: genome / read simulator        csrc/mq_sim.cpp
 """
 import os
 import shutil
@@ -30,16 +30,16 @@ def _stale(target, sources):
 
 
 def build_cuda(force=False, verbose=False):
-    srcs = [os.path.join(CSRC, "mq_lib.cu"), os.path.join(CSRC, "mq_kernels.cuh"), os.path.join(CSRC, "mq_scan_v2.cuh"), os.path.join(CSRC, "mq_scan_v3.cuh"),
-            os.path.join(PKG, "..", "include", "mapquik_b200.h")]
+    srcs = [os.path.join(CSRC, "mq_lib.cu"), os.path.join(CSRC, "mq_pack.cpp"), os.path.join(CSRC, "mq_kernels.cuh"),
+            os.path.join(CSRC, "mq_scan.cuh"), os.path.join(PKG, "..", "include", "mapquik_b200.h")]
     if force or _stale(LIB, srcs):
-        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, srcs[0]]
+        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, srcs[0], srcs[1]]
         subprocess.check_call(cmd)
     return LIB
 
 
 def build_host(force=False):
-    srcs = [os.path.join(CSRC, f) for f in ("mq_sim.cpp", "mq_fastx.cpp") if os.path.exists(os.path.join(CSRC, f))]
+    srcs = [os.path.join(CSRC, "mq_sim.cpp")]
     if force or _stale(HOSTLIB, srcs):
         subprocess.check_call(["g++", "-O3", "-std=c++17", "-fopenmp", "-fPIC", "-shared", "-o", HOSTLIB] + srcs)
     return HOSTLIB

@@ -21,6 +21,18 @@ class Params(C.Structure):
                 ("c", C.c_uint32), ("s", C.c_uint32), ("g", C.c_uint32)]
 
 
+class Exc(C.Structure):
+    _fields_ = [("start", C.c_uint64), ("len", C.c_uint32), ("byte", C.c_uint32)]
+
+
+class Packed(C.Structure):
+    _fields_ = [("words", C.c_void_p), ("flags", C.c_void_p), ("exc", C.c_void_p), ("n_exc", C.c_uint64),
+                ("n_bases", C.c_uint64)]
+
+
+EXC_DTYPE = np.dtype([("start", "<u8"), ("len", "<u4"), ("byte", "<u4")])
+assert EXC_DTYPE.itemsize == 16
+
 HIT_DTYPE = np.dtype([("mapped", "u1"), ("rc", "u1"), ("mapq", "u1"), ("pad_", "u1"), ("ref_idx", "<u4"),
                       ("q_start", "<u8"), ("q_end", "<u8"), ("r_start", "<u8"), ("r_end", "<u8"),
                       ("score", "<u8")])
@@ -32,7 +44,10 @@ EXPORTS = ["mq_create", "mq_destroy", "mq_strerror", "mq_last_error", "mq_abi_ve
            "mq_format_paf", "mq_minimizers", "mq_kminmers", "mq_index_get", "mq_matches", "mq_last_ms",
            "mq_launch_count", "mq_stream", "mq_sync", "mq_table_bytes", "mq_table_slots", "mq_scan_kernel_launches",
            "mq_minimizer_count", "mq_dev_alloc", "mq_dev_free", "mq_dev_upload", "mq_dev_download", "mq_dev_memset",
-           "mq_region_begin", "mq_region_end_ms", "mq_index_save", "mq_index_load", "mq_total_ms"]
+           "mq_region_begin", "mq_region_end_ms", "mq_index_save", "mq_index_load", "mq_total_ms",
+           "mq_create_multi", "mq_device_count", "mq_packed_words", "mq_packed_flag_words", "mq_pack", "mq_pack_at",
+           "mq_unpack", "mq_index_add_packed", "mq_map_batch_packed", "mq_map_batch_packed_device", "mq_minimizers_packed",
+           "mq_store_reserve", "mq_store_commit"]
 
 _lib = None
 
@@ -64,7 +79,22 @@ def lib():
     L.mq_index_nb_mers.restype = C.c_int; L.mq_index_nb_mers.argtypes = [vp, vp, C.c_uint32]
     L.mq_map_batch.restype = C.c_int; L.mq_map_batch.argtypes = [vp, vp, vp, C.c_uint32, vp]
     L.mq_map_batch_device.restype = C.c_int
-    L.mq_map_batch_device.argtypes = [vp, vp, vp, C.c_uint32, C.c_uint64, vp]
+    L.mq_map_batch_device.argtypes = [vp, vp, vp, C.c_uint32, vp]
+    pk = C.POINTER(Packed)
+    L.mq_create_multi.restype = C.c_int; L.mq_create_multi.argtypes = [C.POINTER(vp), C.POINTER(Params), C.POINTER(C.c_int), C.c_int]
+    L.mq_device_count.restype = C.c_int; L.mq_device_count.argtypes = [vp]
+    L.mq_packed_words.restype = C.c_uint64; L.mq_packed_words.argtypes = [C.c_uint64]
+    L.mq_packed_flag_words.restype = C.c_uint64; L.mq_packed_flag_words.argtypes = [C.c_uint64]
+    L.mq_pack.restype = C.c_int; L.mq_pack.argtypes = [vp, C.c_uint64, vp, vp, vp, C.c_uint64, u64p, C.c_int, C.c_int]
+    L.mq_pack_at.restype = C.c_int; L.mq_pack_at.argtypes = [vp, C.c_uint64, C.c_uint64, vp, vp, vp, C.c_uint64, u64p, C.c_int]
+    L.mq_unpack.restype = C.c_int; L.mq_unpack.argtypes = [vp, vp, C.c_uint64, C.c_uint64, C.c_uint64, vp]
+    L.mq_index_add_packed.restype = C.c_int; L.mq_index_add_packed.argtypes = [vp, pk, vp, C.c_uint32, C.c_uint32, vp]
+    L.mq_map_batch_packed.restype = C.c_int; L.mq_map_batch_packed.argtypes = [vp, pk, vp, C.c_uint32, vp]
+    L.mq_map_batch_packed_device.restype = C.c_int; L.mq_map_batch_packed_device.argtypes = [vp, pk, vp, C.c_uint32, vp]
+    L.mq_minimizers_packed.restype = C.c_int
+    L.mq_minimizers_packed.argtypes = [vp, pk, vp, C.c_uint32, vp, vp, vp, C.c_uint64, u64p]
+    L.mq_store_reserve.restype = C.c_int; L.mq_store_reserve.argtypes = [vp, C.c_uint64, C.POINTER(vp), C.POINTER(vp)]
+    L.mq_store_commit.restype = C.c_int; L.mq_store_commit.argtypes = [vp, C.c_uint64, vp, C.c_uint32]
     L.mq_format_paf.restype = C.c_int
     L.mq_format_paf.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64, vp]
     L.mq_minimizers.restype = C.c_int

@@ -1,8 +1,10 @@
-// mq_kernels.cuh -- sm_100a kernels of the mapquik seeding->chaining hot path.
+// mq_kernels.cuh -- sm_100a kernels of the mapquik seeding->chaining hot path (everything but the S1 scan itself,
+// which lives in mq_scan.cuh).
 //
 // Stage map (reference rows of SURVEY.md section 8a):
-//   k_scan_minimizers   S1  HPC + ntHash-1 canonical l-mer hash + universe-minimizer sampling
+//   k_scan_minimizers   S1  (mq_scan.cuh) HPC + ntHash-1 canonical l-mer hash + universe-minimizer sampling
 //                           (the KminmersIterator stage-1 the reference calls at mers.rs:27,53)
+//   k_tile_prefix       S1  exclusive prefix of the per-tile minimizer counts (one launch, last block finishes)
 //   k_gather_minimizers S1  ordered stream compaction of the per-tile event pools
 //   k_insert_kminmers   S2+I3  window of k minimizers -> k-min-mer -> unique-or-tombstone insert
 //                           (mers.rs:29-36, index.rs:100-104)
@@ -20,26 +22,12 @@ namespace mq {
 // ------------------------------------------------------------------------------------------------
 // constants
 // ------------------------------------------------------------------------------------------------
-constexpr int      C_MAX        = 256;             // raw bases per lane chunk (max)
-constexpr int      TW_MAX       = 32 * C_MAX;      // raw bases per warp tile (max)
-constexpr int      LANE_PAD     = 4;               // smem bytes of padding between lane chunks
-constexpr int      HALO_MAX     = 32;              // >= l-1 compressed symbols right of the tile
-constexpr int      SCAN_WARPS   = 4;               // warps (= tiles in flight) per CTA
-constexpr int      TILE_SMEM    = 33 * (C_MAX + LANE_PAD);   // 32 chunks + halo "chunk"
 constexpr uint32_t EV_CAP       = 256;             // staged events per tile before overflow pool
-constexpr uint32_t D_RUN = 8, D_N = 4;             // digest byte: bits0-1 code, bit2 non-ACGT, bit3 run start
 constexpr uint64_t EMPTY_KEY    = 0xFFFFFFFFFFFFFFFFull;
 constexpr int      MQ_MAX_K_    = 32;
 
 constexpr uint64_t SEED_A = 0x3c8bfbb395c60474ull, SEED_C = 0x3193c18562a02b4cull,
                    SEED_G = 0x20323ed082572324ull, SEED_T = 0x295549f54be24456ull;
-
-struct ScanTables {            // per-launch constants derived from l (host fills)
-    uint64_t pairF[16];        // [in | out<<2] : rol(h(in), l-1) ^ ror(h(out), 1)
-    uint64_t pairR[16];        // [in | out<<2] : hc(in) ^ rol(hc(out), l)
-    uint64_t inF[4], outF[4], inR[4], outR[4];   // the single-symbol parts (N-aware path)
-    uint64_t h[4], hc[4];      // base seeds by code (A,C,G,T) and of the complement
-};
 
 struct Slot {                  // 32 B = one DRAM sector
     uint64_t key;
@@ -63,6 +51,16 @@ struct HitRec {                // == mq_hit
 };
 static_assert(sizeof(HitRec) == 48, "mq_hit layout");
 
+// Scalars of one batch, zeroed by ONE memset before its first kernel; the tail is read back by the host once per
+// batch (there is no other device->host traffic between the upload of a batch and the download of its hits).
+struct BatchScalars {
+    uint32_t scan_ticket, ovf_count, probe_ticket, chain_ticket, big_count, prefix_done;
+    uint32_t flags;            // BS_* below; any bit set => the kernels after k_tile_prefix do nothing
+    uint32_t pad_;
+    uint64_t n_minimizers;     // grand total of the tile counts
+};
+constexpr uint32_t BS_MINI_CAP = 1u, BS_OVF_CAP = 2u, BS_RANGE = 4u;
+
 // ------------------------------------------------------------------------------------------------
 // small device helpers
 // ------------------------------------------------------------------------------------------------
@@ -84,9 +82,12 @@ __device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, uint32_t *total) 
 }
 
 // ------------------------------------------------------------------------------------------------
-// generic exclusive scan (u32 -> u32), 3 kernels: block sums, scan of sums, apply.
+// exclusive prefix of the per-tile counts, ONE launch.  Every block scans its 8192 counts in place and publishes its
+// total; the block that finishes last scans the block totals.  The prefix of tile t is therefore read in two pieces,
+// within[t] + blk[t / 8192] (tile_base below); entry n (one past the last tile) reads as the grand total.
 // ------------------------------------------------------------------------------------------------
 constexpr int SCAN_BLK = 1024, SCAN_ITEMS = 8;     // 8192 items per block
+constexpr uint32_t PREFIX_SPAN = SCAN_BLK * SCAN_ITEMS;
 
 __device__ __forceinline__ uint32_t block_excl_scan_1024(uint32_t v, uint32_t *smem33, uint32_t *block_total) {
     uint32_t wt, e = warp_excl_scan(v, &wt);
@@ -101,436 +102,151 @@ __device__ __forceinline__ uint32_t block_excl_scan_1024(uint32_t v, uint32_t *s
     return e;
 }
 
-__global__ void __launch_bounds__(SCAN_BLK) k_scan_block_sums(const uint32_t *in, uint64_t n, uint32_t *block_sums) {
+struct TileBase { const uint32_t *within; const uint32_t *blk; };
+__device__ __forceinline__ uint32_t tile_base(const TileBase &tb, uint32_t t) { return __ldg(tb.within + t) + __ldg(tb.blk + t / PREFIX_SPAN); }
+
+// cnt[0..n) in, within[0..n] out (in place; cnt needs n+1 entries), blk[ceil((n+1)/8192)] out.  mini_cap / ovf_cap: the
+// capacities of the buffers the later kernels write; exceeding one raises a flag instead of writing out of bounds.
+__global__ void __launch_bounds__(SCAN_BLK) k_tile_prefix(uint32_t *cnt, uint32_t n, uint32_t *blk, BatchScalars *sc,
+                                                          uint64_t mini_cap, uint32_t ovf_cap) {
     __shared__ uint32_t sm[33];
-    uint64_t base = (uint64_t)blockIdx.x * SCAN_BLK * SCAN_ITEMS + (uint64_t)threadIdx.x * SCAN_ITEMS;
-    uint32_t s = 0;
-#pragma unroll
-    for (int i = 0; i < SCAN_ITEMS; i++) if (base + i < n) s += in[base + i];
-    uint32_t tot; block_excl_scan_1024(s, sm, &tot);
-    if (threadIdx.x == 0) block_sums[blockIdx.x] = tot;
-}
-// single block: exclusive scan of block_sums in place; total -> *total_out (u64)
-__global__ void __launch_bounds__(SCAN_BLK) k_scan_sums(uint32_t *block_sums, uint32_t nb, uint64_t *total_out) {
-    __shared__ uint32_t sm[33];
-    uint32_t carry = 0;
-    for (uint32_t base = 0; base < nb; base += SCAN_BLK) {
-        uint32_t i = base + threadIdx.x;
-        uint32_t v = i < nb ? block_sums[i] : 0, tot;
-        uint32_t e = block_excl_scan_1024(v, sm, &tot);
-        if (i < nb) block_sums[i] = carry + e;
-        carry += tot;
-    }
-    if (threadIdx.x == 0) *total_out = carry;
-}
-// out[i] = exclusive prefix; out may alias in. out has n+1 entries when write_total (out[n] = total)
-__global__ void __launch_bounds__(SCAN_BLK) k_scan_apply(const uint32_t *in, uint64_t n, const uint32_t *block_sums,
-                                                         uint32_t *out, int write_total) {
-    __shared__ uint32_t sm[33];
-    uint64_t base = (uint64_t)blockIdx.x * SCAN_BLK * SCAN_ITEMS + (uint64_t)threadIdx.x * SCAN_ITEMS;
+    __shared__ bool last;
+    const uint32_t base = blockIdx.x * PREFIX_SPAN + threadIdx.x * SCAN_ITEMS;
     uint32_t v[SCAN_ITEMS], s = 0;
 #pragma unroll
-    for (int i = 0; i < SCAN_ITEMS; i++) { v[i] = (base + i < n) ? in[base + i] : 0; s += v[i]; }
-    uint32_t tot, e = block_excl_scan_1024(s, sm, &tot) + block_sums[blockIdx.x];
+    for (int i = 0; i < SCAN_ITEMS; i++) { v[i] = (base + i < n) ? cnt[base + i] : 0u; s += v[i]; }
+    uint32_t tot, e = block_excl_scan_1024(s, sm, &tot);
 #pragma unroll
-    for (int i = 0; i < SCAN_ITEMS; i++) { if (base + i < n) out[base + i] = e; e += v[i]; }
-    if (write_total && blockIdx.x == gridDim.x - 1 && threadIdx.x == SCAN_BLK - 1) out[n] = block_sums[blockIdx.x] + tot;
-}
-
-// ------------------------------------------------------------------------------------------------
-// tile setup
-// ------------------------------------------------------------------------------------------------
-// tiles of record i: span measured from the 4-byte-aligned address at or below its first byte.
-__global__ void k_tiles_per_seq(const uint64_t *offs, uint32_t n, uint32_t min_len, uint32_t *tiles) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint64_t gs = offs[i], ge = offs[i + 1], len = ge - gs;
-    uint32_t t = 0;
-    if (len >= min_len && len > 0) { uint64_t span = ge - (gs & ~3ull); t = (uint32_t)((span + TW_MAX - 1) / TW_MAX); }
-    tiles[i] = t;
-}
-// tile -> record (binary search over first_tile[n+1])
-__global__ void k_tile_seq(const uint32_t *first_tile, uint32_t n, uint32_t n_tiles, uint32_t *tile_seq) {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_tiles) return;
-    uint32_t lo = 0, hi = n;           // largest i with first_tile[i] <= t and first_tile[i+1] > t
-    while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (first_tile[mid] <= t) lo = mid; else hi = mid; }
-    tile_seq[t] = lo;
-}
-
-// ------------------------------------------------------------------------------------------------
-// S1: the sequence scan
-// ------------------------------------------------------------------------------------------------
-// digest of one 4-byte word: per byte  code | non-ACGT<<2 | run-start<<3.
-// pv = the same word shifted up by one byte with the preceding byte shifted in (for run starts).
-__device__ __forceinline__ uint32_t digest_word(uint32_t u, uint32_t pv, bool use_hpc) {
-    uint32_t t = (u >> 1) & 0x03030303u;
-    uint32_t code = t ^ ((t >> 1) & 0x01010101u);                  // A0 C1 G2 T3
-    // validity: rebuild the expected ASCII from the code with a byte-permute LUT and compare
-    uint32_t sel = (code & 0x3u) | ((code >> 4) & 0x30u) | ((code >> 8) & 0x300u) | ((code >> 12) & 0x3000u);
-    uint32_t expect = __byte_perm(0x54474341u /* 'A','C','G','T' */, 0u, sel);
-    uint32_t diff = expect ^ u;
-    uint32_t bad = (((diff & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | diff) & 0x80808080u;   // 0x80 where byte != expected
-    uint32_t run = 0x80808080u;
-    if (use_hpc) { uint32_t e = u ^ pv; run = (((e & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | e) & 0x80808080u; }
-    return code | (bad >> 5) | (run >> 4);
-}
-
-struct ScanArgs {
-    const uint8_t  *seqs;          // concatenated records (device), base 4-byte aligned, padded
-    const uint64_t *offs;          // n+1
-    const uint32_t *first_tile;    // n+1
-    const uint32_t *tile_seq;      // n_tiles
-    uint32_t n_tiles;
-    uint32_t l;
-    uint32_t use_hpc;
-    uint64_t bound;
-    // outputs
-    uint64_t *ev_hash;             // n_tiles * EV_CAP
-    uint32_t *ev_meta;             // n_tiles * EV_CAP   x' (14b) | lane<<14 (5b) | j<<19 (13b)
-    uint16_t *lane_cnt;            // n_tiles * 32
-    uint32_t *tile_cnt;            // n_tiles (total events of the tile, incl. overflowed)
-    // overflow pool
-    uint32_t *ovf_count;           // single counter
-    uint32_t  ovf_cap;
-    uint32_t *ovf_tile; uint32_t *ovf_meta; uint64_t *ovf_hash;
-    uint32_t *tile_ticket;         // dynamic tile scheduler
-    const uint32_t *emit_range;    // per record (or NULL): [lo, hi) record offsets; only l-mers STARTING inside are emitted
-};
-// emission window of a tile in x' coordinates (segment scans; the whole tile otherwise)
-__device__ __forceinline__ void emit_window(const ScanArgs &a, uint32_t sq, uint64_t gs, uint64_t tlo, uint32_t *xlo, uint32_t *xhi) {
-    *xlo = 0u; *xhi = 0x7FFFFFFFu;
-    if (a.emit_range) {
-        const int64_t sh = (int64_t)gs - (int64_t)tlo;
-        const int64_t lo = (int64_t)a.emit_range[2 * sq] + sh, hi = (int64_t)a.emit_range[2 * sq + 1] + sh;
-        *xlo = lo <= 0 ? 0u : (lo > 0x7FFFFFFF ? 0x7FFFFFFFu : (uint32_t)lo);
-        *xhi = hi <= 0 ? 0u : (hi > 0x7FFFFFFF ? 0x7FFFFFFFu : (uint32_t)hi);
-        if (*xhi < *xlo) *xhi = *xlo;
+    for (int i = 0; i < SCAN_ITEMS; i++) { if (base + i <= n) cnt[base + i] = e; e += v[i]; }
+    if (threadIdx.x == 0) {
+        blk[blockIdx.x] = tot;
+        __threadfence();
+        last = atomicAdd(&sc->prefix_done, 1u) == gridDim.x - 1;
     }
-}
-
-struct LaneState { uint64_t F, R, W; uint32_t WN; };
-
-// N-aware symbol step (prepend `d` on the left, drop the right-most symbol)
-__device__ __forceinline__ void step_generic(LaneState &s, uint32_t d, const ScanTables &T, uint32_t l) {
-    uint32_t in = d & 3, out = (uint32_t)s.W & 3;
-    bool inN = d & D_N, outN = s.WN & 1;
-    uint64_t tf = (inN ? 0 : T.inF[in]) ^ (outN ? 0 : T.outF[out]);
-    uint64_t tr = (inN ? 0 : T.inR[in]) ^ (outN ? 0 : T.outR[out]);
-    s.F = ror1(s.F) ^ tf; s.R = rol1(s.R) ^ tr;
-    s.W = (s.W >> 2) | ((uint64_t)in << (2 * l - 2));
-    s.WN = (s.WN >> 1) | ((inN ? 1u : 0u) << (l - 1));
-}
-
-template <bool HAS_N>
-__device__ __forceinline__ void emit_event(uint32_t x, uint64_t h, uint32_t lane, uint32_t &nloc, uint32_t *tile_ev_smem,
-                                           uint32_t tile, const ScanArgs &a) {
-    uint32_t slot = atomicAdd(tile_ev_smem, 1u);
-    uint32_t meta = x | (lane << 14) | (nloc << 19);
-    nloc++;
-    if (slot < EV_CAP) {
-        a.ev_hash[(uint64_t)tile * EV_CAP + slot] = h;
-        a.ev_meta[(uint64_t)tile * EV_CAP + slot] = meta;
-    } else {
-        uint32_t g = atomicAdd(a.ovf_count, 1u);
-        if (g < a.ovf_cap) { a.ovf_tile[g] = tile; a.ovf_meta[g] = meta; a.ovf_hash[g] = h; }
-    }
-}
-
-__global__ void __launch_bounds__(SCAN_WARPS * 32) k_scan_minimizers(ScanArgs a, ScanTables Tin) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
-    __shared__ ScanTables T;
-    __shared__ uint32_t ev_cnt[SCAN_WARPS];
-    for (uint32_t i = threadIdx.x; i < sizeof(ScanTables) / 8; i += blockDim.x) ((uint64_t *)&T)[i] = ((const uint64_t *)&Tin)[i];
     __syncthreads();
-    const uint32_t lane = lane_id(), wid = threadIdx.x >> 5;
-    uint8_t *S = smem_raw + (size_t)wid * TILE_SMEM;
-    const uint32_t l = a.l;
-    const bool hpc = a.use_hpc != 0;
-    const uint32_t bound_hi = (uint32_t)(a.bound >> 32);
-
-    for (;;) {
-        uint32_t tile = 0;
-        if (lane == 0) tile = atomicAdd(a.tile_ticket, 1u);
-        tile = __shfl_sync(0xffffffffu, tile, 0);
-        if (tile >= a.n_tiles) break;
-        if (lane == 0) ev_cnt[wid] = 0;
-
-        // ---- geometry -------------------------------------------------------------------------
-        const uint32_t sq = a.tile_seq[tile];
-        const uint64_t gs = a.offs[sq], ge = a.offs[sq + 1];
-        const uint64_t A = gs & ~3ull;
-        const uint32_t ft = a.first_tile[sq], nt = a.first_tile[sq + 1] - ft, ti = tile - ft;
-        const uint32_t span = (uint32_t)(ge - A), dv = 32u * nt;
-        uint32_t Cs = (span + dv - 1) / dv;
-        Cs = (Cs + 7u) & ~7u;                                   // multiple of 8 => odd word stride with the pad
-        const uint32_t TWs = 32u * Cs, stride = Cs + LANE_PAD;
-        const uint64_t tlo = A + (uint64_t)ti * TWs;            // aligned address of x' = 0
-        uint32_t nloc = 0;
-        if (tlo >= ge) {                                        // empty tail tile
-            a.lane_cnt[(uint64_t)tile * 32 + lane] = 0;
-            if (lane == 0) a.tile_cnt[tile] = 0;
-            continue;
-        }
-        const uint32_t own_lo = gs > tlo ? (uint32_t)(gs - tlo) : 0u;
-        const uint32_t own_hi = (ge - tlo) < TWs ? (uint32_t)(ge - tlo) : TWs;      // exclusive
-        const uint32_t magic = 0xFFFFFFFFu / Cs + 1u;          // x / Cs == umulhi(x, magic) for x < 2^16
-        uint32_t xlo, xlim; emit_window(a, sq, gs, tlo, &xlo, &xlim);   // segment scans only
-
-        // ---- stage + digest the tile ------------------------------------------------------------
-        const uint32_t *gw = (const uint32_t *)(a.seqs + tlo);
-        uint32_t nwords = (own_hi + 3) >> 2;
-        uint32_t carry = 0;                                     // last byte of the previous word row
-        if (tlo > 0 && lane == 0) carry = a.seqs[tlo - 1];
-        carry = __shfl_sync(0xffffffffu, carry, 0);
-        uint32_t anyN = 0;
-        for (uint32_t w0 = 0; w0 < nwords; w0 += 32) {
-            uint32_t w = w0 + lane;
-            uint32_t u = (w < nwords) ? __ldg(gw + w) : 0u;
-            uint32_t up = __shfl_up_sync(0xffffffffu, u, 1);
-            uint32_t prevb = lane == 0 ? carry : (up >> 24);
-            carry = __shfl_sync(0xffffffffu, u, 31) >> 24;
-            uint32_t dg = digest_word(u, (u << 8) | prevb, hpc);
-            uint32_t x = w << 2;
-            if (x < own_lo || x + 4 > own_hi) {                 // partial word: blank bytes outside the record
-                uint32_t m = 0;
-#pragma unroll
-                for (int b = 0; b < 4; b++) if (x + b >= own_lo && x + b < own_hi) m |= 0xFFu << (8 * b);
-                dg &= m;
-            }
-            if (x <= own_lo && own_lo < x + 4 && tlo + own_lo == gs) dg |= D_RUN << (8 * (own_lo - x));  // record start
-            if (w < nwords) {
-                anyN |= dg & 0x04040404u;
-                uint32_t ch = __umulhi(x, magic);
-                *(uint32_t *)(S + x + ch * LANE_PAD) = dg;
-            }
-        }
-        // blank the rest of the tile window (words beyond the record end) so stale bytes are inert
-        for (uint32_t w = nwords + lane; w < (TWs >> 2); w += 32) {
-            uint32_t x = w << 2; uint32_t ch = __umulhi(x, magic);
-            *(uint32_t *)(S + x + ch * LANE_PAD) = 0u;
-        }
-
-        // ---- halo: up to l-1 further run starts right of the tile -------------------------------
-        uint32_t hcount = 0;
-        uint8_t *H = S + 32u * stride;
-        if (tlo + TWs < ge) {
-            uint64_t haddr = tlo + TWs;                         // 4-aligned
-            uint32_t hcarry = __shfl_sync(0xffffffffu, carry, 0);
-            while (hcount < l - 1 && haddr < ge) {
-                uint64_t wa = haddr + 4ull * lane;
-                uint32_t u = (wa < ge) ? __ldg((const uint32_t *)(a.seqs + wa)) : 0u;
-                uint32_t up = __shfl_up_sync(0xffffffffu, u, 1);
-                uint32_t prevb = lane == 0 ? hcarry : (up >> 24);
-                hcarry = __shfl_sync(0xffffffffu, u, 31) >> 24;
-                uint32_t dg = digest_word(u, (u << 8) | prevb, hpc);
-                uint32_t m = 0;
-#pragma unroll
-                for (int b = 0; b < 4; b++) if (wa + b < ge) m |= 0xFFu << (8 * b);
-                dg &= m;
-                uint32_t runs = (dg >> 3) & 0x01010101u;
-                uint32_t mine = __popc(runs), tot;
-                uint32_t before = warp_excl_scan(mine, &tot);
-                uint32_t r = hcount + before;
-#pragma unroll
-                for (int b = 0; b < 4; b++) {
-                    if ((dg >> (8 * b)) & D_RUN) { if (r < l - 1) { H[r] = (uint8_t)(dg >> (8 * b)); anyN |= (dg >> (8 * b)) & D_N; } r++; }
-                }
-                hcount = min(hcount + tot, l - 1);
-                haddr += 128;
-            }
-        }
-        anyN = __any_sync(0xffffffffu, anyN != 0);
-        __syncwarp();
-        // logical end of the symbols a right-walk may visit: a full tile continues into its halo, a
-        // partial (record-final) tile ends with the record -- do not walk its blank tail
-        const uint32_t data_end = own_hi < TWs ? own_hi : TWs + hcount;
-
-        // ---- warm-up: window of the l-1 symbols right of my chunk (append mode) ------------------
-        LaneState st; st.F = 0; st.R = 0; st.W = 0; st.WN = 0;
-        const uint32_t lo = lane * Cs, hi = lo + Cs;
-        uint32_t m = 0;                                        // real symbols in the window
-        {
-            uint32_t x = hi, p = (lane + 1) * stride, xo = 0;
-            while (m < l - 1 && x < data_end) {
-                uint32_t d = S[p];
-                if (d & D_RUN) {
-                    uint32_t c = d & 3;
-                    if (!(d & D_N)) { st.F ^= rol64(T.h[c], l - 1 - m); st.R ^= rol64(T.hc[c], m); }
-                    else st.WN |= 1u << (l - 1 - m);
-                    st.W |= (uint64_t)c << (2 * (l - 1 - m));
-                    m++;
-                }
-                x++; p++; xo++;
-                if (xo == Cs && x <= TWs) { p += LANE_PAD; xo = 0; }
-            }
-        }
-        uint32_t need = (l - 1) - m;                           // symbols to consume before a window is complete
-        // Indices m..l-1 of the window are still empty (index l-1 always is: the warm-up collects l-1
-        // symbols).  Fill them with phantom 'A's: every prepend drops index l-1, so each phantom is
-        // XORed out again exactly when it leaves and never reaches an emitted hash.
-        for (uint32_t i = m; i < l; i++) {
-            st.F ^= rol64(T.h[0], l - 1 - i); st.R ^= rol64(T.hc[0], i);
-        }
-
-        // ---- main backward scan over my chunk --------------------------------------------------
-        uint32_t *tev = &ev_cnt[wid];
-        int x = (int)hi - 1;
-        const uint8_t *P = S + lane * stride;                  // P[x - lo]
-        // non-emitting steps until the window is complete (record-end lanes only)
-        while (need > 0 && x >= (int)lo) {
-            uint32_t d = P[x - (int)lo];
-            if (d & D_RUN) { step_generic(st, d, T, l); need--; }
-            x--;
-        }
-        if (anyN) {
-            for (; x >= (int)lo; x--) {
-                uint32_t d = P[x - (int)lo];
-                if (d & D_RUN) {
-                    step_generic(st, d, T, l);
-                    uint32_t fh = (uint32_t)(st.F >> 32), rh = (uint32_t)(st.R >> 32);
-                    if (min(fh, rh) <= bound_hi) {
-                        uint64_t h = st.F < st.R ? st.F : st.R;
-                        if (h < a.bound && (uint32_t)x - xlo < xlim - xlo) emit_event<true>((uint32_t)x, h, lane, nloc, tev, tile, a);
-                    }
-                }
-            }
-        } else {
-            uint64_t F = st.F, R = st.R, W = st.W;
-            const uint32_t sh = 2 * l - 2;
-            for (; x >= (int)lo; x--) {
-                uint32_t d = P[x - (int)lo];
-                if (d & D_RUN) {
-                    uint32_t in = d & 3;
-                    uint32_t idx = in | (((uint32_t)W & 3u) << 2);
-                    F = ror1(F) ^ T.pairF[idx];
-                    R = rol1(R) ^ T.pairR[idx];
-                    W = (W >> 2) | ((uint64_t)in << sh);
-                    uint32_t fh = (uint32_t)(F >> 32), rh = (uint32_t)(R >> 32);
-                    if (min(fh, rh) <= bound_hi) {
-                        uint64_t h = F < R ? F : R;
-                        if (h < a.bound && (uint32_t)x - xlo < xlim - xlo) emit_event<false>((uint32_t)x, h, lane, nloc, tev, tile, a);
-                    }
-                }
-            }
-        }
-        __syncwarp();
-        a.lane_cnt[(uint64_t)tile * 32 + lane] = (uint16_t)nloc;
-        if (lane == 0) a.tile_cnt[tile] = *tev;
-        __syncwarp();
+    if (!last) return;
+    __threadfence();
+    // the last block: exclusive scan of the block totals (64-bit carry: a batch may hold >= 2^32 minimizers, which
+    // is reported, never wrapped)
+    unsigned long long carry = 0;
+    for (uint32_t b0 = 0; b0 < gridDim.x; b0 += SCAN_BLK) {
+        const uint32_t i = b0 + threadIdx.x;
+        const uint32_t x = i < gridDim.x ? *(volatile uint32_t *)(blk + i) : 0u;
+        uint32_t t2, e2 = block_excl_scan_1024(x, sm, &t2);
+        if (i < gridDim.x) blk[i] = (uint32_t)(carry + e2);
+        carry += t2;
+        // partial sums above 2^32 - 1 would wrap inside one 1024-block round only if a single round held > 2^32
+        // minimizers, i.e. > 2^32 / 8192 per tile: impossible (a tile holds <= 4096 bases)
     }
+    if (threadIdx.x == 0) {
+        sc->n_minimizers = carry;
+        uint32_t f = 0;
+        if (carry > mini_cap) f |= BS_MINI_CAP;
+        if (carry >= (1ull << 32) - 64) f |= BS_RANGE;
+        if (*(volatile uint32_t *)&sc->ovf_count > ovf_cap) f |= BS_OVF_CAP;
+        if (f) sc->flags = f;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// tiles: a warp-tile covers up to TW_MAX raw bases of one record, on a 16-base aligned grid
+// ------------------------------------------------------------------------------------------------
+#ifndef MQ_CS_MAX
+#define MQ_CS_MAX 128
+#endif
+constexpr int CS_MAX   = MQ_CS_MAX;         // raw bases per lane chunk (<= 128, multiple of 16)
+constexpr int TW_MAX   = 32 * CS_MAX;       // raw bases per warp tile
+// tiles of record [gs, ge) (host and device use the same formula)
+__host__ __device__ inline uint32_t tiles_of_record(uint64_t gs, uint64_t ge, uint32_t min_len) {
+    const uint64_t len = ge - gs;
+    if (len < min_len || len == 0) return 0;
+    return (uint32_t)((ge - (gs & ~15ull) + TW_MAX - 1) / TW_MAX);
+}
+__device__ __forceinline__ void tile_geometry(uint64_t gs, uint64_t ge, uint32_t nt, uint32_t ti, uint32_t *Cs, uint64_t *tlo) {
+    const uint64_t A = gs & ~15ull;
+    const uint32_t span = (uint32_t)(ge - A), d = 32u * nt;     // records are < 2^31 bases: 32-bit division is exact
+    uint32_t c = (span + d - 1) / d;
+    c = (c + 15u) & ~15u;
+    *Cs = c; *tlo = A + (uint64_t)ti * 32u * c;
 }
 
 // ordered compaction: event (lane, j) of tile t -> rank = excl(lane) + n_lane - 1 - j
 struct GatherArgs {
     const uint64_t *ev_hash; const uint32_t *ev_meta; const uint16_t *lane_cnt;
-    const uint32_t *tile_base;       // exclusive scan of the per-tile totals, n_tiles+1 entries
+    TileBase tb;                     // exclusive prefix of the per-tile totals
     const uint32_t *tile_seq; const uint32_t *first_tile; const uint64_t *offs;
     const uint32_t *pos_base;        // per record: position of its first byte inside its reference (or NULL)
     uint32_t n_tiles;
-    uint32_t grid_align;             // 4: k_scan_minimizers (v1) tiles, 16: k_scan_minimizers_v2 tiles
+    const BatchScalars *sc;
     uint32_t *out_pos; uint64_t *out_hash;
 };
-__device__ __forceinline__ void tile_origin(const GatherArgs &g, uint32_t tile, int64_t *x0_to_pos) {
-    uint32_t sq = g.tile_seq[tile];
-    const uint64_t am = (uint64_t)g.grid_align - 1;
-    uint64_t gs = g.offs[sq], ge = g.offs[sq + 1], A = gs & ~am;
-    uint32_t ft = g.first_tile[sq], nt = g.first_tile[sq + 1] - ft, ti = tile - ft;
-    const uint32_t span = (uint32_t)(ge - A), dv = 32u * nt;
-    uint32_t Cs = (span + dv - 1) / dv;
-    const uint32_t cm = g.grid_align == 16 ? 15u : 7u;
-    Cs = (Cs + cm) & ~cm;
-    uint64_t tlo = A + (uint64_t)ti * 32u * Cs;
-    *x0_to_pos = (int64_t)tlo - (int64_t)gs + (g.pos_base ? (int64_t)g.pos_base[sq] : 0);
-}
-// A warp handles GATHER_TPW tiles (typically ~50 events each; 1 is fastest: 0.138 ms vs 0.144 / 0.160 ms for 2 / 4 on the
-// bench workload -- more warps beat more loads per warp), so the kernel lives on memory-level parallelism: the
-// loads of all its tiles are issued in two dependency levels -- everything addressable from the tile id first, then the
-// record geometry and the first 64 events together -- instead of one dependent load after another.
-#ifndef MQ_GATHER_TPW
-#define MQ_GATHER_TPW 1
-#endif
-constexpr int GATHER_TPW = MQ_GATHER_TPW;
+// A warp handles one tile (typically ~50 events), so the kernel lives on memory-level parallelism: its loads are
+// issued in two dependency levels -- everything addressable from the tile id first, then the record geometry and the
+// first 64 events together -- instead of one dependent load after another.
 __global__ void __launch_bounds__(256) k_gather_minimizers(GatherArgs g) {
-    const uint32_t tile0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * GATHER_TPW;
-    if (tile0 >= g.n_tiles) return;
+    const uint32_t tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (tile >= g.n_tiles || g.sc->flags) return;
     const uint32_t lane = lane_id();
-    uint32_t base[GATHER_TPW], total[GATHER_TPW], n[GATHER_TPW], sq[GATHER_TPW];
     // level 1
-#pragma unroll
-    for (int t = 0; t < GATHER_TPW; t++) {
-        const uint32_t tile = tile0 + t;
-        base[t] = 0; total[t] = 0; n[t] = 0; sq[t] = 0;
-        if (tile < g.n_tiles) {
-            base[t] = __ldg(g.tile_base + tile); total[t] = __ldg(g.tile_base + tile + 1);
-            n[t] = __ldg(g.lane_cnt + (uint64_t)tile * 32 + lane);
-            sq[t] = __ldg(g.tile_seq + tile);
-        }
-    }
-    // level 2: geometry of the records and the first two rounds of events
-    uint32_t meta0[GATHER_TPW], meta1[GATHER_TPW], staged[GATHER_TPW], ft[GATHER_TPW], nt[GATHER_TPW];
-    uint64_t h0[GATHER_TPW], h1[GATHER_TPW], gs[GATHER_TPW], ge[GATHER_TPW]; int64_t pb[GATHER_TPW];
-#pragma unroll
-    for (int t = 0; t < GATHER_TPW; t++) {
-        total[t] -= base[t];
-        staged[t] = total[t] < EV_CAP ? total[t] : EV_CAP;
-        const uint64_t eb = (uint64_t)(tile0 + t) * EV_CAP;
-        meta0[t] = meta1[t] = 0; h0[t] = h1[t] = 0; gs[t] = ge[t] = 0; ft[t] = 0; nt[t] = 1; pb[t] = 0;
-        if (total[t]) {
-            if (lane < staged[t]) { meta0[t] = g.ev_meta[eb + lane]; h0[t] = g.ev_hash[eb + lane]; }
-            if (lane + 32 < staged[t]) { meta1[t] = g.ev_meta[eb + lane + 32]; h1[t] = g.ev_hash[eb + lane + 32]; }
-            gs[t] = __ldg(g.offs + sq[t]); ge[t] = __ldg(g.offs + sq[t] + 1);
-            ft[t] = __ldg(g.first_tile + sq[t]); nt[t] = __ldg(g.first_tile + sq[t] + 1) - ft[t];
-            pb[t] = g.pos_base ? (int64_t)__ldg(g.pos_base + sq[t]) : 0;
-        }
-    }
-#pragma unroll
-    for (int t = 0; t < GATHER_TPW; t++) {
-        if (total[t] == 0) continue;                       // warp-uniform
-        const uint32_t tile = tile0 + t;
-        const uint64_t eb = (uint64_t)tile * EV_CAP;
-        const uint64_t am = (uint64_t)g.grid_align - 1, A = gs[t] & ~am;
-        const uint32_t ti = tile - ft[t];
-        uint32_t tot;
-        const uint32_t ex = warp_excl_scan(n[t], &tot);
-        const uint32_t span = (uint32_t)(ge[t] - A), dv = 32u * nt[t];
-        uint32_t Cs = (span + dv - 1) / dv;
-        const uint32_t cm = g.grid_align == 16 ? 15u : 7u;
-        Cs = (Cs + cm) & ~cm;
-        const int64_t org = (int64_t)(A + (uint64_t)ti * 32u * Cs) - (int64_t)gs[t] + pb[t];
-        for (uint32_t s0 = 0; s0 < staged[t]; s0 += 32) {
-            const uint32_t s = s0 + lane;
-            uint32_t meta; uint64_t h;
-            if (s0 == 0) { meta = meta0[t]; h = h0[t]; }
-            else if (s0 == 32) { meta = meta1[t]; h = h1[t]; }
-            else { meta = 0; h = 0; if (s < staged[t]) { meta = g.ev_meta[eb + s]; h = g.ev_hash[eb + s]; } }
-            const uint32_t ln = (meta >> 14) & 31, j = meta >> 19;
-            const uint32_t e = __shfl_sync(0xffffffffu, ex, ln), c = __shfl_sync(0xffffffffu, n[t], ln);
-            if (s < staged[t]) {
-                const uint32_t rank = e + c - 1 - j;
-                g.out_pos[base[t] + rank] = (uint32_t)((int64_t)(meta & 0x3FFF) + org);
-                g.out_hash[base[t] + rank] = h;
-            }
+    const uint32_t base = tile_base(g.tb, tile), total = tile_base(g.tb, tile + 1) - base;
+    const uint32_t n = __ldg(g.lane_cnt + (uint64_t)tile * 32 + lane);
+    const uint32_t sq = __ldg(g.tile_seq + tile);
+    if (total == 0) return;                                // warp-uniform
+    // level 2: geometry of the record and the first two rounds of events
+    const uint32_t staged = total < EV_CAP ? total : EV_CAP;
+    const uint64_t eb = (uint64_t)tile * EV_CAP;
+    uint32_t meta0 = 0, meta1 = 0; uint64_t h0 = 0, h1 = 0;
+    if (lane < staged) { meta0 = g.ev_meta[eb + lane]; h0 = g.ev_hash[eb + lane]; }
+    if (lane + 32 < staged) { meta1 = g.ev_meta[eb + lane + 32]; h1 = g.ev_hash[eb + lane + 32]; }
+    const uint64_t gs = __ldg(g.offs + sq), ge = __ldg(g.offs + sq + 1);
+    const uint32_t ft = __ldg(g.first_tile + sq), nt = __ldg(g.first_tile + sq + 1) - ft;
+    const int64_t pb = g.pos_base ? (int64_t)__ldg(g.pos_base + sq) : 0;
+    uint32_t tot;
+    const uint32_t ex = warp_excl_scan(n, &tot);
+    uint32_t Cs; uint64_t tlo;
+    tile_geometry(gs, ge, nt, tile - ft, &Cs, &tlo);
+    const int64_t org = (int64_t)tlo - (int64_t)gs + pb;
+    for (uint32_t s0 = 0; s0 < staged; s0 += 32) {
+        const uint32_t s = s0 + lane;
+        uint32_t meta; uint64_t h;
+        if (s0 == 0) { meta = meta0; h = h0; }
+        else if (s0 == 32) { meta = meta1; h = h1; }
+        else { meta = 0; h = 0; if (s < staged) { meta = g.ev_meta[eb + s]; h = g.ev_hash[eb + s]; } }
+        const uint32_t ln = (meta >> 14) & 31, j = meta >> 19;
+        const uint32_t e = __shfl_sync(0xffffffffu, ex, ln), c = __shfl_sync(0xffffffffu, n, ln);
+        if (s < staged) {
+            const uint32_t rank = e + c - 1 - j;
+            g.out_pos[base + rank] = (uint32_t)((int64_t)(meta & 0x3FFF) + org);
+            g.out_hash[base + rank] = h;
         }
     }
 }
-__global__ void k_gather_overflow(GatherArgs g, const uint32_t *ovf_tile, const uint32_t *ovf_meta, const uint64_t *ovf_hash,
-                                  uint32_t n_ovf) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_ovf) return;
-    uint32_t tile = ovf_tile[i], meta = ovf_meta[i];
-    uint32_t ln = (meta >> 14) & 31, j = meta >> 19, e = 0;
-    for (uint32_t q = 0; q < ln; q++) e += g.lane_cnt[(uint64_t)tile * 32 + q];
-    uint32_t c = g.lane_cnt[(uint64_t)tile * 32 + ln];
-    int64_t org; tile_origin(g, tile, &org);
-    uint32_t rank = e + c - 1 - j;
-    g.out_pos[g.tile_base[tile] + rank] = (uint32_t)((int64_t)(meta & 0x3FFF) + org);
-    g.out_hash[g.tile_base[tile] + rank] = ovf_hash[i];
+// events that did not fit their tile's pool (density close to 1): grid-stride over the overflow pool
+__global__ void __launch_bounds__(256) k_gather_overflow(GatherArgs g, const uint32_t *ovf_tile, const uint32_t *ovf_meta, const uint64_t *ovf_hash) {
+    if (g.sc->flags) return;
+    const uint32_t n_ovf = g.sc->ovf_count;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_ovf; i += gridDim.x * blockDim.x) {
+        const uint32_t tile = ovf_tile[i], meta = ovf_meta[i];
+        const uint32_t ln = (meta >> 14) & 31, j = meta >> 19;
+        uint32_t e = 0;
+        for (uint32_t q = 0; q < ln; q++) e += g.lane_cnt[(uint64_t)tile * 32 + q];
+        const uint32_t c = g.lane_cnt[(uint64_t)tile * 32 + ln];
+        const uint32_t sq = g.tile_seq[tile];
+        const uint64_t gs = g.offs[sq], ge = g.offs[sq + 1];
+        const uint32_t ft = g.first_tile[sq], nt = g.first_tile[sq + 1] - ft;
+        uint32_t Cs; uint64_t tlo;
+        tile_geometry(gs, ge, nt, tile - ft, &Cs, &tlo);
+        const int64_t org = (int64_t)tlo - (int64_t)gs + (g.pos_base ? (int64_t)g.pos_base[sq] : 0);
+        const uint32_t rank = e + c - 1 - j, base = tile_base(g.tb, tile);
+        g.out_pos[base + rank] = (uint32_t)((int64_t)(meta & 0x3FFF) + org);
+        g.out_hash[base + rank] = ovf_hash[i];
+    }
 }
-// seq_off[i] = tile_base[first_tile[i]]  (i <= n; tile_base has n_tiles+1 entries)
-__global__ void k_seq_mini_off(const uint32_t *first_tile, const uint32_t *tile_base, uint32_t n, uint32_t *seq_off) {
+// seq_off[i] = prefix of record i's first tile (i <= n): the minimizer range of each record, materialised for the
+// callers that want it as a plain array (index build, introspection); the mapping kernels read it through tile_base
+__global__ void k_seq_mini_off(const uint32_t *first_tile, TileBase tb, uint32_t n, uint32_t *seq_off) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i <= n) seq_off[i] = tile_base[first_tile[i]];
+    if (i <= n) seq_off[i] = tile_base(tb, first_tile[i]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -686,21 +402,23 @@ __global__ void k_index_get(Table t, const uint64_t *keys, uint64_t n, uint8_t *
 // ------------------------------------------------------------------------------------------------
 struct ProbeArgs {
     const uint32_t *pos; const uint64_t *hash;     // minimizers of the batch
-    const uint32_t *seq_off;                       // n+1 : minimizer range of each read
+    const uint32_t *first_tile; TileBase tb;       // minimizer range of read r: tile_base(first_tile[r]) .. tile_base(first_tile[r+1])
+    const BatchScalars *sc;
     uint32_t n_reads, k, l;
-    MatchRec *matches;                             // read r writes at seq_off[r] + ordinal
+    MatchRec *matches;                             // read r writes at (its first minimizer) + ordinal
     uint32_t *n_matches;                           // per read
     uint32_t *read_ticket;
 };
 
 __global__ void __launch_bounds__(128) k_probe_match(ProbeArgs a, Table t) {
     const uint32_t lane = lane_id();
+    if (a.sc->flags) return;
     for (;;) {
         uint32_t r = 0;
         if (lane == 0) r = atomicAdd(a.read_ticket, 1u);
         r = __shfl_sync(0xffffffffu, r, 0);
         if (r >= a.n_reads) break;
-        const uint32_t m0 = a.seq_off[r], m1 = a.seq_off[r + 1];
+        const uint32_t m0 = tile_base(a.tb, __ldg(a.first_tile + r)), m1 = tile_base(a.tb, __ldg(a.first_tile + r + 1));
         const uint32_t M = m1 - m0, Q = M >= a.k ? M - a.k + 1 : 0;
         MatchRec *out = a.matches + m0;
         uint32_t n_heads = 0;                       // matches opened so far (warp-uniform)
@@ -811,7 +529,8 @@ __device__ __forceinline__ bool compatible(const M6 &h1, const M6 &h2, uint32_t 
 }
 
 struct ChainArgs {
-    const MatchRec *matches; const uint32_t *n_matches; const uint32_t *seq_off; const uint64_t *offs;
+    const MatchRec *matches; const uint32_t *n_matches; const uint32_t *first_tile; TileBase tb; const BatchScalars *sc;
+    const uint64_t *offs;
     const uint64_t *ref_lens; uint32_t n_refs;
     uint32_t n_reads, c, s, g;
     HitRec *hits;
@@ -884,10 +603,10 @@ __device__ __forceinline__ void chain_thread(const ChainArgs &a, uint32_t r, uin
 
 __global__ void __launch_bounds__(128) k_chain_small(ChainArgs a) {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= a.n_reads) return;
+    if (r >= a.n_reads || a.sc->flags) return;
     const uint32_t n = a.n_matches[r];
     if (n > CHAIN_SMALL) { a.big_list[atomicAdd(a.big_count, 1u)] = r; return; }
-    const MatchRec *ms = a.matches + a.seq_off[r];
+    const MatchRec *ms = a.matches + tile_base(a.tb, __ldg(a.first_tile + r));
     if (n <= 1) chain_thread<1>(a, r, n, ms);
     else if (n == 2) chain_thread<2>(a, r, n, ms);
     else if (n <= 4) chain_thread<4>(a, r, n, ms);
@@ -897,6 +616,7 @@ __global__ void __launch_bounds__(128) k_chain_small(ChainArgs a) {
 
 __global__ void __launch_bounds__(128) k_chain(ChainArgs a) {
     const uint32_t lane = lane_id();
+    if (a.sc->flags) return;
     for (;;) {
         uint32_t r = 0;
         if (lane == 0) r = atomicAdd(a.read_ticket, 1u);
@@ -904,7 +624,7 @@ __global__ void __launch_bounds__(128) k_chain(ChainArgs a) {
         if (a.big_list) { if (r >= *a.big_count) break; r = a.big_list[r]; }      // only the reads k_chain_small queued
         else if (r >= a.n_reads) break;
         const uint32_t n = a.n_matches[r];
-        const MatchRec *ms = a.matches + a.seq_off[r];
+        const MatchRec *ms = a.matches + tile_base(a.tb, __ldg(a.first_tile + r));
         // best / second-best chain score over references (mers.rs:110-129)
         uint64_t best_score = 0, second = 0; uint32_t groups = 0;
         uint32_t b_ref = 0, b_rc = 0, b_mapq = 0; uint64_t b_qs = 0, b_qe = 0, b_rs = 0, b_re = 0;

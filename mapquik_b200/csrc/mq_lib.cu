@@ -1,22 +1,32 @@
-// mq_lib.cu -- host side of libmapquik_b200.so: context, device memory, kernel launches and the
-// extern "C" entry points declared in include/mapquik_b200.h.  No torch, no CPU fallback: every
-// computing entry point fails with MQ_ERR_CUDA when no CUDA device is usable.
+// mq_lib.cu -- host side of libmapquik_b200.so: contexts, device memory, kernel launches and the extern "C" entry
+// points declared in include/mapquik_b200.h.  No torch, no CPU fallback: every computing entry point fails with
+// MQ_ERR_CUDA when no CUDA device is usable.
+//
+// Shape of the mapping path (mq_map_batch*): the batch is cut into sub-batches of <= SUB_BASES bases that flow
+// through two slots -- upload of sub-batch i+1 (copy stream) overlaps the kernels of sub-batch i (compute stream) and
+// the download of the hits of sub-batch i-1 (d2h stream).  The host never waits for the GPU between the upload of a
+// sub-batch and the download of its hits: tile tables are computed on the host from the offsets it already has,
+// device buffers are sized from upper bounds, and the one thing only the GPU knows (how many minimizers a sub-batch
+// produced, whether a pool overflowed) comes back in a 48-byte status record next to the hits and is looked at when
+// the slot is recycled.  A sub-batch whose status reports an overflow is redone with larger buffers (rare: the
+// bounds assume at most ~3x the expected minimizer density).
 #include "../../include/mapquik_b200.h"
 #include "mq_kernels.cuh"
-#include "mq_scan_v2.cuh"
-#include "mq_scan_v3.cuh"
-#include <cstdlib>
-#include <cstddef>
+#include "mq_scan.cuh"
 
 #include <algorithm>
 #include <array>
 #include <chrono>
+#include <cstddef>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <numeric>
 #include <string>
+#include <thread>
 #include <vector>
+#include <sys/stat.h>
 
 using namespace mq;
 
@@ -26,52 +36,75 @@ struct DBuf {
     void *p = nullptr; size_t cap = 0;
     template <class T> T *as() const { return (T *)p; }
 };
+struct HBuf { void *p = nullptr; size_t cap = 0; };      // pinned host memory
 
-constexpr uint64_t MAP_SUB_BATCH_BYTES = 128ull << 20;  // bases per pipelined mapping sub-batch (H2D of i+1 overlaps compute of i)
-constexpr size_t   PAD = 256;                          // slack after sequence buffers (word loads)
+constexpr uint64_t SUB_BASES = 128ull << 20;            // bases per pipelined mapping sub-batch
+constexpr uint64_t ADD_BASES = 256ull << 20;            // bases per pipelined index-build piece batch
+constexpr size_t   PAD = 256;                          // zeroed slack behind sequence buffers (word loads past the end)
+
+// One piece of work for the scan: bases [lo, hi) of the caller's sequence array form a "record" of the batch.
+// Whole records: lo..hi = the record, emit everything.  Segments of a long reference record: the piece starts one
+// base before seg_start (run context) and extends past its own range by the right halo; only l-mers STARTING in
+// [emit_lo, emit_hi) (piece coordinates) are emitted and positions are shifted by pos_base.
+struct Piece { uint64_t lo, hi; uint32_t ref_idx; uint32_t pos_base, emit_lo, emit_hi; uint64_t seg_start; };
+
+struct BatchDev {              // device view of one staged sub-batch
+    const uint8_t *seqs = nullptr; const uint32_t *packed = nullptr, *flags = nullptr; const ExcRec *exc = nullptr; uint32_t n_exc = 0;
+    uint64_t exc_base = 0;     // exception intervals are in coordinates of (slice base index + exc_base)
+    const uint64_t *offs = nullptr; const uint32_t *first_tile = nullptr, *tile_seq = nullptr, *pos_base = nullptr, *emit = nullptr;
+    uint32_t n = 0, n_tiles = 0; uint64_t bases = 0;
+    BatchScalars *sc = nullptr;
+};
+
+struct Slot2 {                 // resources of one in-flight sub-batch
+    DBuf d_in;                 // ASCII bytes, or packed words
+    DBuf d_meta;               // offs u64[n+1] | first_tile u32[n+1] | tile_seq u32[n_tiles] | pos_base u32[n] | emit u32[2n] | flags | exc
+    HBuf h_meta;
+    DBuf d_hits, d_sc;
+    HBuf h_sc;                 // BatchScalars read back
+    cudaEvent_t ev_copied = nullptr, ev_comp = nullptr, ev_done = nullptr;
+    bool busy = false;
+    BatchDev bd;               // what the slot holds (device view; stays valid until the slot is staged again)
+    uint32_t i0 = 0, i1 = 0;   // records [i0, i1) of the call
+};
 
 }  // namespace
 
 struct mq_ctx {
     mq_params p{};
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr, d2h_stream = nullptr;
     uint64_t bound = 0;
     ScanTables tab{};
-    ScanTablesV2 tab2{};
-    ScanTablesV3 tab3{};
-    int v2_ctas_per_sm = 0;
-    bool scan_v1 = false;          // MQ_SCAN_V1=1 selects the first-generation scan kernel (A/B, debugging)
-    bool scan_v2 = false;          // MQ_SCAN_V2=1 selects the second-generation one (contiguous lane streams)
+    int scan_ctas_per_sm[4] = {0, 0, 0, 0};
     std::string err;
     uint64_t launches = 0, scan_kernel_launches = 0;
     int n_sm = 148;
     cudaEvent_t region_a = nullptr, region_b = nullptr;
     uint64_t last_minimizers = 0;
-    // per-batch workspace
-    DBuf d_seqs, d_offs, d_first_tile, d_tile_seq, d_ev_hash, d_ev_meta, d_lane_cnt, d_tile_cnt, d_blocksums,
-         d_scalars, d_ovf_tile, d_ovf_meta, d_ovf_hash, d_pos, d_hash, d_seq_off, d_matches, d_nmatch, d_hits,
-         d_pos_base, d_emit_len, d_misc, d_big_list;
+    // workspace shared by the sub-batches (used on the compute stream only)
+    DBuf d_ev_hash, d_ev_meta, d_lane_cnt, d_tile_cnt, d_blk, d_ovf_tile, d_ovf_meta, d_ovf_hash, d_pos, d_hash, d_seq_off,
+         d_matches, d_nmatch, d_big_list, d_misc;
     uint32_t ovf_cap = 1u << 16;
+    uint64_t mini_cap = 0;        // entries d_pos / d_hash / d_matches can hold
+    double mini_rate = 0;         // learned upper estimate of minimizers per base (grows on overflow)
+    Slot2 slot[2];
     // minimizer store (reference side)
     DBuf st_pos, st_hash; uint64_t st_n = 0;
     std::vector<std::array<uint64_t, 3>> dir;          // (ref_idx, seg_start, count)
     // frozen index
     DBuf d_table, d_ref_lens; uint64_t tmask = 0; bool frozen = false; uint32_t n_refs = 0;
     std::vector<uint64_t> nb_mers; uint64_t n_unique = 0, n_keys = 0;
-    // pinned bounce buffers
-    void *h_pin = nullptr; size_t h_pin_cap = 0;
-    // double-buffered upload path of mq_map_batch
-    cudaStream_t copy_stream = nullptr;
-    cudaEvent_t ev_copied[2] = {nullptr, nullptr};
-    DBuf d_seqs2[2], d_offs2[2];
-    void *h_offs2[2] = {nullptr, nullptr}; size_t h_offs2_cap[2] = {0, 0};
+    HBuf h_pin;                   // bounce buffer (index save / load)
     // timings
     std::map<std::string, float> ms, ms_total;
     uint64_t timer_gen = 0;
-    struct PendingTimer { std::string name; cudaEvent_t a, b; uint64_t gen; };
+    struct PendingTimer { const char *name; cudaEvent_t a, b; uint64_t gen; };
     std::vector<PendingTimer> pending;
     std::vector<cudaEvent_t> ev_pool;
+    // multi-GPU parent: fans out to one child context per device (mq_create_multi)
+    std::vector<mq_ctx *> kids;
+    std::vector<std::array<uint64_t, 2>> kid_share;     // [first read, last read) mapped by each child in the last call
 };
 
 namespace {
@@ -87,7 +120,7 @@ namespace {
 
 int ensure(mq_ctx *c, DBuf &b, size_t bytes) {
     if (bytes <= b.cap) return MQ_OK;
-    if (b.p) { cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+    if (b.p) { cudaStreamSynchronize(c->stream); cudaFree(b.p); b.p = nullptr; b.cap = 0; }
     size_t want = bytes + bytes / 8 + 256;
     cudaError_t e = cudaMalloc(&b.p, want);
     if (e != cudaSuccess) {
@@ -114,39 +147,46 @@ int ensure_keep(mq_ctx *c, DBuf &b, size_t bytes, size_t keep) {
 }
 void dfree(DBuf &b) { if (b.p) cudaFree(b.p); b.p = nullptr; b.cap = 0; }
 
-int ensure_pin(mq_ctx *c, size_t bytes) {
-    if (bytes <= c->h_pin_cap) return MQ_OK;
-    if (c->h_pin) cudaFreeHost(c->h_pin);
-    c->h_pin = nullptr; c->h_pin_cap = 0;
-    CK(cudaMallocHost(&c->h_pin, bytes + bytes / 4));
-    c->h_pin_cap = bytes + bytes / 4;
+int ensure_host(mq_ctx *c, HBuf &b, size_t bytes) {
+    if (bytes <= b.cap) return MQ_OK;
+    if (b.p) cudaFreeHost(b.p);
+    b.p = nullptr; b.cap = 0;
+    const size_t want = bytes + bytes / 4 + 4096;
+    CK(cudaMallocHost(&b.p, want));
+    b.cap = want;
     return MQ_OK;
 }
+void hfree(HBuf &b) { if (b.p) cudaFreeHost(b.p); b.p = nullptr; b.cap = 0; }
 
-// ---- stage timing (CUDA events on the ctx stream) ----------------------------------------------
+// ---- stage timing (CUDA events on the stream the stage runs on) ----------------------------------
 cudaEvent_t get_event(mq_ctx *c) {
     if (!c->ev_pool.empty()) { cudaEvent_t e = c->ev_pool.back(); c->ev_pool.pop_back(); return e; }
     cudaEvent_t e; cudaEventCreate(&e); return e;
 }
 struct StageTimer {
-    mq_ctx *c; std::string name; cudaEvent_t a, b; cudaStream_t st;
+    mq_ctx *c; const char *name; cudaEvent_t a, b; cudaStream_t st;
     StageTimer(mq_ctx *c_, const char *n, cudaStream_t s_ = nullptr) : c(c_), name(n), st(s_ ? s_ : c_->stream) {
         a = get_event(c); b = get_event(c); cudaEventRecord(a, st);
     }
     ~StageTimer() { cudaEventRecord(b, st); c->pending.push_back({name, a, b, c->timer_gen}); }
 };
-// a new call starts a new generation: per-call figures (mq_last_ms) restart, running totals (mq_total_ms) keep
-// accumulating; nothing is synchronised here
-void timers_reset(mq_ctx *c) { c->ms.clear(); c->timer_gen++; }
-void timers_collect(mq_ctx *c) {
-    for (auto &pr : c->pending) {
+// fold every timer whose end event has completed into the totals (never blocks unless `wait`)
+void timers_collect(mq_ctx *c, bool wait = true) {
+    size_t w = 0;
+    for (size_t i = 0; i < c->pending.size(); i++) {
+        auto &pr = c->pending[i];
+        if (!wait && cudaEventQuery(pr.b) != cudaSuccess) { cudaGetLastError(); c->pending[w++] = pr; continue; }
         float t = 0; cudaEventSynchronize(pr.b); cudaEventElapsedTime(&t, pr.a, pr.b);
         if (pr.gen == c->timer_gen) c->ms[pr.name] += t;
         c->ms_total[pr.name] += t;
         c->ev_pool.push_back(pr.a); c->ev_pool.push_back(pr.b);
     }
-    c->pending.clear();
+    c->pending.resize(w);
 }
+// a new call starts a new generation: per-call figures (mq_last_ms) restart, running totals (mq_total_ms) keep
+// accumulating.  Finished timers of earlier calls are folded in here, so a caller that never asks for timings does
+// not accumulate events.
+void timers_reset(mq_ctx *c) { timers_collect(c, false); c->ms.clear(); c->timer_gen++; }
 
 uint64_t hash_bound(double density) {   // (density as FH * H::MAX as FH) as H, saturating like Rust `as`
     double b = density * 18446744073709551615.0;
@@ -156,186 +196,302 @@ uint64_t hash_bound(double density) {   // (density as FH * H::MAX as FH) as H, 
 }
 uint64_t hrol(uint64_t x, unsigned r) { r &= 63; return r ? (x << r) | (x >> (64 - r)) : x; }
 
+// symbol codes are the raw bits (ascii >> 1) & 3: A=0 C=1 T=2 G=3
 void fill_tables(ScanTables &T, uint32_t l) {
-    const uint64_t h[4] = {SEED_A, SEED_C, SEED_G, SEED_T}, hc[4] = {SEED_T, SEED_G, SEED_C, SEED_A};
-    for (int c = 0; c < 4; c++) {
-        T.h[c] = h[c]; T.hc[c] = hc[c];
-        T.inF[c] = hrol(h[c], l - 1); T.outF[c] = hrol(h[c], 63);
-        T.inR[c] = hc[c];             T.outR[c] = hrol(hc[c], l);
+    memset(&T, 0, sizeof(T));
+    const uint64_t h[4] = {SEED_A, SEED_C, SEED_T, SEED_G}, hc[4] = {SEED_T, SEED_G, SEED_A, SEED_C};
+    for (int i = 0; i < 4; i++) {
+        T.inF[i] = hrol(h[i], l - 1); T.outF[i] = hrol(h[i], 63);
+        T.inR[i] = hc[i];             T.outR[i] = hrol(hc[i], l);
     }
     for (int i = 0; i < 4; i++) for (int o = 0; o < 4; o++) {
-        T.pairF[i | (o << 2)] = T.inF[i] ^ T.outF[o];
-        T.pairR[i | (o << 2)] = T.inR[i] ^ T.outR[o];
+        T.pairF[i + 4 * o] = T.inF[i] ^ T.outF[o];
+        T.pairR[i + 4 * o] = T.inR[i] ^ T.outR[o];
     }
-}
-void fill_tables_v2(ScanTablesV2 &T, const ScanTables &S, uint32_t l) {
-    // v2 symbol codes are the raw bits (c>>1)&3: A=0 C=1 T=2 G=3; S is in A,C,G,T order
-    static const int v1_of[4] = {0, 1, 3, 2};
-    static_assert(offsetof(ScanTablesV2, pairR) == 128 && offsetof(ScanTablesV2, inF) == 256 && offsetof(ScanTablesV2, outF) == 288 &&
-                  offsetof(ScanTablesV2, inR) == 320 && offsetof(ScanTablesV2, outR) == 352 && offsetof(ScanTablesV2, sel) == 400,
-                  "the kernel addresses these tables by byte offset");
-    for (int i = 0; i < 4; i++) {
-        T.inF[i] = S.inF[v1_of[i]]; T.outF[i] = S.outF[v1_of[i]]; T.inR[i] = S.inR[v1_of[i]]; T.outR[i] = S.outR[v1_of[i]];
-        for (int o = 0; o < 4; o++) {
-            T.pairF[i + 4 * o] = S.pairF[v1_of[i] | (v1_of[o] << 2)];
-            T.pairR[i + 4 * o] = S.pairR[v1_of[i] | (v1_of[o] << 2)];
-        }
-    }
-    T.F0 = 0; T.R0 = 0;                       // window of l phantom 'A's
-    for (uint32_t i = 0; i < l; i++) { T.F0 ^= hrol(SEED_A, l - 1 - i); T.R0 ^= hrol(SEED_T, i); }
-    for (uint32_t p = 0; p < 16; p++) {       // byte-permute selectors: run-start bytes first, zero fill
+    for (uint32_t i = 0; i < l; i++) { T.F0 ^= hrol(SEED_A, l - 1 - i); T.R0 ^= hrol(SEED_T, i); }   // window of l phantom 'A's
+    auto selector = [](uint32_t p) {          // byte-permute selector: run-start bytes first, zero fill
         uint32_t sel = 0, j = 0;
         for (uint32_t b = 0; b < 4; b++) if (p & (1u << b)) sel |= b << (4 * j++);
         for (; j < 4; j++) sel |= 4u << (4 * j);
-        T.sel[p] = sel;
-    }
+        return sel;
+    };
+    for (uint32_t p = 0; p < 16; p++) T.sel[p] = selector(p);
+    for (uint32_t q = 0; q < 86; q++) T.sel55[q] = selector((q & 1u) | ((q >> 1) & 2u) | ((q >> 2) & 4u) | ((q >> 3) & 8u));
 }
 
-// scalars block layout (u64 words): 0 scan total, 1 counts[2] .. ; u32 view used for tickets
-enum { SC_TOTAL = 0, SC_COUNT0 = 1, SC_COUNT1 = 2, SC_TICKET = 3 /* u32[2] : ticket, ovf */, SC_WORDS = 8 };
+// ---- tile tables (host) ------------------------------------------------------------------------------
+// layout of a slot's meta block; offsets in bytes, all 16-byte aligned
+struct MetaLayout {
+    size_t offs, first_tile, tile_seq, pos_base, emit, flags, exc, total;
+    MetaLayout(uint32_t n, uint32_t n_tiles, bool pieces, size_t flag_words, size_t n_exc) {
+        auto al = [](size_t x) { return (x + 15) & ~(size_t)15; };
+        size_t o = 0;
+        offs = o; o = al(o + ((size_t)n + 1) * 8);
+        first_tile = o; o = al(o + ((size_t)n + 1) * 4);
+        tile_seq = o; o = al(o + (size_t)n_tiles * 4);
+        pos_base = o; o = al(o + (pieces ? (size_t)n * 4 : 0));
+        emit = o; o = al(o + (pieces ? (size_t)n * 8 : 0));
+        flags = o; o = al(o + flag_words * 4);
+        exc = o; o = al(o + n_exc * sizeof(ExcRec));
+        total = o;
+    }
+};
 
-// exclusive scan of n u32 values in place; out gets n+1 entries when write_total; total -> host
-int excl_scan(mq_ctx *c, uint32_t *data, uint64_t n, bool write_total, uint64_t *total_host) {
-    uint32_t nb = (uint32_t)((n + SCAN_BLK * SCAN_ITEMS - 1) / (SCAN_BLK * SCAN_ITEMS));
-    if (nb == 0) nb = 1;
-    int rc = ensure(c, c->d_blocksums, (size_t)nb * 4); if (rc) return rc;
-    uint64_t *d_total = c->d_scalars.as<uint64_t>() + SC_TOTAL;
-    k_scan_block_sums<<<nb, SCAN_BLK, 0, c->stream>>>(data, n, c->d_blocksums.as<uint32_t>());
-    k_scan_sums<<<1, SCAN_BLK, 0, c->stream>>>(c->d_blocksums.as<uint32_t>(), nb, d_total);
-    k_scan_apply<<<nb, SCAN_BLK, 0, c->stream>>>(data, n, c->d_blocksums.as<uint32_t>(), data, write_total ? 1 : 0);
-    c->launches += 3;
-    CK(cudaGetLastError());
-    if (total_host) {
-        CK(cudaMemcpyAsync(total_host, d_total, 8, cudaMemcpyDeviceToHost, c->stream));
-        CK(cudaStreamSynchronize(c->stream));
+uint64_t mini_estimate(const mq_ctx *c, uint64_t bases) {
+    double rate = c->mini_rate;
+    if (rate <= 0) { rate = 2.0 * c->p.density * 1.5 + 0.004; }
+    if (rate > 1.0) rate = 1.0;
+    uint64_t est = (uint64_t)(rate * (double)bases) + 65536;
+    return std::min<uint64_t>(est, bases + 64);
+}
+
+int ensure_workspace(mq_ctx *c, uint32_t n, uint32_t n_tiles, uint64_t bases, bool for_map) {
+    int rc;
+    if ((rc = ensure(c, c->d_ev_hash, (size_t)n_tiles * EV_CAP * 8 + 64))) return rc;
+    if ((rc = ensure(c, c->d_ev_meta, (size_t)n_tiles * EV_CAP * 4 + 64))) return rc;
+    if ((rc = ensure(c, c->d_lane_cnt, (size_t)n_tiles * 32 * 2 + 64))) return rc;
+    if ((rc = ensure(c, c->d_tile_cnt, ((size_t)n_tiles + 2) * 4))) return rc;
+    if ((rc = ensure(c, c->d_blk, ((size_t)n_tiles / PREFIX_SPAN + 2) * 4))) return rc;
+    if ((rc = ensure(c, c->d_ovf_tile, (size_t)c->ovf_cap * 4))) return rc;
+    if ((rc = ensure(c, c->d_ovf_meta, (size_t)c->ovf_cap * 4))) return rc;
+    if ((rc = ensure(c, c->d_ovf_hash, (size_t)c->ovf_cap * 8))) return rc;
+    const uint64_t want = mini_estimate(c, bases);
+    if (want > c->mini_cap) {
+        if ((rc = ensure(c, c->d_pos, (want + 64) * 4))) return rc;
+        if ((rc = ensure(c, c->d_hash, (want + 64) * 8))) return rc;
+        c->mini_cap = want;
+    }
+    if (for_map) {
+        if ((rc = ensure(c, c->d_matches, (c->mini_cap + 64) * sizeof(MatchRec)))) return rc;
+        if ((rc = ensure(c, c->d_nmatch, ((size_t)n + 1) * 4))) return rc;
+        if ((rc = ensure(c, c->d_big_list, ((size_t)n + 2) * 4))) return rc;
     }
     return MQ_OK;
 }
 
-// S1 on a device-resident batch.  Result: c->d_pos / c->d_hash (M entries), c->d_seq_off (n+1).
-int run_scan(mq_ctx *c, const uint8_t *d_seqs, const uint64_t *d_offs, uint32_t n, uint32_t min_len,
-             const uint32_t *d_pos_base, const uint32_t *d_emit_range, uint64_t *M_out) {
-    int rc;
-    *M_out = 0;
-    if ((rc = ensure(c, c->d_first_tile, ((size_t)n + 2) * 4))) return rc;
-    if ((rc = ensure(c, c->d_seq_off, ((size_t)n + 2) * 4))) return rc;
-    uint64_t n_tiles64 = 0;
+template <bool HPC, bool PACKED>
+int launch_scan_t(mq_ctx *c, const ScanArgs &a) {
+    const int vi = (HPC ? 1 : 0) | (PACKED ? 2 : 0);
+    const size_t smem = (size_t)SCAN_WARPS * WARP_BYTES;
+    auto kern = k_scan_minimizers<HPC, PACKED>;
+    if (c->scan_ctas_per_sm[vi] == 0) {      // persistent grid = every CTA the chip can hold
+        int nb = 0;
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, SCAN_WARPS * 32, smem) != cudaSuccess || nb < 1) nb = 1;
+        c->scan_ctas_per_sm[vi] = nb;
+    }
+    const uint32_t ctas_needed = (a.n_tiles + SCAN_WARPS - 1) / SCAN_WARPS;
+    const uint32_t grid = std::min<uint32_t>(ctas_needed, (uint32_t)(c->n_sm * c->scan_ctas_per_sm[vi]));
+    kern<<<grid, SCAN_WARPS * 32, smem, c->stream>>>(a, c->tab);
+    return MQ_OK;
+}
+
+// S1 on a staged sub-batch: scalars memset, scan, tile prefix, gather.  Result: c->d_pos / c->d_hash; the minimizer
+// range of record i is tile_base(first_tile[i]) .. tile_base(first_tile[i+1]).  Nothing here waits for the GPU.
+int enqueue_scan(mq_ctx *c, const BatchDev &b) {
+    CK(cudaMemsetAsync(b.sc, 0, sizeof(BatchScalars), c->stream));
+    if (b.n_tiles == 0) return MQ_OK;
+    ScanArgs a{};
+    a.seqs = b.seqs; a.packed = b.packed; a.flags = b.flags; a.exc = b.exc; a.n_exc = b.n_exc; a.exc_base = b.exc_base;
+    a.offs = b.offs; a.first_tile = b.first_tile; a.tile_seq = b.tile_seq; a.n_tiles = b.n_tiles; a.l = c->p.l; a.bound = c->bound;
+    a.ev_hash = c->d_ev_hash.as<uint64_t>(); a.ev_meta = c->d_ev_meta.as<uint32_t>();
+    a.lane_cnt = c->d_lane_cnt.as<uint16_t>(); a.tile_cnt = c->d_tile_cnt.as<uint32_t>();
+    a.ovf_count = &b.sc->ovf_count; a.ovf_cap = c->ovf_cap;
+    a.ovf_tile = c->d_ovf_tile.as<uint32_t>(); a.ovf_meta = c->d_ovf_meta.as<uint32_t>(); a.ovf_hash = c->d_ovf_hash.as<uint64_t>();
+    a.tile_ticket = &b.sc->scan_ticket; a.emit_range = b.emit;
     {
         StageTimer t(c, "scan");
-        if (c->scan_v1) k_tiles_per_seq<<<(n + 255) / 256, 256, 0, c->stream>>>(d_offs, n, min_len, c->d_first_tile.as<uint32_t>());
-        else k_tiles_per_seq_v2<<<(n + 255) / 256, 256, 0, c->stream>>>(d_offs, n, min_len, c->d_first_tile.as<uint32_t>());
-        c->launches++;
-        if ((rc = excl_scan(c, c->d_first_tile.as<uint32_t>(), n, true, &n_tiles64))) return rc;
-    }
-    if (n_tiles64 >= (1ull << 31)) { c->err = "batch too large (tile count)"; return MQ_ERR_RANGE; }
-    const uint32_t n_tiles = (uint32_t)n_tiles64;
-    if (n_tiles == 0) {
-        CK(cudaMemsetAsync(c->d_seq_off.p, 0, ((size_t)n + 1) * 4, c->stream));
-        return MQ_OK;
-    }
-    if ((rc = ensure(c, c->d_tile_seq, (size_t)n_tiles * 4))) return rc;
-    if ((rc = ensure(c, c->d_ev_hash, (size_t)n_tiles * EV_CAP * 8))) return rc;
-    if ((rc = ensure(c, c->d_ev_meta, (size_t)n_tiles * EV_CAP * 4))) return rc;
-    if ((rc = ensure(c, c->d_lane_cnt, (size_t)n_tiles * 32 * 2))) return rc;
-    if ((rc = ensure(c, c->d_tile_cnt, ((size_t)n_tiles + 2) * 4))) return rc;
-
-    uint64_t M = 0; uint32_t n_ovf = 0;
-    for (int attempt = 0; attempt < 3; attempt++) {
-        if ((rc = ensure(c, c->d_ovf_tile, (size_t)c->ovf_cap * 4))) return rc;
-        if ((rc = ensure(c, c->d_ovf_meta, (size_t)c->ovf_cap * 4))) return rc;
-        if ((rc = ensure(c, c->d_ovf_hash, (size_t)c->ovf_cap * 8))) return rc;
-        uint32_t *tickets = (uint32_t *)(c->d_scalars.as<uint64_t>() + SC_TICKET);
         {
-            StageTimer t(c, "scan");
-            CK(cudaMemsetAsync(tickets, 0, 8, c->stream));
-            k_tile_seq<<<(n_tiles + 255) / 256, 256, 0, c->stream>>>(c->d_first_tile.as<uint32_t>(), n, n_tiles, c->d_tile_seq.as<uint32_t>());
-            ScanArgs a{};
-            a.seqs = d_seqs; a.offs = d_offs; a.first_tile = c->d_first_tile.as<uint32_t>(); a.tile_seq = c->d_tile_seq.as<uint32_t>();
-            a.n_tiles = n_tiles; a.l = c->p.l; a.use_hpc = c->p.use_hpc; a.bound = c->bound;
-            a.ev_hash = c->d_ev_hash.as<uint64_t>(); a.ev_meta = c->d_ev_meta.as<uint32_t>();
-            a.lane_cnt = c->d_lane_cnt.as<uint16_t>(); a.tile_cnt = c->d_tile_cnt.as<uint32_t>();
-            a.ovf_count = tickets + 1; a.ovf_cap = c->ovf_cap;
-            a.ovf_tile = c->d_ovf_tile.as<uint32_t>(); a.ovf_meta = c->d_ovf_meta.as<uint32_t>(); a.ovf_hash = c->d_ovf_hash.as<uint64_t>();
-            a.tile_ticket = tickets; a.emit_range = d_emit_range;
-            {
-                StageTimer tk(c, "scan_kernel");   // the dominant kernel alone (roofline numerator)
-                if (c->scan_v1) {
-                    const uint32_t ctas_needed = (n_tiles + SCAN_WARPS - 1) / SCAN_WARPS;
-                    const uint32_t grid = std::min<uint32_t>(ctas_needed, (uint32_t)c->n_sm * 6);
-                    k_scan_minimizers<<<grid, SCAN_WARPS * 32, SCAN_WARPS * TILE_SMEM, c->stream>>>(a, c->tab);
-                } else {
-                    const uint32_t ctas_needed = (n_tiles + V2_WARPS - 1) / V2_WARPS;
-                    size_t smem = (size_t)V2_WARPS * (c->scan_v2 ? V2_WARP_BYTES : V3_WARP_BYTES);
-                    { const char *e = getenv("MQ_SCAN_PAD"); if (e) smem += (size_t)atoi(e); }   // occupancy experiments
-                    if (c->v2_ctas_per_sm == 0) {      // persistent grid = every CTA the chip can hold
-                        int nb = 0;
-                        const void *kern = c->scan_v2 ? (const void *)k_scan_minimizers_v2 : (c->p.use_hpc ? (const void *)k_scan_minimizers_v3<true> : (const void *)k_scan_minimizers_v3<false>);
-                        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-                        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, V2_WARPS * 32, smem) != cudaSuccess || nb < 1) nb = 1;
-                        c->v2_ctas_per_sm = nb;
-                        if (getenv("MQ_DEBUG")) fprintf(stderr, "[mq] scan kernel: %d CTAs/SM x %d warps, %zu B dynamic smem per CTA\n", nb, V2_WARPS, smem);
-                    }
-                    const uint32_t grid = std::min<uint32_t>(ctas_needed, (uint32_t)(c->n_sm * c->v2_ctas_per_sm));
-                    if (c->scan_v2) k_scan_minimizers_v2<<<grid, V2_WARPS * 32, smem, c->stream>>>(a, c->tab2);
-                    else if (c->p.use_hpc) k_scan_minimizers_v3<true><<<grid, V2_WARPS * 32, smem, c->stream>>>(a, c->tab3);
-                    else k_scan_minimizers_v3<false><<<grid, V2_WARPS * 32, smem, c->stream>>>(a, c->tab3);
-                }
-            }
-            c->launches += 2;
-            c->scan_kernel_launches++;
-            CK(cudaGetLastError());
+            StageTimer tk(c, "scan_kernel");   // the dominant kernel alone (roofline numerator)
+            const bool packed = b.packed != nullptr;
+            if (c->p.use_hpc) { if (packed) launch_scan_t<true, true>(c, a); else launch_scan_t<true, false>(c, a); }
+            else { if (packed) launch_scan_t<false, true>(c, a); else launch_scan_t<false, false>(c, a); }
         }
-        {
-            StageTimer t(c, "gather");
-            if ((rc = excl_scan(c, c->d_tile_cnt.as<uint32_t>(), n_tiles, true, &M))) return rc;
-        }
-        CK(cudaMemcpyAsync(&n_ovf, tickets + 1, 4, cudaMemcpyDeviceToHost, c->stream));
-        CK(cudaStreamSynchronize(c->stream));
-        if (n_ovf <= c->ovf_cap) break;
-        c->ovf_cap = n_ovf + n_ovf / 4 + 1024;    // pool too small: grow and redo the scan
-        if (attempt == 2) { c->err = "overflow pool kept overflowing"; return MQ_ERR_NOMEM; }
+        c->launches++; c->scan_kernel_launches++;
+        CK(cudaGetLastError());
     }
-    if (M >= (1ull << 32) - 64) { c->err = "batch too large (minimizer count)"; return MQ_ERR_RANGE; }
-    if ((rc = ensure(c, c->d_pos, (M + 64) * 4))) return rc;
-    if ((rc = ensure(c, c->d_hash, (M + 64) * 8))) return rc;
     {
         StageTimer t(c, "gather");
+        const uint32_t nb = (b.n_tiles + 1 + PREFIX_SPAN - 1) / PREFIX_SPAN;
+        k_tile_prefix<<<nb, SCAN_BLK, 0, c->stream>>>(c->d_tile_cnt.as<uint32_t>(), b.n_tiles, c->d_blk.as<uint32_t>(), b.sc, c->mini_cap, c->ovf_cap);
         GatherArgs g{};
         g.ev_hash = c->d_ev_hash.as<uint64_t>(); g.ev_meta = c->d_ev_meta.as<uint32_t>(); g.lane_cnt = c->d_lane_cnt.as<uint16_t>();
-        // tile_cnt was scanned in place: the per-tile totals are recovered as differences
-        g.tile_base = c->d_tile_cnt.as<uint32_t>();
-        g.tile_seq = c->d_tile_seq.as<uint32_t>(); g.first_tile = c->d_first_tile.as<uint32_t>(); g.offs = d_offs;
-        g.pos_base = d_pos_base; g.n_tiles = n_tiles; g.grid_align = c->scan_v1 ? 4u : 16u; g.out_pos = c->d_pos.as<uint32_t>(); g.out_hash = c->d_hash.as<uint64_t>();
-        k_gather_minimizers<<<(n_tiles + 8 * GATHER_TPW - 1) / (8 * GATHER_TPW), 256, 0, c->stream>>>(g);
-        c->launches++;
-        if (n_ovf) {
-            k_gather_overflow<<<(n_ovf + 255) / 256, 256, 0, c->stream>>>(g, c->d_ovf_tile.as<uint32_t>(), c->d_ovf_meta.as<uint32_t>(),
-                                                                        c->d_ovf_hash.as<uint64_t>(), n_ovf);
-            c->launches++;
-        }
-        k_seq_mini_off<<<(n + 1 + 255) / 256, 256, 0, c->stream>>>(c->d_first_tile.as<uint32_t>(), c->d_tile_cnt.as<uint32_t>(), n,
-                                                                c->d_seq_off.as<uint32_t>());
+        g.tb = TileBase{c->d_tile_cnt.as<uint32_t>(), c->d_blk.as<uint32_t>()};
+        g.tile_seq = b.tile_seq; g.first_tile = b.first_tile; g.offs = b.offs; g.pos_base = b.pos_base; g.n_tiles = b.n_tiles; g.sc = b.sc;
+        g.out_pos = c->d_pos.as<uint32_t>(); g.out_hash = c->d_hash.as<uint64_t>();
+        k_gather_minimizers<<<(b.n_tiles + 7) / 8, 256, 0, c->stream>>>(g);
+        k_gather_overflow<<<32, 256, 0, c->stream>>>(g, c->d_ovf_tile.as<uint32_t>(), c->d_ovf_meta.as<uint32_t>(), c->d_ovf_hash.as<uint64_t>());
+        c->launches += 3;
+        CK(cudaGetLastError());
+    }
+    return MQ_OK;
+}
+
+// probe / match / chain of a scanned sub-batch
+int enqueue_probe_chain(mq_ctx *c, const BatchDev &b, HitRec *d_hits) {
+    const uint32_t n = b.n;
+    const TileBase tb{c->d_tile_cnt.as<uint32_t>(), c->d_blk.as<uint32_t>()};
+    if (b.n_tiles == 0) {          // no record long enough: every read is unmapped
+        CK(cudaMemsetAsync(d_hits, 0, (size_t)n * sizeof(HitRec), c->stream));
+        return MQ_OK;
+    }
+    Table t{c->d_table.as<Slot>(), c->tmask};
+    {
+        StageTimer tm(c, "probe");
+        ProbeArgs a{};
+        a.pos = c->d_pos.as<uint32_t>(); a.hash = c->d_hash.as<uint64_t>(); a.first_tile = b.first_tile; a.tb = tb; a.sc = b.sc;
+        a.n_reads = n; a.k = c->p.k; a.l = c->p.l; a.matches = c->d_matches.as<MatchRec>(); a.n_matches = c->d_nmatch.as<uint32_t>();
+        a.read_ticket = &b.sc->probe_ticket;
+        const uint32_t grid = std::min<uint32_t>((n + 3) / 4, (uint32_t)c->n_sm * 16);
+        k_probe_match<<<grid, 128, 0, c->stream>>>(a, t);
         c->launches++;
         CK(cudaGetLastError());
     }
-    *M_out = M;
-    c->last_minimizers += M;
+    {
+        StageTimer tm(c, "chain");
+        ChainArgs a{};
+        a.matches = c->d_matches.as<MatchRec>(); a.n_matches = c->d_nmatch.as<uint32_t>(); a.first_tile = b.first_tile; a.tb = tb; a.sc = b.sc;
+        a.offs = b.offs; a.ref_lens = c->d_ref_lens.as<uint64_t>(); a.n_refs = c->n_refs; a.n_reads = n;
+        a.c = c->p.c; a.s = c->p.s; a.g = c->p.g; a.hits = d_hits; a.read_ticket = &b.sc->chain_ticket;
+        // thread per read for the usual handful of Matches; reads with many Matches are queued for the warp kernel
+        a.big_list = c->d_big_list.as<uint32_t>(); a.big_count = &b.sc->big_count;
+        k_chain_small<<<(n + 127) / 128, 128, 0, c->stream>>>(a);
+        const uint32_t grid = std::min<uint32_t>((n + 3) / 4, (uint32_t)c->n_sm * 8);
+        k_chain<<<grid, 128, 0, c->stream>>>(a);
+        c->launches += 2;
+        CK(cudaGetLastError());
+    }
     return MQ_OK;
 }
 
-int upload_batch(mq_ctx *c, const uint8_t *seqs, const uint64_t *offs, uint32_t i0, uint32_t i1) {
-    const uint64_t b0 = offs[i0], b1 = offs[i1], nb = b1 - b0; const uint32_t n = i1 - i0;
+// ---- input descriptions ---------------------------------------------------------------------------------
+struct SeqInput {               // what a batch of sequences looks like to the staging code
+    bool packed = false, resident = false;           // resident: pointers are device pointers of this ctx
+    const uint8_t *seqs = nullptr;
+    const uint32_t *words = nullptr, *flags = nullptr; const mq_exc *exc = nullptr; uint64_t n_exc = 0;
+};
+static_assert(sizeof(mq_exc) == sizeof(ExcRec) && offsetof(mq_exc, len) == offsetof(ExcRec, len), "mq_exc layout");
+
+int init_slot(mq_ctx *c, Slot2 &s) {
+    if (s.ev_done) return MQ_OK;
+    CK(cudaEventCreateWithFlags(&s.ev_copied, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&s.ev_comp, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
     int rc;
-    if ((rc = ensure(c, c->d_seqs, nb + PAD))) return rc;
-    if ((rc = ensure(c, c->d_offs, ((size_t)n + 1) * 8))) return rc;
-    if ((rc = ensure_pin(c, ((size_t)n + 1) * 8))) return rc;
-    uint64_t *ho = (uint64_t *)c->h_pin;
-    for (uint32_t i = 0; i <= n; i++) ho[i] = offs[i0 + i] - b0;
-    StageTimer t(c, "h2d");
-    if (nb) CK(cudaMemcpyAsync(c->d_seqs.p, seqs + b0, nb, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemsetAsync((uint8_t *)c->d_seqs.p + nb, 0, PAD, c->stream));
-    CK(cudaMemcpyAsync(c->d_offs.p, ho, ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    if ((rc = ensure(c, s.d_sc, sizeof(BatchScalars)))) return rc;
+    if ((rc = ensure_host(c, s.h_sc, sizeof(BatchScalars)))) return rc;
+    return MQ_OK;
+}
+int init_streams(mq_ctx *c) {
+    if (c->copy_stream) return MQ_OK;
+    CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
+    int rc;
+    for (auto &s : c->slot) if ((rc = init_slot(c, s))) return rc;
+    return MQ_OK;
+}
+
+// Stage pieces [i0, i1) into slot s: build offsets + tile tables on the host, upload sequence slice and tables on the
+// copy stream.  The slice of the caller's array starts at `origin` (16-base aligned for ASCII, 2048 for packed), piece
+// offsets are relative to it.  Fills bd.
+int stage_pieces(mq_ctx *c, Slot2 &s, const SeqInput &in, const Piece *pc, uint32_t i0, uint32_t i1, uint32_t min_len, bool pieces,
+                 BatchDev &bd) {
+    const uint32_t n = i1 - i0;
+    uint64_t lo = ~0ull, hi = 0;
+    for (uint32_t i = i0; i < i1; i++) { lo = std::min(lo, pc[i].lo); hi = std::max(hi, pc[i].hi); }
+    if (n == 0 || lo > hi) { lo = hi = 0; }
+    const uint64_t origin = in.packed ? (lo & ~2047ull) : (lo & ~15ull);
+    // exception intervals overlapping the slice
+    uint64_t e0 = 0, e1 = 0;
+    if (in.packed && in.n_exc && !in.resident) {
+        e0 = std::partition_point(in.exc, in.exc + in.n_exc, [&](const mq_exc &e) { return e.start + e.len <= origin; }) - in.exc;
+        e1 = std::partition_point(in.exc, in.exc + in.n_exc, [&](const mq_exc &e) { return e.start < hi; }) - in.exc;
+        if (e1 < e0) e1 = e0;
+    }
+    const size_t flag_words = (in.packed && !in.resident) ? (size_t)((hi - origin + 2047) / 2048 + 1) : 0;
+    // tile counts first (they size the meta block)
+    uint64_t n_tiles64 = 0;
+    for (uint32_t i = i0; i < i1; i++) n_tiles64 += tiles_of_record(pc[i].lo - origin, pc[i].hi - origin, min_len);
+    if (n_tiles64 >= (1ull << 31)) { c->err = "batch too large (tile count)"; return MQ_ERR_RANGE; }
+    const uint32_t n_tiles = (uint32_t)n_tiles64;
+    const MetaLayout ml(n, n_tiles, pieces, flag_words, (size_t)(e1 - e0));
+    int rc;
+    if ((rc = ensure_host(c, s.h_meta, ml.total))) return rc;
+    if ((rc = ensure(c, s.d_meta, ml.total))) return rc;
+    uint8_t *hm = (uint8_t *)s.h_meta.p;
+    uint64_t *h_offs = (uint64_t *)(hm + ml.offs);
+    uint32_t *h_ft = (uint32_t *)(hm + ml.first_tile), *h_ts = (uint32_t *)(hm + ml.tile_seq);
+    uint32_t *h_pb = (uint32_t *)(hm + ml.pos_base), *h_em = (uint32_t *)(hm + ml.emit);
+    // records of a batch are contiguous in the caller's array except for index segments, whose pieces may overlap
+    // (context byte, halo): every piece is its own record [lo, hi), so offs is written as n pairs collapsed into
+    // n+1 boundaries only when contiguous.  Segment batches therefore hold ONE piece each (see add_pieces).
+    uint32_t t = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        const Piece &q = pc[i0 + i];
+        h_offs[i] = q.lo - origin;
+        h_ft[i] = t;
+        const uint32_t nt = tiles_of_record(q.lo - origin, q.hi - origin, min_len);
+        for (uint32_t k = 0; k < nt; k++) h_ts[t + k] = i;
+        t += nt;
+        if (pieces) { h_pb[i] = q.pos_base; h_em[2 * i] = q.emit_lo; h_em[2 * i + 1] = q.emit_hi; }
+    }
+    h_offs[n] = n ? pc[i1 - 1].hi - origin : 0;
+    h_ft[n] = t;
+    if (flag_words) memcpy(hm + ml.flags, in.flags + (origin >> 11), flag_words * 4);
+    if (e1 > e0) {
+        ExcRec *he = (ExcRec *)(hm + ml.exc);
+        for (uint64_t e = e0; e < e1; e++) {     // slice coordinates
+            const uint64_t st = std::max(in.exc[e].start, origin), en = in.exc[e].start + in.exc[e].len;
+            he[e - e0] = ExcRec{st - origin, (uint32_t)(en - st), in.exc[e].byte};
+        }
+    }
+    const uint64_t span = hi - origin;            // bases of the slice
+    uint8_t *dm = (uint8_t *)s.d_meta.p;
+    bd = BatchDev{};
+    bd.n = n; bd.n_tiles = n_tiles; bd.bases = span; bd.sc = s.d_sc.as<BatchScalars>();
+    bd.offs = (const uint64_t *)(dm + ml.offs); bd.first_tile = (const uint32_t *)(dm + ml.first_tile);
+    bd.tile_seq = (const uint32_t *)(dm + ml.tile_seq);
+    if (pieces) { bd.pos_base = (const uint32_t *)(dm + ml.pos_base); bd.emit = (const uint32_t *)(dm + ml.emit); }
+    {
+        StageTimer tm(c, "h2d", c->copy_stream);
+        if (in.resident) {
+            if (in.packed) {
+                bd.packed = in.words + (origin >> 4); bd.flags = in.flags + (origin >> 11);
+                bd.exc = (const ExcRec *)in.exc; bd.n_exc = (uint32_t)in.n_exc; bd.exc_base = origin;   // the whole list, absolute coordinates
+            } else bd.seqs = in.seqs + origin;
+        } else if (in.packed) {
+            const size_t wbytes = (size_t)((span + 15) / 16) * 4;
+            if ((rc = ensure(c, s.d_in, wbytes + PAD))) return rc;
+            if (wbytes) CK(cudaMemcpyAsync(s.d_in.p, in.words + (origin >> 4), wbytes, cudaMemcpyHostToDevice, c->copy_stream));
+            CK(cudaMemsetAsync((uint8_t *)s.d_in.p + wbytes, 0, PAD, c->copy_stream));
+            bd.packed = s.d_in.as<uint32_t>(); bd.flags = (const uint32_t *)(dm + ml.flags);
+            bd.exc = (const ExcRec *)(dm + ml.exc); bd.n_exc = (uint32_t)(e1 - e0);
+        } else {
+            if ((rc = ensure(c, s.d_in, span + PAD))) return rc;
+            if (span) CK(cudaMemcpyAsync(s.d_in.p, in.seqs + origin, span, cudaMemcpyHostToDevice, c->copy_stream));
+            CK(cudaMemsetAsync((uint8_t *)s.d_in.p + span, 0, PAD, c->copy_stream));
+            bd.seqs = s.d_in.as<uint8_t>();
+        }
+        CK(cudaMemcpyAsync(s.d_meta.p, s.h_meta.p, ml.total, cudaMemcpyHostToDevice, c->copy_stream));
+    }
+    CK(cudaEventRecord(s.ev_copied, c->copy_stream));
+    s.bd = bd; s.i0 = i0; s.i1 = i1;
+    return MQ_OK;
+}
+
+// after a status record reported an overflow: make room for what it asked for
+int grow_from_status(mq_ctx *c, const BatchScalars &sc, uint64_t bases) {
+    if (sc.flags & BS_RANGE) { c->err = "sub-batch holds 2^32 minimizers or more"; return MQ_ERR_RANGE; }
+    CK(cudaStreamSynchronize(c->stream));
+    if (sc.flags & BS_OVF_CAP) {
+        c->ovf_cap = sc.ovf_count + sc.ovf_count / 4 + 1024;
+        dfree(c->d_ovf_tile); dfree(c->d_ovf_meta); dfree(c->d_ovf_hash);
+    }
+    if (sc.flags & BS_MINI_CAP) {
+        const double rate = (double)sc.n_minimizers / (double)std::max<uint64_t>(bases, 1);
+        c->mini_rate = std::max(c->mini_rate, rate * 1.25 + 0.001);
+    }
     return MQ_OK;
 }
 
@@ -347,6 +503,78 @@ int check_offs(mq_ctx *c, const uint64_t *offs, uint32_t n) {
     return MQ_OK;
 }
 
+// ---- mapping pipeline -------------------------------------------------------------------------------------
+// reads [0, n) of `in` with host offsets `offs`; hits go to out (host) or d_out (device, resident path)
+int map_pipeline(mq_ctx *c, const SeqInput &in, const uint64_t *offs, uint32_t n, mq_hit *out, mq_hit *d_out) {
+    int rc;
+    if ((rc = init_streams(c))) return rc;
+    // sub-batch boundaries
+    std::vector<uint32_t> cut{0};
+    for (uint32_t i0 = 0; i0 < n;) {
+        uint32_t i1 = i0 + 1;
+        while (i1 < n && offs[i1 + 1] - offs[i0] <= SUB_BASES) i1++;
+        cut.push_back(i1); i0 = i1;
+    }
+    const size_t ns = cut.size() - 1;
+    std::vector<Piece> pieces(n);
+    for (uint32_t i = 0; i < n; i++) pieces[i] = Piece{offs[i], offs[i + 1], 0, 0, 0, 0, 0};
+    const uint32_t min_len = c->p.l + c->p.k - 1;
+
+    // finish the sub-batch a slot holds: wait for its hits, look at its status, redo it if a buffer was too small
+    auto retire = [&](Slot2 &s) -> int {
+        if (!s.busy) return MQ_OK;
+        CK(cudaEventSynchronize(s.ev_done));
+        s.busy = false;
+        const BatchScalars *hs = (const BatchScalars *)s.h_sc.p;
+        c->last_minimizers += hs->n_minimizers;
+        for (int attempt = 0; hs->flags; attempt++) {
+            if (attempt == 3) { c->err = "sub-batch kept overflowing its buffers"; return MQ_ERR_NOMEM; }
+            int r2;
+            c->last_minimizers -= hs->n_minimizers;
+            if ((r2 = grow_from_status(c, *hs, s.bd.bases))) return r2;
+            // the slot still holds the inputs and its device view: run it again, synchronously
+            const BatchDev &bd = s.bd;
+            const uint32_t m = s.i1 - s.i0;
+            if ((r2 = ensure_workspace(c, m, bd.n_tiles, bd.bases, true))) return r2;
+            HitRec *dh = d_out ? (HitRec *)d_out + s.i0 : s.d_hits.as<HitRec>();
+            if ((r2 = enqueue_scan(c, bd))) return r2;
+            if ((r2 = enqueue_probe_chain(c, bd, dh))) return r2;
+            if (!d_out) CK(cudaMemcpyAsync(out + s.i0, dh, (size_t)m * sizeof(HitRec), cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaMemcpyAsync(s.h_sc.p, s.d_sc.p, sizeof(BatchScalars), cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+            c->last_minimizers += hs->n_minimizers;
+        }
+        return MQ_OK;
+    };
+
+    for (size_t i = 0; i < ns; i++) {
+        Slot2 &s = c->slot[i & 1];
+        if ((rc = retire(s))) return rc;
+        const uint32_t m = cut[i + 1] - cut[i];
+        BatchDev bd;
+        if ((rc = stage_pieces(c, s, in, pieces.data(), cut[i], cut[i + 1], min_len, false, bd))) return rc;
+        if ((rc = ensure_workspace(c, m, bd.n_tiles, bd.bases, true))) return rc;
+        HitRec *dh;
+        if (d_out) dh = (HitRec *)d_out + cut[i];
+        else { if ((rc = ensure(c, s.d_hits, (size_t)m * sizeof(HitRec)))) return rc; dh = s.d_hits.as<HitRec>(); }
+        CK(cudaStreamWaitEvent(c->stream, s.ev_copied, 0));
+        if ((rc = enqueue_scan(c, bd))) return rc;
+        if ((rc = enqueue_probe_chain(c, bd, dh))) return rc;
+        CK(cudaEventRecord(s.ev_comp, c->stream));
+        CK(cudaStreamWaitEvent(c->d2h_stream, s.ev_comp, 0));
+        {
+            StageTimer t(c, "d2h", c->d2h_stream);
+            if (!d_out) CK(cudaMemcpyAsync(out + cut[i], dh, (size_t)m * sizeof(HitRec), cudaMemcpyDeviceToHost, c->d2h_stream));
+            CK(cudaMemcpyAsync(s.h_sc.p, s.d_sc.p, sizeof(BatchScalars), cudaMemcpyDeviceToHost, c->d2h_stream));
+        }
+        CK(cudaEventRecord(s.ev_done, c->d2h_stream));
+        s.busy = true;
+    }
+    for (auto &s : c->slot) if ((rc = retire(s))) return rc;
+    return MQ_OK;
+}
+
+// ---- index build ---------------------------------------------------------------------------------------
 int store_append(mq_ctx *c, uint64_t M) {
     int rc;
     if ((rc = ensure_keep(c, c->st_pos, (c->st_n + M + 64) * 4, c->st_n * 4))) return rc;
@@ -359,51 +587,114 @@ int store_append(mq_ctx *c, uint64_t M) {
     return MQ_OK;
 }
 
-// map a device-resident batch: S1 -> probe/match -> chain
-int map_device(mq_ctx *c, const uint8_t *d_seqs, const uint64_t *d_offs, uint32_t n, HitRec *d_hits) {
-    int rc; uint64_t M = 0;
-    if ((rc = run_scan(c, d_seqs, d_offs, n, c->p.l + c->p.k - 1, nullptr, nullptr, &M))) return rc;
-    if ((rc = ensure(c, c->d_matches, (M + 64) * sizeof(MatchRec)))) return rc;
-    if ((rc = ensure(c, c->d_nmatch, ((size_t)n + 1) * 4))) return rc;
-    if ((rc = ensure(c, c->d_big_list, ((size_t)n + 2) * 4))) return rc;
-    uint32_t *tickets = (uint32_t *)(c->d_scalars.as<uint64_t>() + SC_TICKET);
-    Table t{c->d_table.as<Slot>(), c->tmask};
-    {
-        StageTimer tm(c, "probe");
-        CK(cudaMemsetAsync(tickets, 0, 8, c->stream));
-        ProbeArgs a{};
-        a.pos = c->d_pos.as<uint32_t>(); a.hash = c->d_hash.as<uint64_t>(); a.seq_off = c->d_seq_off.as<uint32_t>();
-        a.n_reads = n; a.k = c->p.k; a.l = c->p.l; a.matches = c->d_matches.as<MatchRec>(); a.n_matches = c->d_nmatch.as<uint32_t>();
-        a.read_ticket = tickets;
-        const uint32_t grid = std::min<uint32_t>((n + 3) / 4, (uint32_t)c->n_sm * 16);
-        k_probe_match<<<grid, 128, 0, c->stream>>>(a, t);
-        c->launches++;
-        CK(cudaGetLastError());
+// scan one staged batch to completion (index build and introspection paths): returns M and, if wanted, the per-record
+// minimizer offsets (n+1).  Waits for the GPU; redoes the batch if a buffer was too small.
+int scan_sync(mq_ctx *c, Slot2 &s, const BatchDev &bd, uint64_t *M_out, std::vector<uint32_t> *seq_off) {
+    int rc;
+    BatchScalars *hs = (BatchScalars *)s.h_sc.p;
+    for (int attempt = 0;; attempt++) {
+        if ((rc = ensure_workspace(c, bd.n, bd.n_tiles, bd.bases, false))) return rc;
+        if ((rc = ensure(c, c->d_seq_off, ((size_t)bd.n + 2) * 4))) return rc;
+        CK(cudaStreamWaitEvent(c->stream, s.ev_copied, 0));
+        if ((rc = enqueue_scan(c, bd))) return rc;
+        if (bd.n_tiles) {
+            k_seq_mini_off<<<(bd.n + 1 + 255) / 256, 256, 0, c->stream>>>(bd.first_tile, TileBase{c->d_tile_cnt.as<uint32_t>(), c->d_blk.as<uint32_t>()},
+                                                                        bd.n, c->d_seq_off.as<uint32_t>());
+            c->launches++;
+        } else CK(cudaMemsetAsync(c->d_seq_off.p, 0, ((size_t)bd.n + 1) * 4, c->stream));
+        CK(cudaMemcpyAsync(hs, bd.sc, sizeof(BatchScalars), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        if (!hs->flags) break;
+        if (attempt == 3) { c->err = "batch kept overflowing its buffers"; return MQ_ERR_NOMEM; }
+        if ((rc = grow_from_status(c, *hs, bd.bases))) return rc;
     }
-    {
-        StageTimer tm(c, "chain");
-        ChainArgs a{};
-        a.matches = c->d_matches.as<MatchRec>(); a.n_matches = c->d_nmatch.as<uint32_t>(); a.seq_off = c->d_seq_off.as<uint32_t>();
-        a.offs = d_offs; a.ref_lens = c->d_ref_lens.as<uint64_t>(); a.n_refs = c->n_refs; a.n_reads = n;
-        a.c = c->p.c; a.s = c->p.s; a.g = c->p.g; a.hits = d_hits; a.read_ticket = tickets + 1;
-        // thread per read for the usual handful of Matches; reads with many Matches are queued for the warp kernel
-        a.big_list = c->d_big_list.as<uint32_t>(); a.big_count = c->d_big_list.as<uint32_t>() + n;
-        CK(cudaMemsetAsync(a.big_count, 0, 4, c->stream));
-        k_chain_small<<<(n + 127) / 128, 128, 0, c->stream>>>(a);
-        const uint32_t grid = std::min<uint32_t>((n + 3) / 4, (uint32_t)c->n_sm * 8);
-        k_chain<<<grid, 128, 0, c->stream>>>(a);
-        c->launches += 2;
-        CK(cudaGetLastError());
+    *M_out = hs->n_minimizers;
+    c->last_minimizers += hs->n_minimizers;
+    if (seq_off) {
+        seq_off->resize((size_t)bd.n + 1);
+        CK(cudaMemcpyAsync(seq_off->data(), c->d_seq_off.p, ((size_t)bd.n + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
     }
     return MQ_OK;
 }
+
+// number of bases after `from` needed to see `need` further run starts (or the end of the record)
+uint64_t halo_end(const SeqInput &in, uint64_t rec_lo, uint64_t rec_hi, uint64_t from, uint32_t need, bool hpc) {
+    if (!hpc) return std::min(rec_hi, from + need);
+    auto byte_at = [&](uint64_t i) -> uint32_t {
+        if (!in.packed) return in.seqs[i];
+        uint32_t b = (in.words[i >> 4] >> (2 * (i & 15))) & 3u;
+        if ((in.flags[i >> 11] >> ((i >> 6) & 31)) & 1u) {
+            const mq_exc *e = std::partition_point(in.exc, in.exc + in.n_exc, [&](const mq_exc &x) { return x.start + x.len <= i; });
+            if (e != in.exc + in.n_exc && e->start <= i) return 0x100u | e->byte;
+        }
+        return b;
+    };
+    uint64_t i = from;
+    uint32_t prev = from > rec_lo ? byte_at(from - 1) : 0xFFFFu;
+    while (i < rec_hi && need) { const uint32_t b = byte_at(i); if (b != prev) need--; prev = b; i++; }
+    // round up generously: whole 64-base blocks, so the scan's halo loop never runs out before the record does
+    return std::min<uint64_t>(rec_hi, (i + 63) & ~(uint64_t)63);
+}
+
+// Scan pieces of reference records into the minimizer store.  Long records are cut into sub-pieces of <= ADD_BASES
+// bases so that uploads overlap scans; `ref_len_of(ref_idx)` is only used for validation by the callers.
+int add_pieces(mq_ctx *c, const SeqInput &in, std::vector<Piece> &pcs, std::vector<uint64_t> *counts) {
+    int rc;
+    if ((rc = init_streams(c))) return rc;
+    if (counts) counts->assign(pcs.size(), 0);
+    // batches: consecutive whole-record pieces share a batch while contiguous and small; a segment piece is alone
+    std::vector<std::array<size_t, 2>> bt;
+    for (size_t i = 0; i < pcs.size();) {
+        size_t j = i + 1;
+        if (pcs[i].emit_hi == 0) while (j < pcs.size() && pcs[j].emit_hi == 0 && pcs[j].lo == pcs[j - 1].hi && pcs[j].hi - pcs[i].lo <= ADD_BASES && j - i < (1u << 20)) j++;
+        bt.push_back({i, j}); i = j;
+    }
+    auto stage = [&](size_t b) -> int {
+        const bool seg = pcs[bt[b][0]].emit_hi != 0;
+        BatchDev bd;
+        return stage_pieces(c, c->slot[b & 1], in, pcs.data(), (uint32_t)bt[b][0], (uint32_t)bt[b][1], seg ? 0 : c->p.l + c->p.k - 1, seg, bd);
+    };
+    if (!bt.empty() && (rc = stage(0))) return rc;
+    for (size_t b = 0; b < bt.size(); b++) {
+        // upload of the next batch (copy stream) overlaps the scan of this one
+        if (b + 1 < bt.size() && (rc = stage(b + 1))) return rc;
+        Slot2 &s = c->slot[b & 1];
+        uint64_t M = 0; std::vector<uint32_t> so;
+        if ((rc = scan_sync(c, s, s.bd, &M, &so))) return rc;
+        if ((rc = store_append(c, M))) return rc;
+        for (size_t q = bt[b][0]; q < bt[b][1]; q++) {
+            const uint64_t cnt = so[q - bt[b][0] + 1] - so[q - bt[b][0]];
+            c->dir.push_back({(uint64_t)pcs[q].ref_idx, pcs[q].seg_start, cnt});
+            if (counts) (*counts)[q] = cnt;
+        }
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    return MQ_OK;
+}
+
+// cut record [lo, hi) (caller-array coordinates) of reference ref_idx, restricted to record positions
+// [own_lo, own_hi), into pieces of <= ADD_BASES bases
+void pieces_of_range(const mq_ctx *c, const SeqInput &in, uint64_t lo, uint64_t hi, uint32_t ref_idx, uint64_t own_lo, uint64_t own_hi,
+                     std::vector<Piece> &out) {
+    const uint64_t len = hi - lo;
+    if (own_lo == 0 && own_hi == len && len <= ADD_BASES) { out.push_back(Piece{lo, hi, ref_idx, 0, 0, 0, 0}); return; }
+    for (uint64_t s0 = own_lo; s0 < own_hi; s0 += ADD_BASES) {
+        const uint64_t s1 = std::min(own_hi, s0 + ADD_BASES);
+        const uint64_t ctx = s0 > 0 ? 1 : 0;
+        const uint64_t he = halo_end(in, lo, hi, lo + s1, c->p.l - 1, c->p.use_hpc != 0);
+        out.push_back(Piece{lo + s0 - ctx, he, ref_idx, (uint32_t)(s0 - ctx), (uint32_t)ctx, (uint32_t)(ctx + s1 - s0), s0});
+    }
+}
+
+int freeze_local(mq_ctx *c, const uint64_t *ref_lens, uint32_t n_refs);
 
 }  // namespace
 
 // =================================================================================================
 extern "C" {
 
-int mq_abi_version(void) { return 1; }
+int mq_abi_version(void) { return 2; }
 
 const char *mq_strerror(int code) {
     switch (code) {
@@ -418,49 +709,82 @@ const char *mq_strerror(int code) {
 }
 const char *mq_last_error(const mq_ctx *c) { return c ? c->err.c_str() : ""; }
 
-int mq_create(mq_ctx **out, const mq_params *p, int device) {
-    if (!out || !p) return MQ_ERR_ARG;
-    *out = nullptr;
-    if (p->l < 2 || p->l > MQ_MAX_L || p->k < 1 || p->k > MQ_MAX_K || !(p->density >= 0.0)) return MQ_ERR_ARG;
+static int create_one(mq_ctx **out, const mq_params *p, int device) {
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) { cudaGetLastError(); return MQ_ERR_CUDA; }
     if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return MQ_ERR_CUDA; }
-    mq_ctx *c = new mq_ctx();
+    mq_ctx *c = new (std::nothrow) mq_ctx();
+    if (!c) return MQ_ERR_NOMEM;
     c->p = *p; c->device = device; c->bound = hash_bound(p->density);
     fill_tables(c->tab, p->l);
-    fill_tables_v2(c->tab2, c->tab, p->l);
-    fill_tables_v3(c->tab3, c->tab2);
-    { const char *e = getenv("MQ_SCAN_V1"); c->scan_v1 = e && e[0] == '1'; }
-    { const char *e = getenv("MQ_SCAN_V2"); c->scan_v2 = e && e[0] == '1'; }
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->n_sm = prop.multiProcessorCount;
+    // random 32-byte probes into a multi-GB table: fetch one sector per miss, not two
+    cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32); cudaGetLastError();
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return MQ_ERR_CUDA; }
-    if (cudaMalloc(&c->d_scalars.p, SC_WORDS * 8) != cudaSuccess) { cudaStreamDestroy(c->stream); delete c; return MQ_ERR_CUDA; }
-    c->d_scalars.cap = SC_WORDS * 8;
-    cudaMemsetAsync(c->d_scalars.p, 0, SC_WORDS * 8, c->stream);
     *out = c;
     return MQ_OK;
 }
 
+int mq_create(mq_ctx **out, const mq_params *p, int device) {
+    if (!out || !p) return MQ_ERR_ARG;
+    *out = nullptr;
+    if (p->l < 2 || p->l > MQ_MAX_L || p->k < 1 || p->k > MQ_MAX_K || !(p->density >= 0.0)) return MQ_ERR_ARG;
+    try { return create_one(out, p, device); } catch (...) { return MQ_ERR_NOMEM; }
+}
+
+int mq_create_multi(mq_ctx **out, const mq_params *p, const int *devices, int n_devices) {
+    if (!out || !p || !devices || n_devices < 1) return MQ_ERR_ARG;
+    *out = nullptr;
+    if (p->l < 2 || p->l > MQ_MAX_L || p->k < 1 || p->k > MQ_MAX_K || !(p->density >= 0.0)) return MQ_ERR_ARG;
+    if (n_devices == 1) return mq_create(out, p, devices[0]);
+    try {
+        mq_ctx *par = new mq_ctx();
+        par->p = *p; par->device = devices[0]; par->bound = hash_bound(p->density);
+        for (int i = 0; i < n_devices; i++) {
+            mq_ctx *k = nullptr;
+            int rc = create_one(&k, p, devices[i]);
+            if (rc) { mq_destroy(par); return rc; }
+            par->kids.push_back(k);
+        }
+        // peer access lets the store exchange go GPU to GPU over NVLink; without it cudaMemcpyPeer stages through the host
+        for (int i = 0; i < n_devices; i++) {
+            cudaSetDevice(devices[i]);
+            for (int j = 0; j < n_devices; j++) if (devices[i] != devices[j]) {     // (a device may be listed twice: two contexts on it)
+                int can = 0; cudaDeviceCanAccessPeer(&can, devices[i], devices[j]);
+                if (can) { cudaDeviceEnablePeerAccess(devices[j], 0); cudaGetLastError(); }
+            }
+        }
+        *out = par;
+        return MQ_OK;
+    } catch (...) { return MQ_ERR_NOMEM; }
+}
+int mq_device_count(const mq_ctx *c) { return !c ? 0 : (c->kids.empty() ? 1 : (int)c->kids.size()); }
+
 void mq_destroy(mq_ctx *c) {
     if (!c) return;
+    for (mq_ctx *k : c->kids) mq_destroy(k);
+    if (!c->stream) { delete c; return; }            // multi-GPU parent: owns no device state
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+    if (c->d2h_stream) cudaStreamSynchronize(c->d2h_stream);
     timers_collect(c);
-    DBuf *bufs[] = {&c->d_seqs, &c->d_offs, &c->d_first_tile, &c->d_tile_seq, &c->d_ev_hash, &c->d_ev_meta, &c->d_lane_cnt,
-                    &c->d_tile_cnt, &c->d_blocksums, &c->d_scalars, &c->d_ovf_tile, &c->d_ovf_meta, &c->d_ovf_hash, &c->d_pos,
-                    &c->d_hash, &c->d_seq_off, &c->d_matches, &c->d_nmatch, &c->d_hits, &c->d_pos_base, &c->d_emit_len, &c->d_big_list,
-                    &c->d_misc, &c->st_pos, &c->st_hash, &c->d_table, &c->d_ref_lens};
+    DBuf *bufs[] = {&c->d_ev_hash, &c->d_ev_meta, &c->d_lane_cnt, &c->d_tile_cnt, &c->d_blk, &c->d_ovf_tile, &c->d_ovf_meta, &c->d_ovf_hash,
+                    &c->d_pos, &c->d_hash, &c->d_seq_off, &c->d_matches, &c->d_nmatch, &c->d_big_list, &c->d_misc, &c->st_pos, &c->st_hash,
+                    &c->d_table, &c->d_ref_lens};
     for (DBuf *b : bufs) dfree(*b);
+    for (auto &s : c->slot) {
+        dfree(s.d_in); dfree(s.d_meta); dfree(s.d_hits); dfree(s.d_sc); hfree(s.h_meta); hfree(s.h_sc);
+        if (s.ev_copied) cudaEventDestroy(s.ev_copied);
+        if (s.ev_comp) cudaEventDestroy(s.ev_comp);
+        if (s.ev_done) cudaEventDestroy(s.ev_done);
+    }
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     if (c->region_a) { cudaEventDestroy(c->region_a); cudaEventDestroy(c->region_b); }
-    if (c->h_pin) cudaFreeHost(c->h_pin);
-    for (int b = 0; b < 2; b++) {
-        dfree(c->d_seqs2[b]); dfree(c->d_offs2[b]);
-        if (c->h_offs2[b]) cudaFreeHost(c->h_offs2[b]);
-        if (c->ev_copied[b]) cudaEventDestroy(c->ev_copied[b]);
-    }
+    hfree(c->h_pin);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -468,28 +792,45 @@ void mq_destroy(mq_ctx *c) {
 void *mq_host_alloc(size_t bytes) { void *p = nullptr; if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; } return p; }
 void mq_host_free(void *p) { if (p) cudaFreeHost(p); }
 
-void *mq_stream(mq_ctx *c) { return c ? (void *)c->stream : nullptr; }
-int mq_sync(mq_ctx *c) { if (!c) return MQ_ERR_ARG; cudaSetDevice(c->device); CK(cudaStreamSynchronize(c->stream)); timers_collect(c); return MQ_OK; }
-uint64_t mq_launch_count(mq_ctx *c) { return c ? c->launches : 0; }
+#define FIRST(c) ((c)->kids.empty() ? (c) : (c)->kids[0])
+void *mq_stream(mq_ctx *c) { return c ? (void *)FIRST(c)->stream : nullptr; }
+int mq_sync(mq_ctx *c) {
+    if (!c) return MQ_ERR_ARG;
+    if (!c->kids.empty()) { for (mq_ctx *k : c->kids) { int rc = mq_sync(k); if (rc) { c->err = k->err; return rc; } } return MQ_OK; }
+    cudaSetDevice(c->device); CK(cudaStreamSynchronize(c->stream)); timers_collect(c); return MQ_OK;
+}
+uint64_t mq_launch_count(mq_ctx *c) {
+    if (!c) return 0;
+    uint64_t s = c->launches; for (mq_ctx *k : c->kids) s += k->launches; return s;
+}
 double mq_total_ms(mq_ctx *c, const char *stage) {
     if (!c || !stage) return -1.0;
+    if (!c->kids.empty()) { double m = 0; for (mq_ctx *k : c->kids) m = std::max(m, mq_total_ms(k, stage)); return m; }
+    cudaSetDevice(c->device);
     timers_collect(c);
     auto it = c->ms_total.find(stage);
     return it == c->ms_total.end() ? 0.0 : it->second;
 }
 double mq_last_ms(mq_ctx *c, const char *stage) {
     if (!c || !stage) return -1.0;
+    if (!c->kids.empty()) { double m = 0; for (mq_ctx *k : c->kids) m = std::max(m, mq_last_ms(k, stage)); return m; }
+    cudaSetDevice(c->device);
     timers_collect(c);
     if (!strcmp(stage, "total")) { double s = 0; for (auto &kv : c->ms) if (kv.first != "scan_kernel") s += kv.second; return s; }
     auto it = c->ms.find(stage);
     return it == c->ms.end() ? 0.0 : it->second;
 }
-uint64_t mq_scan_kernel_launches(mq_ctx *c) { return c ? c->scan_kernel_launches : 0; }
-uint64_t mq_minimizer_count(mq_ctx *c, int reset) { if (!c) return 0; uint64_t v = c->last_minimizers; if (reset) c->last_minimizers = 0; return v; }
+uint64_t mq_scan_kernel_launches(mq_ctx *c) { if (!c) return 0; uint64_t s = c->scan_kernel_launches; for (mq_ctx *k : c->kids) s += k->scan_kernel_launches; return s; }
+uint64_t mq_minimizer_count(mq_ctx *c, int reset) {
+    if (!c) return 0;
+    uint64_t v = c->last_minimizers; if (reset) c->last_minimizers = 0;
+    for (mq_ctx *k : c->kids) v += mq_minimizer_count(k, reset);
+    return v;
+}
 
-// device-memory helpers so that callers can keep inputs resident in HBM without another runtime
+// device-memory helpers so that callers can keep inputs resident in HBM without another runtime (single-GPU contexts)
 void *mq_dev_alloc(mq_ctx *c, size_t bytes) {
-    if (!c) return nullptr;
+    if (!c || !c->kids.empty()) return nullptr;
     cudaSetDevice(c->device);
     void *p = nullptr;
     if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
@@ -497,28 +838,28 @@ void *mq_dev_alloc(mq_ctx *c, size_t bytes) {
 }
 void mq_dev_free(mq_ctx *c, void *p) { if (c && p) { cudaSetDevice(c->device); cudaFree(p); } }
 int mq_dev_upload(mq_ctx *c, void *dst, const void *src, size_t bytes) {
-    if (!c || (bytes && (!dst || !src))) return MQ_ERR_ARG;
+    if (!c || !c->kids.empty() || (bytes && (!dst || !src))) return MQ_ERR_ARG;
     cudaSetDevice(c->device);
     CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     return MQ_OK;
 }
 int mq_dev_download(mq_ctx *c, void *dst, const void *src, size_t bytes) {
-    if (!c || (bytes && (!dst || !src))) return MQ_ERR_ARG;
+    if (!c || !c->kids.empty() || (bytes && (!dst || !src))) return MQ_ERR_ARG;
     cudaSetDevice(c->device);
     CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     return MQ_OK;
 }
 int mq_dev_memset(mq_ctx *c, void *dst, int value, size_t bytes) {
-    if (!c || (bytes && !dst)) return MQ_ERR_ARG;
+    if (!c || !c->kids.empty() || (bytes && !dst)) return MQ_ERR_ARG;
     cudaSetDevice(c->device);
     CK(cudaMemsetAsync(dst, value, bytes, c->stream));
     return MQ_OK;
 }
 // CUDA-event bracket on the ctx stream around any sequence of calls
 int mq_region_begin(mq_ctx *c) {
-    if (!c) return MQ_ERR_ARG;
+    if (!c || !c->kids.empty()) return MQ_ERR_ARG;
     cudaSetDevice(c->device);
     if (!c->region_a) { CK(cudaEventCreate(&c->region_a)); CK(cudaEventCreate(&c->region_b)); }
     CK(cudaStreamSynchronize(c->stream));
@@ -534,37 +875,92 @@ double mq_region_end_ms(mq_ctx *c) {
     return ms;
 }
 
-uint64_t mq_table_bytes(mq_ctx *c) { return c && c->frozen ? (c->tmask + 2) * sizeof(Slot) : 0; }
-uint64_t mq_table_slots(mq_ctx *c) { return c && c->frozen ? c->tmask + 1 : 0; }
+uint64_t mq_table_bytes(mq_ctx *c) { if (!c) return 0; c = FIRST(c); return c->frozen ? (c->tmask + 2) * sizeof(Slot) : 0; }
+uint64_t mq_table_slots(mq_ctx *c) { if (!c) return 0; c = FIRST(c); return c->frozen ? c->tmask + 1 : 0; }
 
 // ---- index build ---------------------------------------------------------------------------------
-int mq_index_add(mq_ctx *c, const uint8_t *seqs, const uint64_t *offs, uint32_t n, uint32_t first_ref_idx, uint64_t *nb_mers_out) {
-    if (!c || (!seqs && n) || !offs) return MQ_ERR_ARG;
-    if (c->frozen) { c->err = "index already frozen"; return MQ_ERR_STATE; }
-    cudaSetDevice(c->device);
-    timers_reset(c);
+static int index_add_impl(mq_ctx *c, const SeqInput &in, const uint64_t *offs, uint32_t n, uint32_t first_ref_idx, uint64_t *nb_mers_out) {
+    if (c->kids.empty() ? c->frozen : c->kids[0]->frozen) { c->err = "index already frozen"; return MQ_ERR_STATE; }
     int rc;
     if ((rc = check_offs(c, offs, n))) return rc;
     if (n == 0) return MQ_OK;
-    if ((rc = upload_batch(c, seqs, offs, 0, n))) return rc;
-    uint64_t M = 0;
-    if ((rc = run_scan(c, c->d_seqs.as<uint8_t>(), c->d_offs.as<uint64_t>(), n, c->p.l + c->p.k - 1, nullptr, nullptr, &M))) return rc;
-    if ((rc = store_append(c, M))) return rc;
-    std::vector<uint32_t> so((size_t)n + 1);
-    CK(cudaMemcpyAsync(so.data(), c->d_seq_off.p, ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    for (uint32_t i = 0; i < n; i++) {
-        uint64_t cnt = so[i + 1] - so[i];
-        c->dir.push_back({(uint64_t)first_ref_idx + i, 0ull, cnt});
-        if (nb_mers_out) nb_mers_out[i] = cnt >= c->p.k ? cnt - c->p.k + 1 : 0;
+    const uint32_t min_len = c->p.l + c->p.k - 1;
+    if (c->kids.empty()) {
+        cudaSetDevice(c->device);
+        timers_reset(c);
+        std::vector<Piece> pcs; std::vector<uint32_t> owner;       // owner[piece] = record
+        for (uint32_t i = 0; i < n; i++) {
+            const size_t before = pcs.size();
+            const uint64_t len = offs[i + 1] - offs[i];
+            if (len < min_len) pcs.push_back(Piece{offs[i], offs[i + 1], first_ref_idx + i, 0, 0, 0, 0});   // mers.rs:18: yields nothing (no tiles)
+            else pieces_of_range(c, in, offs[i], offs[i + 1], first_ref_idx + i, 0, len, pcs);
+            for (size_t q = before; q < pcs.size(); q++) owner.push_back(i);
+        }
+        std::vector<uint64_t> counts;
+        if ((rc = add_pieces(c, in, pcs, &counts))) return rc;
+        if (nb_mers_out) {
+            std::vector<uint64_t> per(n, 0);
+            for (size_t q = 0; q < pcs.size(); q++) per[owner[q]] += counts[q];
+            for (uint32_t i = 0; i < n; i++) nb_mers_out[i] = per[i] >= c->p.k ? per[i] - c->p.k + 1 : 0;
+        }
+        timers_collect(c);
+        return MQ_OK;
     }
-    timers_collect(c);
+    // multi-GPU: every record is cut into one base range per device (closures.rs:85 parallelises over records, whose
+    // sizes are too unequal for that to balance); the device threads scan concurrently
+    const size_t G = c->kids.size();
+    std::vector<std::vector<Piece>> pcs(G);
+    std::vector<std::vector<uint32_t>> owner(G);
+    for (uint32_t i = 0; i < n; i++) {
+        const uint64_t len = offs[i + 1] - offs[i];
+        for (size_t g = 0; g < G; g++) {
+            const size_t before = pcs[g].size();
+            if (len < min_len) { if (g == 0) pcs[g].push_back(Piece{offs[i], offs[i + 1], first_ref_idx + i, 0, 0, 0, 0}); }
+            else {
+                const uint64_t a = len * g / G, b = len * (g + 1) / G;
+                if (b > a) pieces_of_range(c, in, offs[i], offs[i + 1], first_ref_idx + i, a, b, pcs[g]);
+            }
+            for (size_t q = before; q < pcs[g].size(); q++) owner[g].push_back(i);
+        }
+    }
+    std::vector<int> rcs(G, 0);
+    std::vector<std::vector<uint64_t>> counts(G);
+    std::vector<std::thread> th;
+    for (size_t g = 0; g < G; g++) th.emplace_back([&, g]() {
+        mq_ctx *k = c->kids[g];
+        cudaSetDevice(k->device);
+        timers_reset(k);
+        rcs[g] = add_pieces(k, in, pcs[g], &counts[g]);
+        timers_collect(k);
+    });
+    for (auto &t : th) t.join();
+    for (size_t g = 0; g < G; g++) if (rcs[g]) { c->err = c->kids[g]->err; return rcs[g]; }
+    if (nb_mers_out) {
+        std::vector<uint64_t> per(n, 0);
+        for (size_t g = 0; g < G; g++) for (size_t q = 0; q < pcs[g].size(); q++) per[owner[g][q]] += counts[g][q];
+        for (uint32_t i = 0; i < n; i++) nb_mers_out[i] = per[i] >= c->p.k ? per[i] - c->p.k + 1 : 0;
+    }
     return MQ_OK;
+}
+
+int mq_index_add(mq_ctx *c, const uint8_t *seqs, const uint64_t *offs, uint32_t n, uint32_t first_ref_idx, uint64_t *nb_mers_out) {
+    if (!c || (!seqs && n) || !offs) return MQ_ERR_ARG;
+    try {
+        SeqInput in; in.seqs = seqs;
+        return index_add_impl(c, in, offs, n, first_ref_idx, nb_mers_out);
+    } catch (...) { c->err = "host allocation failed"; return MQ_ERR_NOMEM; }
+}
+int mq_index_add_packed(mq_ctx *c, const mq_packed *pk, const uint64_t *offs, uint32_t n, uint32_t first_ref_idx, uint64_t *nb_mers_out) {
+    if (!c || !pk || !offs || (n && (!pk->words || !pk->flags)) || (pk->n_exc && !pk->exc)) return MQ_ERR_ARG;
+    try {
+        SeqInput in; in.packed = true; in.words = pk->words; in.flags = pk->flags; in.exc = pk->exc; in.n_exc = pk->n_exc;
+        return index_add_impl(c, in, offs, n, first_ref_idx, nb_mers_out);
+    } catch (...) { c->err = "host allocation failed"; return MQ_ERR_NOMEM; }
 }
 
 int mq_index_add_segment(mq_ctx *c, const uint8_t *bytes, uint64_t n_bytes, uint32_t ref_idx, uint64_t ref_len,
                          uint64_t seg_start, uint64_t own_len) {
-    if (!c || !bytes) return MQ_ERR_ARG;
+    if (!c || !bytes || !c->kids.empty()) return MQ_ERR_ARG;
     if (c->frozen) { c->err = "index already frozen"; return MQ_ERR_STATE; }
     if (ref_len >= (1ull << 31) || seg_start + own_len > ref_len) { c->err = "segment outside its record / record too long"; return MQ_ERR_RANGE; }
     cudaSetDevice(c->device);
@@ -572,42 +968,25 @@ int mq_index_add_segment(mq_ctx *c, const uint8_t *bytes, uint64_t n_bytes, uint
     if (ref_len < (uint64_t)c->p.l + c->p.k - 1 || own_len == 0) { c->dir.push_back({(uint64_t)ref_idx, seg_start, 0ull}); return MQ_OK; }   // mers.rs:18
     const uint64_t ctx = seg_start > 0 ? 1 : 0;
     if (n_bytes < ctx + own_len) { c->err = "segment buffer shorter than ctx+own_len"; return MQ_ERR_ARG; }
-    int rc;
-    if ((rc = ensure(c, c->d_seqs, n_bytes + PAD))) return rc;
-    if ((rc = ensure(c, c->d_offs, 2 * 8))) return rc;
-    if ((rc = ensure(c, c->d_pos_base, 4))) return rc;
-    if ((rc = ensure(c, c->d_emit_len, 8))) return rc;
-    if ((rc = ensure_pin(c, 64))) return rc;
-    {
-        StageTimer t(c, "h2d");
-        // the record handed to the scan INCLUDES the context byte, so run starts are decided exactly as
-        // in a whole-record scan; only l-mers starting in [ctx, ctx+own_len) are emitted
-        uint64_t *ho = (uint64_t *)c->h_pin; ho[0] = 0; ho[1] = n_bytes;
-        uint32_t *hu = (uint32_t *)(ho + 2); hu[0] = (uint32_t)(seg_start - ctx); hu[1] = (uint32_t)ctx; hu[2] = (uint32_t)(ctx + own_len);
-        CK(cudaMemcpyAsync(c->d_seqs.p, bytes, n_bytes, cudaMemcpyHostToDevice, c->stream));
-        CK(cudaMemsetAsync((uint8_t *)c->d_seqs.p + n_bytes, 0, PAD, c->stream));
-        CK(cudaMemcpyAsync(c->d_offs.p, ho, 16, cudaMemcpyHostToDevice, c->stream));
-        CK(cudaMemcpyAsync(c->d_pos_base.p, hu, 4, cudaMemcpyHostToDevice, c->stream));
-        CK(cudaMemcpyAsync(c->d_emit_len.p, hu + 1, 8, cudaMemcpyHostToDevice, c->stream));
-    }
-    uint64_t M = 0;
-    if ((rc = run_scan(c, c->d_seqs.as<uint8_t>(), c->d_offs.as<uint64_t>(), 1, 0, c->d_pos_base.as<uint32_t>(),
-                       c->d_emit_len.as<uint32_t>(), &M))) return rc;
-    if ((rc = store_append(c, M))) return rc;
-    c->dir.push_back({(uint64_t)ref_idx, seg_start, M});
-    CK(cudaStreamSynchronize(c->stream));
-    timers_collect(c);
-    return MQ_OK;
+    try {
+        // the record handed to the scan INCLUDES the context byte, so run starts are decided exactly as in a
+        // whole-record scan; only l-mers starting in [ctx, ctx+own_len) are emitted
+        SeqInput in; in.seqs = bytes;
+        std::vector<Piece> pcs{Piece{0, n_bytes, ref_idx, (uint32_t)(seg_start - ctx), (uint32_t)ctx, (uint32_t)(ctx + own_len), seg_start}};
+        int rc = add_pieces(c, in, pcs, nullptr);
+        timers_collect(c);
+        return rc;
+    } catch (...) { c->err = "host allocation failed"; return MQ_ERR_NOMEM; }
 }
 
 int mq_store_info(mq_ctx *c, uint64_t *n_minimizers, uint32_t *n_segments) {
-    if (!c) return MQ_ERR_ARG;
+    if (!c || !c->kids.empty()) return MQ_ERR_ARG;
     if (n_minimizers) *n_minimizers = c->st_n;
     if (n_segments) *n_segments = (uint32_t)c->dir.size();
     return MQ_OK;
 }
 int mq_store_export(mq_ctx *c, void **d_pos, void **d_hash, uint64_t *dir) {
-    if (!c) return MQ_ERR_ARG;
+    if (!c || !c->kids.empty()) return MQ_ERR_ARG;
     cudaSetDevice(c->device);
     CK(cudaStreamSynchronize(c->stream));
     if (d_pos) *d_pos = c->st_pos.p;
@@ -615,8 +994,34 @@ int mq_store_export(mq_ctx *c, void **d_pos, void **d_hash, uint64_t *dir) {
     if (dir) for (size_t i = 0; i < c->dir.size(); i++) { dir[3 * i] = c->dir[i][0]; dir[3 * i + 1] = c->dir[i][1]; dir[3 * i + 2] = c->dir[i][2]; }
     return MQ_OK;
 }
+// make room for a store of n_minimizers entries and hand out its device arrays: a collective (ncclAllGather /
+// broadcast of every rank's share) can then land directly in place; mq_store_commit says what arrived
+int mq_store_reserve(mq_ctx *c, uint64_t n_minimizers, void **d_pos, void **d_hash) {
+    if (!c || !c->kids.empty() || !d_pos || !d_hash) return MQ_ERR_ARG;
+    if (c->frozen) { c->err = "index already frozen"; return MQ_ERR_STATE; }
+    cudaSetDevice(c->device);
+    int rc;
+    if ((rc = ensure_keep(c, c->st_pos, (n_minimizers + 64) * 4, c->st_n * 4))) return rc;
+    if ((rc = ensure_keep(c, c->st_hash, (n_minimizers + 64) * 8, c->st_n * 8))) return rc;
+    CK(cudaStreamSynchronize(c->stream));
+    *d_pos = c->st_pos.p; *d_hash = c->st_hash.p;
+    return MQ_OK;
+}
+int mq_store_commit(mq_ctx *c, uint64_t n_minimizers, const uint64_t *dir, uint32_t n_seg) {
+    if (!c || !c->kids.empty() || (n_seg && !dir)) return MQ_ERR_ARG;
+    if (c->frozen) { c->err = "index already frozen"; return MQ_ERR_STATE; }
+    uint64_t tot = 0;
+    for (uint32_t i = 0; i < n_seg; i++) tot += dir[3 * i + 2];
+    if (tot != n_minimizers || (n_minimizers + 64) * 4 > c->st_pos.cap) { c->err = "directory counts do not add up to n_minimizers"; return MQ_ERR_ARG; }
+    try {
+        c->st_n = n_minimizers;
+        c->dir.clear();
+        for (uint32_t i = 0; i < n_seg; i++) c->dir.push_back({dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]});
+    } catch (...) { return MQ_ERR_NOMEM; }
+    return MQ_OK;
+}
 int mq_store_import(mq_ctx *c, const void *d_pos, const void *d_hash, uint64_t n_min, const uint64_t *dir, uint32_t n_seg) {
-    if (!c || (n_min && (!d_pos || !d_hash)) || (n_seg && !dir)) return MQ_ERR_ARG;
+    if (!c || !c->kids.empty() || (n_min && (!d_pos || !d_hash)) || (n_seg && !dir)) return MQ_ERR_ARG;
     if (c->frozen) { c->err = "index already frozen"; return MQ_ERR_STATE; }
     cudaSetDevice(c->device);
     uint64_t tot = 0;
@@ -633,14 +1038,19 @@ int mq_store_import(mq_ctx *c, const void *d_pos, const void *d_hash, uint64_t n
     CK(cudaStreamSynchronize(c->stream));
     dfree(c->st_pos); dfree(c->st_hash);
     c->st_pos = np; c->st_hash = nh; c->st_n = n_min;
-    c->dir.clear();
-    for (uint32_t i = 0; i < n_seg; i++) c->dir.push_back({dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]});
+    try {
+        c->dir.clear();
+        for (uint32_t i = 0; i < n_seg; i++) c->dir.push_back({dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]});
+    } catch (...) { return MQ_ERR_NOMEM; }
     return MQ_OK;
 }
 
-int mq_index_freeze(mq_ctx *c, const uint64_t *ref_lens, uint32_t n_refs, uint64_t *n_unique, uint64_t *n_keys) {
-    if (!c || (n_refs && !ref_lens)) return MQ_ERR_ARG;
-    if (c->frozen) { c->err = "index already frozen"; return MQ_ERR_STATE; }
+}  // extern "C"
+
+namespace {
+
+// build the table of this context from its store (which must hold the minimizers of the WHOLE reference)
+int freeze_local(mq_ctx *c, const uint64_t *ref_lens, uint32_t n_refs) {
     cudaSetDevice(c->device);
     timers_reset(c);
     int rc;
@@ -672,14 +1082,14 @@ int mq_index_freeze(mq_ctx *c, const uint64_t *ref_lens, uint32_t n_refs, uint64
     std::vector<std::array<uint64_t, 3>> sd(ns);
     for (size_t i = 0; i < ns; i++) sd[i] = c->dir[perm[i]];
     // records = runs of equal ref_idx
-    std::vector<uint32_t> rec_off, rec_id, km_off;
+    std::vector<uint32_t> rec_off, rec_id;
     uint64_t acc = 0, n_tuples = 0;
     c->nb_mers.assign(n_refs, 0);
     for (size_t i = 0; i < ns;) {
         size_t j = i; uint64_t cnt = 0;
         while (j < ns && sd[j][0] == sd[i][0]) { cnt += sd[j][2]; j++; }
         if (sd[i][0] >= n_refs) { c->err = "segment ref_idx >= n_refs"; return MQ_ERR_ARG; }
-        rec_off.push_back((uint32_t)acc); rec_id.push_back((uint32_t)sd[i][0]); km_off.push_back((uint32_t)n_tuples);
+        rec_off.push_back((uint32_t)acc); rec_id.push_back((uint32_t)sd[i][0]);
         uint64_t q = cnt >= c->p.k ? cnt - c->p.k + 1 : 0;
         c->nb_mers[sd[i][0]] = q; n_tuples += q; acc += cnt;
         i = j;
@@ -694,8 +1104,9 @@ int mq_index_freeze(mq_ctx *c, const uint64_t *ref_lens, uint32_t n_refs, uint64
     if ((rc = ensure(c, c->d_table, (cap + 1) * sizeof(Slot)))) return rc;
     c->tmask = cap - 1;
     if ((rc = ensure(c, c->d_ref_lens, ((size_t)n_refs + 1) * 8))) return rc;
-    if ((rc = ensure(c, c->d_misc, ((size_t)n_rec + 2) * 4 * 3))) return rc;
+    if ((rc = ensure(c, c->d_misc, ((size_t)n_rec + 2) * 4 * 3 + 64))) return rc;
     uint32_t *d_rec_off = c->d_misc.as<uint32_t>(), *d_rec_id = d_rec_off + n_rec + 2;
+    unsigned long long *d_cnt = (unsigned long long *)(d_rec_id + n_rec + 2 + ((n_rec & 1) ? 1 : 0));   // 8-byte aligned
     {
         StageTimer t(c, "insert");
         if (n_refs) CK(cudaMemcpyAsync(c->d_ref_lens.p, ref_lens, (size_t)n_refs * 8, cudaMemcpyHostToDevice, c->stream));
@@ -711,7 +1122,6 @@ int mq_index_freeze(mq_ctx *c, const uint64_t *ref_lens, uint32_t n_refs, uint64
             k_insert_kminmers<<<(uint32_t)((c->st_n + 255) / 256), 256, 0, c->stream>>>(a, t2, 1);
             c->launches++;
         }
-        unsigned long long *d_cnt = (unsigned long long *)(c->d_scalars.as<uint64_t>() + SC_COUNT0);
         CK(cudaMemsetAsync(d_cnt, 0, 16, c->stream));
         k_table_count<<<c->n_sm * 8, 256, 0, c->stream>>>(c->d_table.as<Slot>(), cap + 1, d_cnt);
         c->launches++;
@@ -721,16 +1131,90 @@ int mq_index_freeze(mq_ctx *c, const uint64_t *ref_lens, uint32_t n_refs, uint64
         CK(cudaStreamSynchronize(c->stream));
         c->n_unique = hc[0]; c->n_keys = hc[1];
     }
-    if (n_unique) *n_unique = c->n_unique;
-    if (n_keys) *n_keys = c->n_keys;
     c->n_refs = n_refs; c->frozen = true;
     dfree(c->st_pos); dfree(c->st_hash); c->st_n = 0;
     timers_collect(c);
     return MQ_OK;
 }
 
+// multi-GPU store exchange: every child ends up with the union of all stores (an all-gather of device arrays,
+// GPU to GPU: cudaMemcpyPeerAsync rides NVLink when peer access is on).  Every child pulls the parts of the others.
+int exchange_stores(mq_ctx *par) {
+    const size_t G = par->kids.size();
+    std::vector<uint64_t> cnt(G), off(G + 1, 0);
+    for (size_t g = 0; g < G; g++) { cnt[g] = par->kids[g]->st_n; off[g + 1] = off[g] + cnt[g]; }
+    const uint64_t tot = off[G];
+    std::vector<DBuf> np(G), nh(G);
+    for (size_t g = 0; g < G; g++) {
+        mq_ctx *c = par->kids[g];
+        cudaSetDevice(c->device);
+        int rc;
+        if ((rc = ensure(c, np[g], (tot + 64) * 4))) { par->err = c->err; return rc; }
+        if ((rc = ensure(c, nh[g], (tot + 64) * 8))) { par->err = c->err; return rc; }
+    }
+    for (size_t g = 0; g < G; g++) {
+        mq_ctx *c = par->kids[g];
+        cudaSetDevice(c->device);
+        StageTimer t(c, "exchange");
+        for (size_t q = 0; q < G; q++) {
+            const size_t src = (g + q) % G;                  // start with my own part, then walk the ring
+            mq_ctx *s = par->kids[src];
+            if (!cnt[src]) continue;
+            cudaError_t e1 = cudaMemcpyPeerAsync(np[g].as<uint32_t>() + off[src], c->device, s->st_pos.p, s->device, cnt[src] * 4, c->stream);
+            cudaError_t e2 = cudaMemcpyPeerAsync(nh[g].as<uint64_t>() + off[src], c->device, s->st_hash.p, s->device, cnt[src] * 8, c->stream);
+            if (e1 != cudaSuccess || e2 != cudaSuccess) { par->err = std::string("cudaMemcpyPeerAsync: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2); return MQ_ERR_CUDA; }
+        }
+    }
+    for (size_t g = 0; g < G; g++) {
+        mq_ctx *c = par->kids[g];
+        cudaSetDevice(c->device);
+        if (cudaStreamSynchronize(c->stream) != cudaSuccess) { par->err = "store exchange failed"; return MQ_ERR_CUDA; }
+    }
+    std::vector<std::array<uint64_t, 3>> dir;
+    for (size_t g = 0; g < G; g++) for (auto &d : par->kids[g]->dir) dir.push_back(d);
+    for (size_t g = 0; g < G; g++) {
+        mq_ctx *c = par->kids[g];
+        cudaSetDevice(c->device);
+        dfree(c->st_pos); dfree(c->st_hash);
+        c->st_pos = np[g]; c->st_hash = nh[g]; c->st_n = tot; c->dir = dir;
+    }
+    return MQ_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mq_index_freeze(mq_ctx *c, const uint64_t *ref_lens, uint32_t n_refs, uint64_t *n_unique, uint64_t *n_keys) {
+    if (!c || (n_refs && !ref_lens)) return MQ_ERR_ARG;
+    try {
+        if (c->kids.empty()) {
+            if (c->frozen) { c->err = "index already frozen"; return MQ_ERR_STATE; }
+            int rc = freeze_local(c, ref_lens, n_refs);
+            if (rc) return rc;
+            if (n_unique) *n_unique = c->n_unique;
+            if (n_keys) *n_keys = c->n_keys;
+            return MQ_OK;
+        }
+        if (c->kids[0]->frozen) { c->err = "index already frozen"; return MQ_ERR_STATE; }
+        int rc = exchange_stores(c);
+        if (rc) return rc;
+        const size_t G = c->kids.size();
+        std::vector<int> rcs(G, 0);
+        std::vector<std::thread> th;
+        for (size_t g = 0; g < G; g++) th.emplace_back([&, g]() { rcs[g] = freeze_local(c->kids[g], ref_lens, n_refs); });
+        for (auto &t : th) t.join();
+        for (size_t g = 0; g < G; g++) if (rcs[g]) { c->err = c->kids[g]->err; return rcs[g]; }
+        for (size_t g = 1; g < G; g++) if (c->kids[g]->n_unique != c->kids[0]->n_unique || c->kids[g]->n_keys != c->kids[0]->n_keys) { c->err = "replicated tables differ"; return MQ_ERR_STATE; }
+        if (n_unique) *n_unique = c->kids[0]->n_unique;
+        if (n_keys) *n_keys = c->kids[0]->n_keys;
+        return MQ_OK;
+    } catch (...) { c->err = "host allocation failed"; return MQ_ERR_NOMEM; }
+}
+
 int mq_index_nb_mers(mq_ctx *c, uint64_t *nb, uint32_t n_refs) {
     if (!c || !nb) return MQ_ERR_ARG;
+    c = FIRST(c);
     if (!c->frozen) return MQ_ERR_STATE;
     for (uint32_t i = 0; i < n_refs; i++) nb[i] = i < c->nb_mers.size() ? c->nb_mers[i] : 0;
     return MQ_OK;
@@ -747,72 +1231,80 @@ struct IndexFileHeader {
 }
 int mq_index_save(mq_ctx *c, const char *path, const char *names_blob, uint64_t names_bytes) {
     if (!c || !path || (names_bytes && !names_blob)) return MQ_ERR_ARG;
+    c = FIRST(c);
     if (!c->frozen) { c->err = "index not frozen"; return MQ_ERR_STATE; }
     cudaSetDevice(c->device);
-    FILE *f = fopen(path, "wb");
-    if (!f) { c->err = std::string("cannot create ") + path; return MQ_ERR_ARG; }
-    IndexFileHeader h{};
-    memcpy(h.magic, "MQB200IX", 8);
-    h.version = 1; h.k = c->p.k; h.l = c->p.l; h.use_hpc = c->p.use_hpc; h.density = c->p.density;
-    h.slots = c->tmask + 2; h.n_unique = c->n_unique; h.n_keys = c->n_keys; h.n_refs = c->n_refs; h.names_bytes = names_bytes;
-    bool ok = fwrite(&h, sizeof h, 1, f) == 1;
-    std::vector<uint64_t> lens(c->n_refs);
-    if (c->n_refs) {
-        if (cudaMemcpy(lens.data(), c->d_ref_lens.p, (size_t)c->n_refs * 8, cudaMemcpyDeviceToHost) != cudaSuccess) { fclose(f); c->err = "D2H ref_lens"; return MQ_ERR_CUDA; }
-        ok = ok && fwrite(lens.data(), 8, c->n_refs, f) == c->n_refs;
-        std::vector<uint64_t> nb(c->n_refs, 0);
-        for (uint32_t i = 0; i < c->n_refs && i < c->nb_mers.size(); i++) nb[i] = c->nb_mers[i];
-        ok = ok && fwrite(nb.data(), 8, c->n_refs, f) == c->n_refs;
-    }
-    if (names_bytes) ok = ok && fwrite(names_blob, 1, names_bytes, f) == names_bytes;
-    const size_t CH = 64u << 20;                       // table goes out in 64 MB pieces through the pinned bounce buffer
-    int rc = ensure_pin(c, CH);
-    if (rc) { fclose(f); return rc; }
-    const size_t total = (size_t)h.slots * sizeof(Slot);
-    for (size_t off = 0; off < total && ok; off += CH) {
-        const size_t n = std::min(CH, total - off);
-        if (cudaMemcpy(c->h_pin, (const uint8_t *)c->d_table.p + off, n, cudaMemcpyDeviceToHost) != cudaSuccess) { fclose(f); c->err = "D2H table"; return MQ_ERR_CUDA; }
-        ok = fwrite(c->h_pin, 1, n, f) == n;
-    }
-    ok = (fclose(f) == 0) && ok;
-    if (!ok) { c->err = std::string("short write to ") + path; return MQ_ERR_ARG; }
-    return MQ_OK;
+    try {
+        FILE *f = fopen(path, "wb");
+        if (!f) { c->err = std::string("cannot create ") + path; return MQ_ERR_ARG; }
+        IndexFileHeader h{};
+        memcpy(h.magic, "MQB200IX", 8);
+        h.version = 1; h.k = c->p.k; h.l = c->p.l; h.use_hpc = c->p.use_hpc; h.density = c->p.density;
+        h.slots = c->tmask + 2; h.n_unique = c->n_unique; h.n_keys = c->n_keys; h.n_refs = c->n_refs; h.names_bytes = names_bytes;
+        bool ok = fwrite(&h, sizeof h, 1, f) == 1;
+        std::vector<uint64_t> lens(c->n_refs);
+        if (c->n_refs) {
+            if (cudaMemcpy(lens.data(), c->d_ref_lens.p, (size_t)c->n_refs * 8, cudaMemcpyDeviceToHost) != cudaSuccess) { fclose(f); c->err = "D2H ref_lens"; return MQ_ERR_CUDA; }
+            ok = ok && fwrite(lens.data(), 8, c->n_refs, f) == c->n_refs;
+            std::vector<uint64_t> nb(c->n_refs, 0);
+            for (uint32_t i = 0; i < c->n_refs && i < c->nb_mers.size(); i++) nb[i] = c->nb_mers[i];
+            ok = ok && fwrite(nb.data(), 8, c->n_refs, f) == c->n_refs;
+        }
+        if (names_bytes) ok = ok && fwrite(names_blob, 1, names_bytes, f) == names_bytes;
+        const size_t CH = 64u << 20;                       // table goes out in 64 MB pieces through the pinned bounce buffer
+        int rc = ensure_host(c, c->h_pin, CH);
+        if (rc) { fclose(f); return rc; }
+        const size_t total = (size_t)h.slots * sizeof(Slot);
+        for (size_t off = 0; off < total && ok; off += CH) {
+            const size_t n = std::min(CH, total - off);
+            if (cudaMemcpy(c->h_pin.p, (const uint8_t *)c->d_table.p + off, n, cudaMemcpyDeviceToHost) != cudaSuccess) { fclose(f); c->err = "D2H table"; return MQ_ERR_CUDA; }
+            ok = fwrite(c->h_pin.p, 1, n, f) == n;
+        }
+        ok = (fclose(f) == 0) && ok;
+        if (!ok) { c->err = std::string("short write to ") + path; return MQ_ERR_ARG; }
+        return MQ_OK;
+    } catch (...) { c->err = "host allocation failed"; return MQ_ERR_NOMEM; }
 }
-int mq_index_load(mq_ctx *c, const char *path, uint64_t *ref_lens_out, uint32_t ref_cap, uint32_t *n_refs_out, char *names_out,
-                  uint64_t names_cap, uint64_t *names_bytes_out, uint64_t *n_unique_out) {
-    if (!c || !path) return MQ_ERR_ARG;
+
+static int index_load_one(mq_ctx *c, const char *path, uint64_t *ref_lens_out, uint32_t ref_cap, uint32_t *n_refs_out, char *names_out,
+                          uint64_t names_cap, uint64_t *names_bytes_out, uint64_t *n_unique_out) {
     if (c->frozen || c->st_n || !c->dir.empty()) { c->err = "load needs a fresh context"; return MQ_ERR_STATE; }
     cudaSetDevice(c->device);
     FILE *f = fopen(path, "rb");
     if (!f) { c->err = std::string("cannot open ") + path; return MQ_ERR_ARG; }
+    struct Closer { FILE *f; ~Closer() { fclose(f); } } closer{f};
+    struct stat st;
+    if (fstat(fileno(f), &st) != 0) { c->err = "cannot stat index file"; return MQ_ERR_ARG; }
+    const uint64_t fsize = (uint64_t)st.st_size;
     IndexFileHeader h{};
-    if (fread(&h, sizeof h, 1, f) != 1 || memcmp(h.magic, "MQB200IX", 8) != 0 || h.version != 1) { fclose(f); c->err = "not a mapquik_b200 index file"; return MQ_ERR_ARG; }
+    if (fread(&h, sizeof h, 1, f) != 1 || memcmp(h.magic, "MQB200IX", 8) != 0 || h.version != 1) { c->err = "not a mapquik_b200 index file"; return MQ_ERR_ARG; }
     if (h.k != c->p.k || h.l != c->p.l || h.use_hpc != c->p.use_hpc || h.density != c->p.density) {
-        fclose(f); c->err = "index was built with different k / l / density / hpc"; return MQ_ERR_ARG;
+        c->err = "index was built with different k / l / density / hpc"; return MQ_ERR_ARG;
     }
-    if (h.slots < 2 || ((h.slots - 1) & (h.slots - 2)) != 0) { fclose(f); c->err = "corrupt index header"; return MQ_ERR_ARG; }
+    // the header is untrusted: every size must be consistent with the file before anything is allocated from it
+    if (h.slots < 2 || ((h.slots - 1) & (h.slots - 2)) != 0 || h.slots > (1ull << 40) || h.n_refs >= (1ull << 31) || h.names_bytes > fsize ||
+        sizeof h + h.n_refs * 16 + h.names_bytes + h.slots * sizeof(Slot) != fsize) { c->err = "corrupt or truncated index file"; return MQ_ERR_ARG; }
     if (n_refs_out) *n_refs_out = (uint32_t)h.n_refs;
     if (names_bytes_out) *names_bytes_out = h.names_bytes;
     if (n_unique_out) *n_unique_out = h.n_unique;
     std::vector<uint64_t> lens(h.n_refs), nb(h.n_refs);
     bool ok = true;
     if (h.n_refs) ok = fread(lens.data(), 8, h.n_refs, f) == h.n_refs && fread(nb.data(), 8, h.n_refs, f) == h.n_refs;
-    if (ref_lens_out) { if (ref_cap < h.n_refs) { fclose(f); c->err = "ref_lens_out too small"; return MQ_ERR_ARG; } memcpy(ref_lens_out, lens.data(), h.n_refs * 8); }
+    if (ref_lens_out) { if (ref_cap < h.n_refs) { c->err = "ref_lens_out too small"; return MQ_ERR_ARG; } memcpy(ref_lens_out, lens.data(), h.n_refs * 8); }
     if (h.names_bytes) {
-        if (names_out) { if (names_cap < h.names_bytes) { fclose(f); c->err = "names_out too small"; return MQ_ERR_ARG; } ok = ok && fread(names_out, 1, h.names_bytes, f) == h.names_bytes; }
+        if (names_out) { if (names_cap < h.names_bytes) { c->err = "names_out too small"; return MQ_ERR_ARG; } ok = ok && fread(names_out, 1, h.names_bytes, f) == h.names_bytes; }
         else ok = ok && fseek(f, (long)h.names_bytes, SEEK_CUR) == 0;
     }
     int rc;
     const size_t total = (size_t)h.slots * sizeof(Slot), CH = 64u << 20;
-    if ((rc = ensure(c, c->d_table, total))) { fclose(f); return rc; }
-    if ((rc = ensure(c, c->d_ref_lens, (h.n_refs + 1) * 8))) { fclose(f); return rc; }
-    if ((rc = ensure_pin(c, CH))) { fclose(f); return rc; }
+    if ((rc = ensure(c, c->d_table, total))) return rc;
+    if ((rc = ensure(c, c->d_ref_lens, (h.n_refs + 1) * 8))) return rc;
+    if ((rc = ensure_host(c, c->h_pin, CH))) return rc;
     for (size_t off = 0; off < total && ok; off += CH) {
         const size_t n = std::min(CH, total - off);
-        ok = fread(c->h_pin, 1, n, f) == n;
-        if (ok && cudaMemcpy((uint8_t *)c->d_table.p + off, c->h_pin, n, cudaMemcpyHostToDevice) != cudaSuccess) { fclose(f); c->err = "H2D table"; return MQ_ERR_CUDA; }
+        ok = fread(c->h_pin.p, 1, n, f) == n;
+        if (ok && cudaMemcpy((uint8_t *)c->d_table.p + off, c->h_pin.p, n, cudaMemcpyHostToDevice) != cudaSuccess) { c->err = "H2D table"; return MQ_ERR_CUDA; }
     }
-    fclose(f);
     if (!ok) { c->err = "truncated index file"; return MQ_ERR_ARG; }
     if (h.n_refs && cudaMemcpy(c->d_ref_lens.p, lens.data(), h.n_refs * 8, cudaMemcpyHostToDevice) != cudaSuccess) { c->err = "H2D ref_lens"; return MQ_ERR_CUDA; }
     c->tmask = h.slots - 2; c->n_refs = (uint32_t)h.n_refs; c->n_unique = h.n_unique; c->n_keys = h.n_keys;
@@ -820,86 +1312,91 @@ int mq_index_load(mq_ctx *c, const char *path, uint64_t *ref_lens_out, uint32_t 
     c->frozen = true;
     return MQ_OK;
 }
-
-// ---- mapping ---------------------------------------------------------------------------------------
-int mq_map_batch_device(mq_ctx *c, const uint8_t *d_seqs, const uint64_t *d_offs, uint32_t n, uint64_t total_bytes, mq_hit *d_out) {
-    if (!c || !d_offs || !d_out || (!d_seqs && total_bytes)) return MQ_ERR_ARG;
-    if (!c->frozen) { c->err = "index not frozen"; return MQ_ERR_STATE; }
-    if (((uintptr_t)d_seqs & 15) != 0) { c->err = "device sequence buffer must be 16-byte aligned"; return MQ_ERR_ARG; }
-    cudaSetDevice(c->device);
-    timers_reset(c);
-    if (n == 0) return MQ_OK;
-    int rc = map_device(c, d_seqs, d_offs, n, (HitRec *)d_out);
-    return rc;
+int mq_index_load(mq_ctx *c, const char *path, uint64_t *ref_lens_out, uint32_t ref_cap, uint32_t *n_refs_out, char *names_out,
+                  uint64_t names_cap, uint64_t *names_bytes_out, uint64_t *n_unique_out) {
+    if (!c || !path) return MQ_ERR_ARG;
+    try {
+        if (c->kids.empty()) return index_load_one(c, path, ref_lens_out, ref_cap, n_refs_out, names_out, names_cap, names_bytes_out, n_unique_out);
+        for (size_t g = 0; g < c->kids.size(); g++) {
+            int rc = index_load_one(c->kids[g], path, g ? nullptr : ref_lens_out, ref_cap, n_refs_out, g ? nullptr : names_out, names_cap, names_bytes_out, n_unique_out);
+            if (rc) { c->err = c->kids[g]->err; return rc; }
+        }
+        return MQ_OK;
+    } catch (...) { c->err = "host allocation failed"; return MQ_ERR_NOMEM; }
 }
 
-// upload sub-batch [i0, i1) into double-buffer slot b on the copy stream
-static int upload_async(mq_ctx *c, int b, const uint8_t *seqs, const uint64_t *offs, uint32_t i0, uint32_t i1) {
-    const uint64_t b0 = offs[i0], nb = offs[i1] - b0; const uint32_t m = i1 - i0;
+// ---- mapping ---------------------------------------------------------------------------------------
+static int map_impl(mq_ctx *c, const SeqInput &in, const uint64_t *offs, uint32_t n, mq_hit *out, mq_hit *d_out) {
     int rc;
-    if ((rc = ensure(c, c->d_seqs2[b], nb + PAD))) return rc;
-    if ((rc = ensure(c, c->d_offs2[b], ((size_t)m + 1) * 8))) return rc;
-    if (c->h_offs2_cap[b] < ((size_t)m + 1) * 8) {
-        if (c->h_offs2[b]) cudaFreeHost(c->h_offs2[b]);
-        c->h_offs2[b] = nullptr; c->h_offs2_cap[b] = 0;
-        size_t want = ((size_t)m + 1) * 8 * 2;
-        CK(cudaMallocHost(&c->h_offs2[b], want));
-        c->h_offs2_cap[b] = want;
+    if ((rc = check_offs(c, offs, n))) return rc;
+    if (c->kids.empty()) {
+        if (!c->frozen) { c->err = "index not frozen"; return MQ_ERR_STATE; }
+        cudaSetDevice(c->device);
+        timers_reset(c);
+        if (n == 0) return MQ_OK;
+        rc = map_pipeline(c, in, offs, n, out, d_out);
+        timers_collect(c, false);
+        return rc;
     }
-    uint64_t *ho = (uint64_t *)c->h_offs2[b];
-    for (uint32_t i = 0; i <= m; i++) ho[i] = offs[i0 + i] - b0;
-    {
-        StageTimer t(c, "h2d", c->copy_stream);
-        if (nb) CK(cudaMemcpyAsync(c->d_seqs2[b].p, seqs + b0, nb, cudaMemcpyHostToDevice, c->copy_stream));
-        CK(cudaMemsetAsync((uint8_t *)c->d_seqs2[b].p + nb, 0, PAD, c->copy_stream));
-        CK(cudaMemcpyAsync(c->d_offs2[b].p, ho, ((size_t)m + 1) * 8, cudaMemcpyHostToDevice, c->copy_stream));
+    // multi-GPU: reads are sharded in contiguous blocks of near-equal base counts, no inter-GPU communication
+    // (find_matches is a pure function of the read and the frozen index, mers.rs:77)
+    if (!c->kids[0]->frozen) { c->err = "index not frozen"; return MQ_ERR_STATE; }
+    if (d_out || in.resident) { c->err = "device-resident inputs need a single-GPU context"; return MQ_ERR_ARG; }
+    if (n == 0) return MQ_OK;
+    const size_t G = c->kids.size();
+    std::vector<uint32_t> cut(G + 1, n);
+    cut[0] = 0;
+    const uint64_t total = offs[n] - offs[0];
+    for (size_t g = 1; g < G; g++) {
+        const uint64_t want = offs[0] + total * g / G;
+        cut[g] = (uint32_t)(std::lower_bound(offs, offs + n + 1, want) - offs);
+        cut[g] = std::max(cut[g], cut[g - 1]);
     }
-    CK(cudaEventRecord(c->ev_copied[b], c->copy_stream));
+    c->kid_share.assign(G, {0, 0});
+    std::vector<int> rcs(G, 0);
+    std::vector<std::thread> th;
+    for (size_t g = 0; g < G; g++) {
+        c->kid_share[g] = {cut[g], cut[g + 1]};
+        if (cut[g + 1] == cut[g]) continue;
+        th.emplace_back([&, g]() {
+            mq_ctx *k = c->kids[g];
+            cudaSetDevice(k->device);
+            timers_reset(k);
+            rcs[g] = map_pipeline(k, in, offs + cut[g], cut[g + 1] - cut[g], out + cut[g], nullptr);
+            timers_collect(k, false);
+        });
+    }
+    for (auto &t : th) t.join();
+    for (size_t g = 0; g < G; g++) if (rcs[g]) { c->err = c->kids[g]->err; return rcs[g]; }
     return MQ_OK;
 }
 
 int mq_map_batch(mq_ctx *c, const uint8_t *seqs, const uint64_t *offs, uint32_t n, mq_hit *out) {
     if (!c || !offs || (!seqs && n) || (!out && n)) return MQ_ERR_ARG;
-    if (!c->frozen) { c->err = "index not frozen"; return MQ_ERR_STATE; }
-    cudaSetDevice(c->device);
-    timers_reset(c);
-    int rc;
-    if ((rc = check_offs(c, offs, n))) return rc;
-    if (n == 0) return MQ_OK;
-    if (!c->copy_stream) {
-        CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-        CK(cudaEventCreateWithFlags(&c->ev_copied[0], cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&c->ev_copied[1], cudaEventDisableTiming));
-    }
-    // sub-batch boundaries: about an eighth of the batch, between 128 MB and 1 GB -- small enough that the first
-    // (un-overlapped) upload is short, large enough that per-sub-batch launches and scalar read-backs stay negligible
-    const uint64_t total_bytes = offs[n] - offs[0];
-    const uint64_t sub_bytes = std::min<uint64_t>(std::max<uint64_t>(total_bytes / 8, MAP_SUB_BATCH_BYTES), 1ull << 30);
-    std::vector<uint32_t> cut{0};
-    for (uint32_t i0 = 0; i0 < n;) {
-        uint32_t i1 = i0 + 1;
-        while (i1 < n && offs[i1 + 1] - offs[i0] <= sub_bytes) i1++;
-        cut.push_back(i1); i0 = i1;
-    }
-    const size_t ns = cut.size() - 1;
-    // H2D of sub-batch i+1 runs on the copy stream while sub-batch i computes
-    if ((rc = upload_async(c, 0, seqs, offs, cut[0], cut[1]))) return rc;
-    for (size_t i = 0; i < ns; i++) {
-        const int b = (int)(i & 1);
-        const uint32_t m = cut[i + 1] - cut[i];
-        if (i + 1 < ns && (rc = upload_async(c, 1 - b, seqs, offs, cut[i + 1], cut[i + 2]))) return rc;
-        CK(cudaStreamWaitEvent(c->stream, c->ev_copied[b], 0));
-        if ((rc = ensure(c, c->d_hits, (size_t)m * sizeof(HitRec)))) return rc;
-        if ((rc = map_device(c, c->d_seqs2[b].as<uint8_t>(), c->d_offs2[b].as<uint64_t>(), m, c->d_hits.as<HitRec>()))) return rc;
-        {
-            StageTimer t(c, "d2h");
-            CK(cudaMemcpyAsync(out + cut[i], c->d_hits.p, (size_t)m * sizeof(HitRec), cudaMemcpyDeviceToHost, c->stream));
-        }
-        CK(cudaStreamSynchronize(c->stream));      // slot b and d_hits are free again
-    }
-    CK(cudaStreamSynchronize(c->copy_stream));
-    timers_collect(c);
-    return MQ_OK;
+    try { SeqInput in; in.seqs = seqs; return map_impl(c, in, offs, n, out, nullptr); }
+    catch (...) { c->err = "host allocation failed"; return MQ_ERR_NOMEM; }
+}
+int mq_map_batch_packed(mq_ctx *c, const mq_packed *pk, const uint64_t *offs, uint32_t n, mq_hit *out) {
+    if (!c || !pk || !offs || (n && (!pk->words || !pk->flags || !out)) || (pk->n_exc && !pk->exc)) return MQ_ERR_ARG;
+    try {
+        SeqInput in; in.packed = true; in.words = pk->words; in.flags = pk->flags; in.exc = pk->exc; in.n_exc = pk->n_exc;
+        return map_impl(c, in, offs, n, out, nullptr);
+    } catch (...) { c->err = "host allocation failed"; return MQ_ERR_NOMEM; }
+}
+int mq_map_batch_device(mq_ctx *c, const uint8_t *d_seqs, const uint64_t *offs, uint32_t n, mq_hit *d_out) {
+    if (!c || !offs || (n && (!d_seqs || !d_out))) return MQ_ERR_ARG;
+    if (((uintptr_t)d_seqs & 15) != 0) { c->err = "device sequence buffer must be 16-byte aligned"; return MQ_ERR_ARG; }
+    try { SeqInput in; in.seqs = d_seqs; in.resident = true; return map_impl(c, in, offs, n, nullptr, d_out); }
+    catch (...) { c->err = "host allocation failed"; return MQ_ERR_NOMEM; }
+}
+int mq_map_batch_packed_device(mq_ctx *c, const mq_packed *d_pk, const uint64_t *offs, uint32_t n, mq_hit *d_out) {
+    if (!c || !d_pk || !offs || (n && (!d_pk->words || !d_pk->flags || !d_out)) || (d_pk->n_exc && !d_pk->exc)) return MQ_ERR_ARG;
+    if (((uintptr_t)d_pk->words & 15) != 0) { c->err = "device word buffer must be 16-byte aligned"; return MQ_ERR_ARG; }
+    if (d_pk->n_exc >= (1ull << 32)) { c->err = "too many exception intervals"; return MQ_ERR_RANGE; }
+    try {
+        SeqInput in; in.packed = true; in.resident = true; in.words = d_pk->words; in.flags = d_pk->flags; in.exc = d_pk->exc; in.n_exc = d_pk->n_exc;
+        return map_impl(c, in, offs, n, nullptr, d_out);
+    } catch (...) { c->err = "host allocation failed"; return MQ_ERR_NOMEM; }
 }
 
 int mq_format_paf(char *buf, size_t cap, const char *q_id, uint64_t q_len, const char *r_id, uint64_t r_len, const mq_hit *h) {
@@ -911,26 +1408,28 @@ int mq_format_paf(char *buf, size_t cap, const char *q_id, uint64_t q_len, const
     return (w < 0 || (size_t)w >= cap) ? MQ_ERR_ARG : w;
 }
 
-// ---- introspection -----------------------------------------------------------------------------------
-int mq_minimizers(mq_ctx *c, const uint8_t *seqs, const uint64_t *offs, uint32_t n, uint64_t *seq_off, uint32_t *pos,
-                  uint64_t *hash, uint64_t cap, uint64_t *n_total) {
-    if (!c || !offs || (!seqs && n)) return MQ_ERR_ARG;
+// ---- introspection (single-GPU contexts; synchronous) ---------------------------------------------------------
+// stage records [0, n) of an ASCII or packed host batch into slot 0 and scan them
+static int scan_batch_sync(mq_ctx *c, const SeqInput &in, const uint64_t *offs, uint32_t n, uint32_t min_len, BatchDev &bd, uint64_t *M,
+                           std::vector<uint32_t> *so) {
+    int rc;
+    if ((rc = init_streams(c))) return rc;
+    std::vector<Piece> pcs(n);
+    for (uint32_t i = 0; i < n; i++) pcs[i] = Piece{offs[i], offs[i + 1], 0, 0, 0, 0, 0};
+    if ((rc = stage_pieces(c, c->slot[0], in, pcs.data(), 0, n, min_len, false, bd))) return rc;
+    return scan_sync(c, c->slot[0], bd, M, so);
+}
+
+static int minimizers_impl(mq_ctx *c, const SeqInput &in, const uint64_t *offs, uint32_t n, uint64_t *seq_off, uint32_t *pos,
+                           uint64_t *hash, uint64_t cap, uint64_t *n_total) {
     cudaSetDevice(c->device);
     timers_reset(c);
     int rc;
     if ((rc = check_offs(c, offs, n))) return rc;
-    uint64_t M = 0;
-    if (n) {
-        if ((rc = upload_batch(c, seqs, offs, 0, n))) return rc;
-        if ((rc = run_scan(c, c->d_seqs.as<uint8_t>(), c->d_offs.as<uint64_t>(), n, 0, nullptr, nullptr, &M))) return rc;
-    }
+    uint64_t M = 0; std::vector<uint32_t> so; BatchDev bd;
+    if (n && (rc = scan_batch_sync(c, in, offs, n, 0, bd, &M, &so))) return rc;
     if (n_total) *n_total = M;
-    if (seq_off && n) {
-        std::vector<uint32_t> so((size_t)n + 1);
-        CK(cudaMemcpyAsync(so.data(), c->d_seq_off.p, ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
-        CK(cudaStreamSynchronize(c->stream));
-        for (uint32_t i = 0; i <= n; i++) seq_off[i] = so[i];
-    }
+    if (seq_off && n) for (uint32_t i = 0; i <= n; i++) seq_off[i] = so[i];
     if (pos && hash && M) {
         if (cap < M) { c->err = "output capacity too small"; return MQ_ERR_ARG; }
         CK(cudaMemcpyAsync(pos, c->d_pos.p, M * 4, cudaMemcpyDeviceToHost, c->stream));
@@ -940,53 +1439,68 @@ int mq_minimizers(mq_ctx *c, const uint8_t *seqs, const uint64_t *offs, uint32_t
     timers_collect(c);
     return MQ_OK;
 }
+int mq_minimizers(mq_ctx *c, const uint8_t *seqs, const uint64_t *offs, uint32_t n, uint64_t *seq_off, uint32_t *pos,
+                  uint64_t *hash, uint64_t cap, uint64_t *n_total) {
+    if (!c || !c->kids.empty() || !offs || (!seqs && n)) return MQ_ERR_ARG;
+    try { SeqInput in; in.seqs = seqs; return minimizers_impl(c, in, offs, n, seq_off, pos, hash, cap, n_total); }
+    catch (...) { c->err = "host allocation failed"; return MQ_ERR_NOMEM; }
+}
+int mq_minimizers_packed(mq_ctx *c, const mq_packed *pk, const uint64_t *offs, uint32_t n, uint64_t *seq_off, uint32_t *pos,
+                         uint64_t *hash, uint64_t cap, uint64_t *n_total) {
+    if (!c || !c->kids.empty() || !pk || !offs || (n && (!pk->words || !pk->flags)) || (pk->n_exc && !pk->exc)) return MQ_ERR_ARG;
+    try {
+        SeqInput in; in.packed = true; in.words = pk->words; in.flags = pk->flags; in.exc = pk->exc; in.n_exc = pk->n_exc;
+        return minimizers_impl(c, in, offs, n, seq_off, pos, hash, cap, n_total);
+    } catch (...) { c->err = "host allocation failed"; return MQ_ERR_NOMEM; }
+}
 
 int mq_kminmers(mq_ctx *c, const uint8_t *seqs, const uint64_t *offs, uint32_t n, uint64_t *seq_off, uint32_t *start,
                 uint32_t *end, uint32_t *offrev, uint64_t *hash, uint64_t cap, uint64_t *n_total) {
-    if (!c || !offs || (!seqs && n)) return MQ_ERR_ARG;
+    if (!c || !c->kids.empty() || !offs || (!seqs && n)) return MQ_ERR_ARG;
     cudaSetDevice(c->device);
     timers_reset(c);
     int rc;
     if ((rc = check_offs(c, offs, n))) return rc;
-    uint64_t M = 0, Q = 0;
-    std::vector<uint32_t> so((size_t)n + 1, 0), ko((size_t)n + 1, 0);
-    if (n) {
-        if ((rc = upload_batch(c, seqs, offs, 0, n))) return rc;
-        if ((rc = run_scan(c, c->d_seqs.as<uint8_t>(), c->d_offs.as<uint64_t>(), n, c->p.l + c->p.k - 1, nullptr, nullptr, &M))) return rc;
-        CK(cudaMemcpyAsync(so.data(), c->d_seq_off.p, ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
+    try {
+        uint64_t M = 0, Q = 0;
+        std::vector<uint32_t> so((size_t)n + 1, 0), ko((size_t)n + 1, 0);
+        if (n) {
+            SeqInput in; in.seqs = seqs; BatchDev bd;
+            if ((rc = scan_batch_sync(c, in, offs, n, c->p.l + c->p.k - 1, bd, &M, &so))) return rc;
+            for (uint32_t i = 0; i < n; i++) { uint32_t cnt = so[i + 1] - so[i]; ko[i + 1] = ko[i] + (cnt >= c->p.k ? cnt - c->p.k + 1 : 0); }
+            Q = ko[n];
+        }
+        if (n_total) *n_total = Q;
+        if (seq_off) for (uint32_t i = 0; i <= n; i++) seq_off[i] = ko[i];
+        if (start && end && offrev && hash && Q) {
+            if (cap < Q) { c->err = "output capacity too small"; return MQ_ERR_ARG; }
+            if ((rc = ensure(c, c->d_misc, ((size_t)n + 2) * 4 + (Q + 16) * (4 * 3 + 8) + 64))) return rc;
+            uint64_t *t_hash = c->d_misc.as<uint64_t>();
+            uint32_t *t_start = (uint32_t *)(t_hash + Q + 1), *t_end = t_start + Q + 1, *t_off = t_end + Q + 1, *d_ko = t_off + Q + 1;
+            CK(cudaMemcpyAsync(d_ko, ko.data(), ((size_t)n + 1) * 4, cudaMemcpyHostToDevice, c->stream));
+            KminmerArgs a{};
+            a.pos = c->d_pos.as<uint32_t>(); a.hash = c->d_hash.as<uint64_t>(); a.n_min = (uint32_t)M;
+            a.rec_off = c->d_seq_off.as<uint32_t>(); a.rec_id = nullptr; a.n_rec = n; a.km_off = d_ko; a.k = c->p.k; a.l = c->p.l;
+            a.t_start = t_start; a.t_end = t_end; a.t_offrev = t_off; a.t_hash = t_hash;
+            Table t{nullptr, 0};
+            k_insert_kminmers<<<(uint32_t)((M + 255) / 256), 256, 0, c->stream>>>(a, t, 0);
+            c->launches++;
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(start, t_start, Q * 4, cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaMemcpyAsync(end, t_end, Q * 4, cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaMemcpyAsync(offrev, t_off, Q * 4, cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaMemcpyAsync(hash, t_hash, Q * 8, cudaMemcpyDeviceToHost, c->stream));
+        }
         CK(cudaStreamSynchronize(c->stream));
-        for (uint32_t i = 0; i < n; i++) { uint32_t cnt = so[i + 1] - so[i]; ko[i + 1] = ko[i] + (cnt >= c->p.k ? cnt - c->p.k + 1 : 0); }
-        Q = ko[n];
-    }
-    if (n_total) *n_total = Q;
-    if (seq_off) for (uint32_t i = 0; i <= n; i++) seq_off[i] = ko[i];
-    if (start && end && offrev && hash && Q) {
-        if (cap < Q) { c->err = "output capacity too small"; return MQ_ERR_ARG; }
-        if ((rc = ensure(c, c->d_misc, ((size_t)n + 2) * 4 + (Q + 16) * (4 * 3 + 8) + 64))) return rc;
-        uint64_t *t_hash = c->d_misc.as<uint64_t>();
-        uint32_t *t_start = (uint32_t *)(t_hash + Q + 1), *t_end = t_start + Q + 1, *t_off = t_end + Q + 1, *d_ko = t_off + Q + 1;
-        CK(cudaMemcpyAsync(d_ko, ko.data(), ((size_t)n + 1) * 4, cudaMemcpyHostToDevice, c->stream));
-        KminmerArgs a{};
-        a.pos = c->d_pos.as<uint32_t>(); a.hash = c->d_hash.as<uint64_t>(); a.n_min = (uint32_t)M;
-        a.rec_off = c->d_seq_off.as<uint32_t>(); a.rec_id = nullptr; a.n_rec = n; a.km_off = d_ko; a.k = c->p.k; a.l = c->p.l;
-        a.t_start = t_start; a.t_end = t_end; a.t_offrev = t_off; a.t_hash = t_hash;
-        Table t{nullptr, 0};
-        k_insert_kminmers<<<(uint32_t)((M + 255) / 256), 256, 0, c->stream>>>(a, t, 0);
-        c->launches++;
-        CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(start, t_start, Q * 4, cudaMemcpyDeviceToHost, c->stream));
-        CK(cudaMemcpyAsync(end, t_end, Q * 4, cudaMemcpyDeviceToHost, c->stream));
-        CK(cudaMemcpyAsync(offrev, t_off, Q * 4, cudaMemcpyDeviceToHost, c->stream));
-        CK(cudaMemcpyAsync(hash, t_hash, Q * 8, cudaMemcpyDeviceToHost, c->stream));
-    }
-    CK(cudaStreamSynchronize(c->stream));
-    timers_collect(c);
-    return MQ_OK;
+        timers_collect(c);
+        return MQ_OK;
+    } catch (...) { c->err = "host allocation failed"; return MQ_ERR_NOMEM; }
 }
 
 int mq_index_get(mq_ctx *c, const uint64_t *hashes, uint64_t n, uint8_t *found, uint32_t *id, uint32_t *start, uint32_t *end,
                  uint32_t *offset, uint8_t *rc_out) {
     if (!c || (n && (!hashes || !found || !id || !start || !end || !offset || !rc_out))) return MQ_ERR_ARG;
+    c = FIRST(c);
     if (!c->frozen) return MQ_ERR_STATE;
     cudaSetDevice(c->device);
     if (n == 0) return MQ_OK;
@@ -1013,7 +1527,7 @@ int mq_index_get(mq_ctx *c, const uint64_t *hashes, uint64_t n, uint8_t *found, 
 
 int mq_matches(mq_ctx *c, const uint8_t *seqs, const uint64_t *offs, uint32_t n, uint64_t *match_off, uint32_t *fields6,
                uint64_t cap, uint64_t *n_total) {
-    if (!c || !offs || (!seqs && n)) return MQ_ERR_ARG;
+    if (!c || !c->kids.empty() || !offs || (!seqs && n)) return MQ_ERR_ARG;
     if (!c->frozen) return MQ_ERR_STATE;
     cudaSetDevice(c->device);
     timers_reset(c);
@@ -1021,34 +1535,38 @@ int mq_matches(mq_ctx *c, const uint8_t *seqs, const uint64_t *offs, uint32_t n,
     if ((rc = check_offs(c, offs, n))) return rc;
     if (n_total) *n_total = 0;
     if (n == 0) { if (match_off) match_off[0] = 0; return MQ_OK; }
-    if ((rc = upload_batch(c, seqs, offs, 0, n))) return rc;
-    if ((rc = ensure(c, c->d_hits, (size_t)n * sizeof(HitRec)))) return rc;
-    if ((rc = map_device(c, c->d_seqs.as<uint8_t>(), c->d_offs.as<uint64_t>(), n, c->d_hits.as<HitRec>()))) return rc;
-    std::vector<uint32_t> so((size_t)n + 1), nm(n);
-    CK(cudaMemcpyAsync(so.data(), c->d_seq_off.p, ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(nm.data(), c->d_nmatch.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    uint64_t tot = 0;
-    for (uint32_t i = 0; i < n; i++) { if (match_off) match_off[i] = tot; tot += nm[i]; }
-    if (match_off) match_off[n] = tot;
-    if (n_total) *n_total = tot;
-    if (fields6 && tot) {
-        if (cap < tot) { c->err = "output capacity too small"; return MQ_ERR_ARG; }
-        // only the first nm[i] records of a read's region are written by the kernel: copy exactly those
-        std::vector<MatchRec> all(so[n]);
-        for (uint32_t i = 0; i < n; i++)
-            if (nm[i]) CK(cudaMemcpyAsync(all.data() + so[i], c->d_matches.as<MatchRec>() + so[i], (size_t)nm[i] * sizeof(MatchRec),
-                                          cudaMemcpyDeviceToHost, c->stream));
+    try {
+        SeqInput in; in.seqs = seqs; BatchDev bd; uint64_t M = 0; std::vector<uint32_t> so;
+        if ((rc = scan_batch_sync(c, in, offs, n, c->p.l + c->p.k - 1, bd, &M, &so))) return rc;
+        if ((rc = ensure_workspace(c, n, bd.n_tiles, bd.bases, true))) return rc;
+        if ((rc = ensure(c, c->slot[0].d_hits, (size_t)n * sizeof(HitRec)))) return rc;
+        CK(cudaMemsetAsync(c->d_nmatch.p, 0, ((size_t)n + 1) * 4, c->stream));
+        if ((rc = enqueue_probe_chain(c, bd, c->slot[0].d_hits.as<HitRec>()))) return rc;
+        std::vector<uint32_t> nm(n);
+        CK(cudaMemcpyAsync(nm.data(), c->d_nmatch.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
-        uint64_t w = 0;
-        for (uint32_t i = 0; i < n; i++) for (uint32_t j = 0; j < nm[i]; j++, w++) {
-            const MatchRec &m = all[so[i] + j];
-            uint32_t *f = fields6 + 6 * w;
-            f[0] = m.q_start; f[1] = m.q_end; f[2] = m.r_start; f[3] = m.r_end; f[4] = m.last_j - m.head_j + 1; f[5] = m.ref_rc;
+        uint64_t tot = 0;
+        for (uint32_t i = 0; i < n; i++) { if (match_off) match_off[i] = tot; tot += nm[i]; }
+        if (match_off) match_off[n] = tot;
+        if (n_total) *n_total = tot;
+        if (fields6 && tot) {
+            if (cap < tot) { c->err = "output capacity too small"; return MQ_ERR_ARG; }
+            // only the first nm[i] records of a read's region are written by the kernel: copy exactly those
+            std::vector<MatchRec> all(so[n]);
+            for (uint32_t i = 0; i < n; i++)
+                if (nm[i]) CK(cudaMemcpyAsync(all.data() + so[i], c->d_matches.as<MatchRec>() + so[i], (size_t)nm[i] * sizeof(MatchRec),
+                                              cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+            uint64_t w = 0;
+            for (uint32_t i = 0; i < n; i++) for (uint32_t j = 0; j < nm[i]; j++, w++) {
+                const MatchRec &m = all[so[i] + j];
+                uint32_t *f = fields6 + 6 * w;
+                f[0] = m.q_start; f[1] = m.q_end; f[2] = m.r_start; f[3] = m.r_end; f[4] = m.last_j - m.head_j + 1; f[5] = m.ref_rc;
+            }
         }
-    }
-    timers_collect(c);
-    return MQ_OK;
+        timers_collect(c);
+        return MQ_OK;
+    } catch (...) { c->err = "host allocation failed"; return MQ_ERR_NOMEM; }
 }
 
 }  // extern "C"

@@ -67,13 +67,18 @@ uint64_t mutate_copy(const uint8_t *src, uint64_t n, uint8_t *dst, uint64_t cap,
 
 extern "C" {
 
-// Uniform random ACGT.
+// Uniform random ACGT.  Blocks of 1 Mbase own a generator each, so the result does not depend on the thread count.
 void mqsim_random_bases(uint64_t seed, uint64_t stream, uint8_t *out, uint64_t n) {
-    Rng r(seed, stream);
-    uint64_t i = 0;
-    while (i < n) {
-        uint64_t x = r.next();
-        for (int j = 0; j < 32 && i < n; j++, x >>= 2) out[i++] = (uint8_t)BASES[x & 3];
+    const uint64_t BLK = 1u << 20;
+    const int64_t nb = (int64_t)((n + BLK - 1) / BLK);
+    #pragma omp parallel for schedule(dynamic, 4)
+    for (int64_t b = 0; b < nb; b++) {
+        Rng r(seed, (stream << 24) + (uint64_t)b + 1);
+        uint64_t i = (uint64_t)b * BLK; const uint64_t end = std::min(n, i + BLK);
+        while (i < end) {
+            uint64_t x = r.next();
+            for (int j = 0; j < 32 && i < end; j++, x >>= 2) out[i++] = (uint8_t)BASES[x & 3];
+        }
     }
 }
 
@@ -163,12 +168,28 @@ struct mqsim_read_cfg {
     double error_rate;   // total, split 1:1:1 substitution / insertion / deletion
 };
 
+// Errors are placed by drawing the error-free stretch before each one from a geometric distribution (one draw per
+// error instead of one per base); both passes replay the same stream.
+static inline uint64_t clean_stretch(Rng &e, double inv_log1mp) {
+    double u = e.uni();
+    if (u < 1e-300) u = 1e-300;
+    const double g = std::floor(std::log(u) * inv_log1mp);
+    return g > 4.0e18 ? (uint64_t)4e18 : (uint64_t)g;
+}
+static inline void copy_template(uint8_t *dst, const uint8_t *src, uint64_t len, uint64_t j, uint64_t n, bool rc) {
+    if (!rc) { memcpy(dst, src + j, n); return; }
+    static const struct CT { uint8_t t[256]; CT() { for (int i = 0; i < 256; i++) t[i] = comp((uint8_t)i); } } ct;
+    const uint8_t *p = src + (len - 1 - j);            // template base j on the reverse strand
+    for (uint64_t i = 0; i < n; i++) dst[i] = ct.t[p[-(int64_t)i]];
+}
+
 // Pass 1: choose template (contig, start, len, strand) for reads [first, first+n) and compute the
 // length of every simulated read.  contig_offs has n_contigs+1 entries into `genome`.
 void mqsim_reads_plan(const mqsim_read_cfg *cfg, const uint64_t *contig_offs, uint32_t n_contigs,
                       uint64_t first, uint64_t n, uint32_t *t_contig, uint64_t *t_start, uint64_t *t_len,
                       uint8_t *t_strand, uint64_t *out_len) {
     const uint64_t total = contig_offs[n_contigs];
+    const double p = cfg->error_rate, ilog = p > 0 && p < 1 ? 1.0 / std::log(1.0 - p) : 0.0;
     #pragma omp parallel for schedule(static)
     for (int64_t ii = 0; ii < (int64_t)n; ii++) {
         uint64_t i = first + (uint64_t)ii;
@@ -187,14 +208,16 @@ void mqsim_reads_plan(const mqsim_read_cfg *cfg, const uint64_t *contig_offs, ui
         uint8_t strand = (uint8_t)(r.next() & 1);
         t_contig[ii] = c; t_start[ii] = start; t_len[ii] = len; t_strand[ii] = strand;
         Rng e(cfg->seed, i * 2 + 2);   // error stream: replayed identically in pass 2
-        uint64_t w = 0; const double p = cfg->error_rate;
-        for (uint64_t j = 0; j < len; j++) {
-            if (p > 0 && e.uni() < p) {
-                uint64_t t = e.below(3);
-                if (t == 0) { e.below(4); e.below(4); e.below(4); w++; }   // substitution draws (bounded replay)
-                else if (t == 1) { e.below(4); w += 2; }                    // insertion
-                /* t == 2: deletion */
-            } else w++;
+        uint64_t w = 0, j = 0;
+        while (j < len) {
+            const uint64_t run = p > 0 ? std::min(len - j, clean_stretch(e, ilog)) : len - j;
+            w += run; j += run;
+            if (j >= len) break;
+            const uint64_t t = e.below(3);
+            if (t == 0) { e.below(4); e.below(4); e.below(4); w++; }   // substitution draws (bounded replay)
+            else if (t == 1) { e.below(4); w += 2; }                    // insertion
+            /* t == 2: deletion */
+            j++;
         }
         out_len[ii] = w;
     }
@@ -204,27 +227,32 @@ void mqsim_reads_plan(const mqsim_read_cfg *cfg, const uint64_t *contig_offs, ui
 void mqsim_reads_fill(const mqsim_read_cfg *cfg, const uint8_t *genome, const uint64_t *contig_offs,
                       uint64_t first, uint64_t n, const uint32_t *t_contig, const uint64_t *t_start,
                       const uint64_t *t_len, const uint8_t *t_strand, const uint64_t *out_offs, uint8_t *out) {
+    const double p = cfg->error_rate, ilog = p > 0 && p < 1 ? 1.0 / std::log(1.0 - p) : 0.0;
     #pragma omp parallel for schedule(static)
     for (int64_t ii = 0; ii < (int64_t)n; ii++) {
         uint64_t i = first + (uint64_t)ii;
         const uint8_t *src = genome + contig_offs[t_contig[ii]] + t_start[ii];
         const uint64_t len = t_len[ii];
+        const bool rc = t_strand[ii] != 0;
         uint8_t *dst = out + out_offs[ii];
         Rng e(cfg->seed, i * 2 + 2);
-        uint64_t w = 0; const double p = cfg->error_rate;
-        for (uint64_t j = 0; j < len; j++) {
-            uint8_t b = t_strand[ii] ? comp(src[len - 1 - j]) : src[j];
-            if (p > 0 && e.uni() < p) {
-                uint64_t t = e.below(3);
-                if (t == 0) {   // substitution: three fixed draws pick a base != b
-                    uint64_t d0 = e.below(4), d1 = e.below(4), d2 = e.below(4);
-                    uint8_t nb = (uint8_t)BASES[d0];
-                    if (nb == b) nb = (uint8_t)BASES[d1];
-                    if (nb == b) nb = (uint8_t)BASES[d2];
-                    if (nb == b) nb = (uint8_t)BASES[(d2 + 1) & 3];
-                    dst[w++] = nb;
-                } else if (t == 1) { dst[w++] = (uint8_t)BASES[e.below(4)]; dst[w++] = b; }
-            } else dst[w++] = b;
+        uint64_t w = 0, j = 0;
+        while (j < len) {
+            const uint64_t run = p > 0 ? std::min(len - j, clean_stretch(e, ilog)) : len - j;
+            copy_template(dst + w, src, len, j, run, rc);
+            w += run; j += run;
+            if (j >= len) break;
+            const uint8_t b = rc ? comp(src[len - 1 - j]) : src[j];
+            const uint64_t t = e.below(3);
+            if (t == 0) {   // substitution: three fixed draws pick a base != b
+                uint64_t d0 = e.below(4), d1 = e.below(4), d2 = e.below(4);
+                uint8_t nb = (uint8_t)BASES[d0];
+                if (nb == b) nb = (uint8_t)BASES[d1];
+                if (nb == b) nb = (uint8_t)BASES[d2];
+                if (nb == b) nb = (uint8_t)BASES[(d2 + 1) & 3];
+                dst[w++] = nb;
+            } else if (t == 1) { dst[w++] = (uint8_t)BASES[e.below(4)]; dst[w++] = b; }
+            j++;
         }
     }
 }

@@ -18,7 +18,7 @@ import ctypes as C
 import numpy as np
 
 from . import capi
-from .capi import HIT_DTYPE, MqError, Params as _CParams
+from .capi import EXC_DTYPE, HIT_DTYPE, MqError, Packed as _CPacked, Params as _CParams
 
 
 class Params:
@@ -52,13 +52,78 @@ def concat(seqs):
     return np.ascontiguousarray(buf), offs
 
 
+class PackedSeqs:
+    """A sequence array in the packed input format (mq_pack): 2-bit codes + block bitmap + exception intervals.
+    `pinned=True` keeps the three arrays in pinned host memory (mq_host_alloc) for full-speed uploads."""
+
+    def __init__(self, ascii_u8, n_threads=0, fold_case=False, pinned=False):
+        L = capi.lib()
+        a = np.ascontiguousarray(ascii_u8, dtype=np.uint8)
+        self.n_bases = int(a.size)
+        nw, nf = int(L.mq_packed_words(a.size)), int(L.mq_packed_flag_words(a.size))
+        self._pinned = []
+        self._L = L
+        self.words = self._alloc(L, nw, np.uint32, pinned); self.flags = self._alloc(L, nf, np.uint32, pinned)
+        cap = 1024
+        while True:
+            exc = np.zeros(cap, EXC_DTYPE); n = C.c_uint64()
+            rc = L.mq_pack(a.ctypes.data, a.size, self.words.ctypes.data, self.flags.ctypes.data, exc.ctypes.data, cap, C.byref(n),
+                           n_threads, 1 if fold_case else 0)
+            if rc == 0:
+                break
+            if rc == -5 and n.value > cap:
+                cap = int(n.value) + 16
+                continue
+            raise MqError(f"mq_pack: {L.mq_strerror(rc).decode()}")
+        self.exc = exc[:n.value].copy()
+        if pinned and self.exc.size:
+            e = self._alloc(L, self.exc.size, EXC_DTYPE, True); e[:] = self.exc; self.exc = e
+
+    def _alloc(self, L, n, dtype, pinned):
+        nbytes = max(int(n) * np.dtype(dtype).itemsize, 16)
+        if not pinned:
+            return np.zeros(n, dtype)
+        ptr = L.mq_host_alloc(nbytes)
+        if not ptr:
+            raise MqError("mq_host_alloc failed")
+        self._pinned.append(ptr)
+        return np.frombuffer((C.c_uint8 * nbytes).from_address(ptr), dtype=np.uint8, count=int(n) * np.dtype(dtype).itemsize).view(dtype)
+
+    def c_struct(self):
+        return _CPacked(self.words.ctypes.data, self.flags.ctypes.data, self.exc.ctypes.data if self.exc.size else None,
+                        self.exc.size, self.n_bases)
+
+    @property
+    def nbytes(self):
+        return int(self.words.nbytes + self.flags.nbytes + self.exc.nbytes)
+
+    def unpack(self, first=0, n=None):
+        n = self.n_bases - first if n is None else n
+        out = np.zeros(n, np.uint8)
+        rc = self._L.mq_unpack(self.words.ctypes.data, self.exc.ctypes.data if self.exc.size else None, self.exc.size, first, n,
+                               out.ctypes.data)
+        if rc:
+            raise MqError("mq_unpack")
+        return out
+
+    def close(self):
+        for p in self._pinned:
+            self._L.mq_host_free(p)
+        self._pinned = []
+
+
 class Index:
-    def __init__(self, params=None, device=0):
+    def __init__(self, params=None, device=0, devices=None):
+        """device: one GPU (mq_create); devices=[...]: one context over several GPUs of this process (mq_create_multi)"""
         self.params = params or Params()
         self._L = capi.lib()
         self._h = C.c_void_p()
         cp = self.params.c_struct()
-        rc = self._L.mq_create(C.byref(self._h), C.byref(cp), device)
+        if devices is not None:
+            arr = (C.c_int * len(devices))(*devices)
+            rc = self._L.mq_create_multi(C.byref(self._h), C.byref(cp), arr, len(devices))
+        else:
+            rc = self._L.mq_create(C.byref(self._h), C.byref(cp), device)
         if rc != 0:
             self._h = None
             raise MqError(f"mq_create: {self._L.mq_strerror(rc).decode()}")
@@ -94,6 +159,18 @@ class Index:
         first = len(self.ref_map) if first_ref_idx is None else first_ref_idx
         nb = np.zeros(n, np.uint64)
         self._ck(self._L.mq_index_add(self._h, seqs.ctypes.data, offs.ctypes.data, n, first, nb.ctypes.data), "mq_index_add")
+        for i in range(n):
+            self.ref_map[first + i] = (names[i], int(offs[i + 1] - offs[i]))
+        return nb
+
+    def add_batch_packed(self, names, packed, offs, first_ref_idx=None):
+        """≙ ref_extract on packed sequences (PackedSeqs)"""
+        offs = np.ascontiguousarray(offs, dtype=np.uint64)
+        n = offs.size - 1
+        first = len(self.ref_map) if first_ref_idx is None else first_ref_idx
+        nb = np.zeros(n, np.uint64)
+        cs = packed.c_struct()
+        self._ck(self._L.mq_index_add_packed(self._h, C.byref(cs), offs.ctypes.data, n, first, nb.ctypes.data), "mq_index_add_packed")
         for i in range(n):
             self.ref_map[first + i] = (names[i], int(offs[i + 1] - offs[i]))
         return nb
@@ -180,8 +257,24 @@ class Index:
         self._ck(self._L.mq_map_batch(self._h, seqs.ctypes.data, offs.ctypes.data, n, hits.ctypes.data), "mq_map_batch")
         return hits
 
-    def map_batch_device(self, d_seqs, d_offs, n, total_bytes, d_hits):
-        self._ck(self._L.mq_map_batch_device(self._h, d_seqs, d_offs, n, total_bytes, d_hits), "mq_map_batch_device")
+    def map_batch_packed(self, packed, offs, out=None):
+        offs = np.ascontiguousarray(offs, dtype=np.uint64)
+        n = offs.size - 1
+        hits = out if out is not None else np.zeros(n, HIT_DTYPE)
+        cs = packed.c_struct()
+        self._ck(self._L.mq_map_batch_packed(self._h, C.byref(cs), offs.ctypes.data, n, hits.ctypes.data), "mq_map_batch_packed")
+        return hits
+
+    def map_batch_device(self, d_seqs, offs, d_hits):
+        """sequences and hits resident on the device; offs is a HOST uint64 array"""
+        offs = np.ascontiguousarray(offs, dtype=np.uint64)
+        self._ck(self._L.mq_map_batch_device(self._h, d_seqs, offs.ctypes.data, offs.size - 1, d_hits), "mq_map_batch_device")
+
+    def map_batch_packed_device(self, d_words, d_flags, d_exc, n_exc, n_bases, offs, d_hits):
+        offs = np.ascontiguousarray(offs, dtype=np.uint64)
+        cs = _CPacked(d_words, d_flags, d_exc, n_exc, n_bases)
+        self._ck(self._L.mq_map_batch_packed_device(self._h, C.byref(cs), offs.ctypes.data, offs.size - 1, d_hits),
+                 "mq_map_batch_packed_device")
 
     def paf_line(self, q_id, q_len, hit):
         if not hit["mapped"]:
@@ -209,6 +302,16 @@ class Index:
         pos = np.zeros(tot.value, np.uint32); hs = np.zeros(tot.value, np.uint64)
         self._ck(self._L.mq_minimizers(self._h, seqs.ctypes.data, offs.ctypes.data, n, so.ctypes.data, pos.ctypes.data,
                                        hs.ctypes.data, tot.value, C.byref(tot)), "mq_minimizers")
+        return so, pos, hs
+
+    def minimizers_packed(self, packed, offs):
+        offs = np.ascontiguousarray(offs, dtype=np.uint64)
+        n = offs.size - 1; tot = C.c_uint64(); so = np.zeros(n + 1, np.uint64); cs = packed.c_struct()
+        self._ck(self._L.mq_minimizers_packed(self._h, C.byref(cs), offs.ctypes.data, n, so.ctypes.data, None, None, 0,
+                                              C.byref(tot)), "mq_minimizers_packed")
+        pos = np.zeros(tot.value, np.uint32); hs = np.zeros(tot.value, np.uint64)
+        self._ck(self._L.mq_minimizers_packed(self._h, C.byref(cs), offs.ctypes.data, n, so.ctypes.data, pos.ctypes.data,
+                                              hs.ctypes.data, tot.value, C.byref(tot)), "mq_minimizers_packed")
         return so, pos, hs
 
     def kminmers(self, seqs, offs):

@@ -69,7 +69,10 @@ def test_bad_params_rejected_before_any_device_work():
     for k, l in ((5, 1), (5, 33), (0, 31), (33, 31)):
         p = capi.Params(k, l, 0.01, 1, 4, 11, 2000)
         assert L.mq_create(C.byref(h), C.byref(p), 0) == -1
-    assert L.mq_abi_version() == 1
+    assert L.mq_abi_version() == 2
+    d = (C.c_int * 2)(0, 1)
+    assert L.mq_create_multi(C.byref(h), C.byref(capi.Params(5, 33, 0.01, 1, 4, 11, 2000)), d, 2) == -1
+    assert L.mq_create_multi(C.byref(h), C.byref(capi.Params(5, 31, 0.01, 1, 4, 11, 2000)), d, 0) == -1
 
 
 def test_upper_casing_mirror():

@@ -22,31 +22,52 @@ def run_bench(*args, env=None):
 
 
 def test_reference_arm_line():
-    d = run_bench("--impl", "reference", "--steps", "1", "--warmup", "1", env={"OMP_NUM_THREADS": "1"})
+    d = run_bench("--impl", "reference", "--config", "2", "--reads", "25000", "--steps", "1", "--warmup", "1")
     assert COMMON <= set(d) and d["impl"] == "reference"
     assert d["unit"] == "reads/s" and d["higher_is_better"] is True and d["vs_baseline"] is None and d["dtype"] == "u64"
     assert "workload" in d["config"] and "model" not in d["config"]
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert d["value"] > 0 and d["mapped_reads"] == 25000
+    assert d["value"] > 0 and d["mapped_reads"] == 25000 and d["config"]["reads_per_step"] == 25000
+    assert d["upstream"]["found"] in (True, False)
 
 
 def test_reference_arm_other_ranks_stay_silent():
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"], capture_output=True,
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", "2", "--gpus", "2"], capture_output=True,
                        text=True, cwd=ROOT, env={**os.environ, "RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
     assert r.returncode == 0 and r.stdout.strip() == ""
 
 
-@pytest.mark.gpu
-def test_gpu_arm_line():
-    d = run_bench("--steps", "3", "--warmup", "3", "--reads", "20000")
-    assert COMMON | {"roofline", "gpu_launches", "clocks"} <= set(d) and "impl" not in d
-    assert d["n_gpus"] == 1 and d["scaling"] == "weak" and d["data"] == "synthetic"
+GPU_KEYS = {"roofline", "gpu_launches", "clocks", "parity", "e2e_prepacked", "e2e_packed", "value_ascii", "index_build"}
+
+
+def check_gpu_line(d, n_reads):
+    assert COMMON | GPU_KEYS <= set(d) and "impl" not in d
+    assert d["n_gpus"] == 1 and d["data"] == "synthetic"
     rf = d["roofline"]
     assert rf["bound"] == "hbm" and rf["unit"] == "GB/s" and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9
-    assert d["gpu_launches"] > 0 and d["e2e"]["h2d_bytes_per_step"] > 20000 * 1000 and d["e2e"]["d2h_bytes_per_step"] == 20000 * 48
+    assert d["gpu_launches"] > 0 and d["e2e"]["h2d_bytes_per_step"] > n_reads * 1000 and d["e2e"]["d2h_bytes_per_step"] == n_reads * 48
     assert d["e2e"]["value"] < d["value"]                       # the PCIe copies are inside the e2e region
+    assert d["e2e_prepacked"]["h2d_bytes_per_base"] < 0.27      # 2 bits per base + offsets + bitmap
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    par = d["parity"]
+    assert par["paths_identical"] is True and par["hits_identical"] is True and par["index_identical"] is True
+
+
+@pytest.mark.gpu
+def test_gpu_arm_line_config2():
+    d = run_bench("--config", "2", "--steps", "3", "--warmup", "3", "--reads", "20000", "--check", "5000")
+    check_gpu_line(d, 20000)
+    assert d["scaling"] == "weak" and d["parity"]["checked_reads"] == 5000
+
+
+@pytest.mark.gpu
+def test_gpu_arm_line_default_config3_subsample():
+    # the default workload (BASELINE configs[2]: 3.1 Gbp genome) with a subsample of its reads, parity checked in the run
+    d = run_bench("--steps", "3", "--warmup", "3", "--reads", "30000", "--check", "3000")
+    check_gpu_line(d, 30000)
+    assert d["scaling"] == "strong" and "configs[2]" in d["config"]["workload"] and d["n_unique_kminmers"] > 40000000
+    assert d["mapped_fraction"] > 0.97 and d["wrong_q60"] <= 3
 
 
 def test_committed_round_lines_keep_the_contract():

@@ -4,7 +4,7 @@ import pytest
 
 from conftest import random_dna, revcomp
 from oracle import pyoracle as O
-from mapquik_b200 import Index, Params, concat, sim
+from mapquik_b200 import Index, PackedSeqs, Params, concat, sim
 
 pytestmark = pytest.mark.gpu
 
@@ -22,17 +22,20 @@ def oracle_minimizers(seqs, offs, p):
         np.concatenate(hs) if hs else np.zeros(0, np.uint64)
 
 
-@pytest.fixture(params=["v3", "v2", "v1"])
-def scan_version(request, monkeypatch):
-    """all generations of the S1 kernel stay under test (MQ_SCAN_V1 / MQ_SCAN_V2 are read at mq_create)"""
-    monkeypatch.setenv("MQ_SCAN_V1", "1" if request.param == "v1" else "0")
-    monkeypatch.setenv("MQ_SCAN_V2", "1" if request.param == "v2" else "0")
+@pytest.fixture(params=["ascii", "packed"])
+def fmt(request):
+    """both input formats of the S1 kernel: upper-cased ASCII and 2-bit packed codes (+ exception intervals)"""
     return request.param
 
 
-def check_minimizers(seqs, offs, p):
+def check_minimizers(seqs, offs, p, fmt="ascii"):
     ix = Index(p)
-    so, pos, hs = ix.minimizers(seqs, offs)
+    if fmt == "packed":
+        pk = PackedSeqs(seqs)
+        assert np.array_equal(pk.unpack(), seqs)
+        so, pos, hs = ix.minimizers_packed(pk, offs)
+    else:
+        so, pos, hs = ix.minimizers(seqs, offs)
     eso, epos, ehs = oracle_minimizers(seqs, offs, p)
     assert np.array_equal(so, eso), (so[:10], eso[:10])
     assert np.array_equal(pos.astype(np.uint64), epos)
@@ -77,10 +80,10 @@ def adversarial_seqs(rng):
                                            # full 128-symbol lane streams with the longest window: the least spare rows
                                            # for parked candidates (v3), first sparse, then every l-mer selected
                                            (32, 0.05, False), (32, 1.0, False)])
-def test_minimizers_adversarial(l, density, hpc, scan_version):
+def test_minimizers_adversarial(l, density, hpc, fmt):
     rng = np.random.default_rng(7)
     buf, offs = concat_raw(adversarial_seqs(rng))
-    check_minimizers(buf, offs, Params(k=5, l=l, density=density, use_hpc=hpc))
+    check_minimizers(buf, offs, Params(k=5, l=l, density=density, use_hpc=hpc), fmt)
 
 
 def concat_raw(seqs):
@@ -88,23 +91,26 @@ def concat_raw(seqs):
     return (np.concatenate(seqs) if seqs else np.zeros(0, np.uint8)), offs
 
 
-def test_minimizers_reads_and_genome(scan_version):
+def test_minimizers_reads_and_genome(fmt):
     g, go, _ = sim.genome(11, [1500000, 700001, 123457])
-    n = check_minimizers(g, go, Params())
+    n = check_minimizers(g, go, Params(), fmt)
     assert n > 20000
     rb, ro, _, _ = sim.reads(11, g, go, 500, 10000, 3000)
-    check_minimizers(rb, ro, Params())
-    check_minimizers(rb, ro, Params(l=16, k=8))
+    check_minimizers(rb, ro, Params(), fmt)
+    check_minimizers(rb, ro, Params(l=16, k=8), fmt)
 
 
-def test_minimizers_dense_overflow_pool(scan_version):
-    # density 1.0 selects every l-mer: every tile overflows its staged-event pool into the global pool
+def test_minimizers_dense_overflow_pool(fmt):
+    # density 1.0 selects every l-mer: every tile overflows its staged-event pool into the global pool, and the
+    # minimizer buffers sized for the expected density are too small (status record -> redo with larger buffers)
     rng = np.random.default_rng(3)
     buf, offs = concat_raw([random_dna(rng, 100000), random_dna(rng, 20000)])
-    check_minimizers(buf, offs, Params(l=7, density=1.0, use_hpc=False))
+    check_minimizers(buf, offs, Params(l=7, density=1.0, use_hpc=False), fmt)
+    big, boffs = concat_raw([random_dna(rng, 3000000)])
+    check_minimizers(big, boffs, Params(l=9, density=1.0, use_hpc=False), fmt)
 
 
-def test_giant_runs_stay_fast_and_exact():
+def test_giant_runs_stay_fast_and_exact(fmt):
     # a 6 Mbp N-gap and a 3 Mbp homopolymer inside one record: tiles inside a run must not walk to its end
     import time
     rng = np.random.default_rng(12)
@@ -112,7 +118,7 @@ def test_giant_runs_stay_fast_and_exact():
                         np.full(3000000, ord("A"), np.uint8), random_dna(rng, 100000)])
     buf, offs = concat_raw([x, random_dna(rng, 50000)])
     t0 = time.perf_counter()
-    check_minimizers(buf, offs, Params())
+    check_minimizers(buf, offs, Params(), fmt)
     assert time.perf_counter() - t0 < 60
 
 
@@ -304,7 +310,7 @@ def test_edge_reads():
     ix.close()
 
 
-def test_segment_partitioned_index_equals_whole(scan_version):
+def test_segment_partitioned_index_equals_whole():
     # multi-GPU style build: the reference is cut into base-range segments (with halo) and the result
     # must equal the single-shot index
     p = Params()
@@ -408,7 +414,7 @@ def _fuzz_record(rng, n):
 
 
 @pytest.mark.parametrize("seed", range(24))
-def test_minimizers_fuzz_tile_boundaries(seed, scan_version):
+def test_minimizers_fuzz_tile_boundaries(seed, fmt):
     # record lengths around every granularity of the tiling (16-byte groups, 128-byte lane chunks, 4,096 / 8,192-base
     # tiles), random start alignment (records are packed back to back), random l / density / HPC
     rng = np.random.default_rng(1000 + seed)
@@ -420,7 +426,7 @@ def test_minimizers_fuzz_tile_boundaries(seed, scan_version):
     buf, offs = concat_raw(seqs)
     l = int(rng.integers(2, 33))
     p = Params(k=int(rng.integers(1, 9)), l=l, density=float(rng.choice([0.005, 0.01, 0.05, 0.3, 1.0])), use_hpc=bool(rng.integers(0, 2)))
-    check_minimizers(buf, offs, p)
+    check_minimizers(buf, offs, p, fmt)
 
 
 @pytest.mark.parametrize("seed", range(8))
@@ -524,3 +530,149 @@ def test_segment_partition_tiny_and_odd_contigs():
     rb, ro, _, _ = sim.reads(77, buf, offs, 300, 3000, 1000, min_len=200)
     assert whole.map_batch(rb, ro).tobytes() == part.map_batch(rb, ro).tobytes()
     whole.close(); part.close()
+
+
+# ---- packed input: the same results as the ASCII path and the oracle, through every packed entry point ------------------
+def test_packed_index_and_hits_equal_ascii_and_oracle():
+    p = Params()
+    g, go, names = sim.genome(101, [900000, 400000, 30])
+    g = g.copy(); g[5000:5600] = ord("N"); g[700000] = ord("R")
+    ix, oix = build_both(p, names, g, go)
+    pg = PackedSeqs(g)
+    ixp = Index(p)
+    nbp = ixp.add_batch_packed(names, pg, go)
+    assert ixp.freeze() == ix.n_unique and ixp.n_keys == ix.n_keys
+    assert np.array_equal(nbp, ix.nb_mers())
+    rb, ro, rn, _ = sim.reads(101, g, go, 2500, 9000, 3000, contig_names=names)
+    rb = rb.copy(); rb[np.random.default_rng(1).integers(0, rb.size, 500)] = ord("N")
+    pr = PackedSeqs(rb, pinned=True)
+    hits = compare_hits(ix, oix, rb, ro, rn)
+    for index in (ix, ixp):
+        assert index.map_batch_packed(pr, ro).tobytes() == hits.tobytes()
+    assert ixp.map_batch(rb, ro).tobytes() == hits.tobytes()
+    pr.close(); ix.close(); ixp.close()
+
+
+def test_packed_split_invariance_many_sub_batches():
+    # more bases than one pipelined sub-batch (128 Mbases): slices that start off any 2048-base boundary, exception
+    # intervals cut by slice edges, results independent of how the batch is cut
+    p = Params()
+    g, go, names = sim.genome(102, [4000000])
+    ix = Index(p); ix.add_batch(names, g, go); ix.freeze()
+    rb, ro, _, _ = sim.reads(102, g, go, 16000, 10000, 2000)
+    rb = rb.copy()
+    rng = np.random.default_rng(2)
+    for s in rng.integers(0, rb.size - 3000, 300):
+        rb[s:s + int(rng.integers(1, 2500))] = ord("N")
+    assert rb.size > (128 << 20)
+    pr = PackedSeqs(rb)
+    whole = ix.map_batch_packed(pr, ro)
+    assert ix.map_batch(rb, ro).tobytes() == whole.tobytes()
+    lo, hi = 777, 9001
+    sub = PackedSeqs(rb[int(ro[lo]):int(ro[hi])])
+    assert ix.map_batch_packed(sub, ro[lo:hi + 1] - ro[lo]).tobytes() == whole[lo:hi].tobytes()
+    from oracle import pyoracle as O2
+    oix = O2.Index(oparams(p), 1 << 16); oix.add_batch(names, g, go)
+    assert oix.map_batch(rb[:int(ro[3000])], ro[:3001]).tobytes() == whole[:3000].tobytes()
+    ix.close()
+
+
+def test_device_resident_entry_points_equal_host_ones():
+    import ctypes as C
+    from mapquik_b200 import capi, HIT_DTYPE
+    L = capi.lib()
+    p = Params()
+    g, go, names = sim.genome(103, [1500000, 200000])
+    ix = Index(p); ix.add_batch(names, g, go); ix.freeze()
+    rb, ro, _, _ = sim.reads(103, g, go, 3000, 9000, 2500)
+    rb = rb.copy(); rb[100:140] = ord("N"); rb[-5] = ord("Y")
+    ref = ix.map_batch(rb, ro)
+    h = ix.handle; n = len(ro) - 1
+    d_hits = L.mq_dev_alloc(h, n * 48)
+    # ASCII resident
+    d_seqs = L.mq_dev_alloc(h, rb.size + 256)
+    L.mq_dev_memset(h, d_seqs, 0, rb.size + 256); assert L.mq_dev_upload(h, d_seqs, rb.ctypes.data, rb.size) == 0
+    ix.map_batch_device(d_seqs, ro, d_hits)
+    out = np.zeros(n, HIT_DTYPE); assert L.mq_dev_download(h, out.ctypes.data, d_hits, n * 48) == 0
+    assert out.tobytes() == ref.tobytes()
+    # packed resident
+    pr = PackedSeqs(rb)
+    d_w = L.mq_dev_alloc(h, pr.words.nbytes); d_f = L.mq_dev_alloc(h, pr.flags.nbytes); d_e = L.mq_dev_alloc(h, max(pr.exc.nbytes, 16))
+    assert L.mq_dev_upload(h, d_w, pr.words.ctypes.data, pr.words.nbytes) == 0
+    assert L.mq_dev_upload(h, d_f, pr.flags.ctypes.data, pr.flags.nbytes) == 0
+    assert L.mq_dev_upload(h, d_e, pr.exc.ctypes.data, pr.exc.nbytes) == 0
+    L.mq_dev_memset(h, d_hits, 0, n * 48)
+    ix.map_batch_packed_device(d_w, d_f, d_e, pr.exc.size, pr.n_bases, ro, d_hits)
+    assert L.mq_dev_download(h, out.ctypes.data, d_hits, n * 48) == 0
+    assert out.tobytes() == ref.tobytes()
+    for d in (d_hits, d_seqs, d_w, d_f, d_e):
+        L.mq_dev_free(h, d)
+    ix.close()
+
+
+# ---- one context over several GPUs (mq_create_multi) ---------------------------------------------------------------------
+def _device_ids(n):
+    import torch
+    have = torch.cuda.device_count()
+    return [i % have for i in range(n)]         # on a one-GPU box the same device serves twice: same code path, same answers
+
+
+@pytest.mark.parametrize("n_dev", [2, 3])
+def test_multi_gpu_context_equals_single(n_dev):
+    p = Params()
+    g, go, names = sim.genome(104, [1200000, 500000, 77, 20000])
+    g = g.copy(); g[300000:300800] = ord("A"); g[900000:900050] = ord("N")
+    one = Index(p); nb1 = one.add_batch(names, g, go); one.freeze()
+    multi = Index(p, devices=_device_ids(n_dev))
+    nbm = multi.add_batch(names, g, go)
+    assert multi.freeze() == one.n_unique and multi.n_keys == one.n_keys
+    assert np.array_equal(nb1, nbm) and np.array_equal(one.nb_mers(), multi.nb_mers())
+    rb, ro, _, _ = sim.reads(104, g, go, 5000, 9000, 3000)
+    h1 = one.map_batch(rb, ro)
+    assert multi.map_batch(rb, ro).tobytes() == h1.tobytes()
+    pr = PackedSeqs(rb)
+    assert multi.map_batch_packed(pr, ro).tobytes() == h1.tobytes()
+    # packed reference through the multi-GPU build as well
+    multi2 = Index(p, devices=_device_ids(n_dev))
+    multi2.add_batch_packed(names, PackedSeqs(g), go); multi2.freeze()
+    assert multi2.n_unique == one.n_unique and multi2.map_batch(rb, ro).tobytes() == h1.tobytes()
+    one.close(); multi.close(); multi2.close()
+
+
+# ---- BASELINE configs 2-5 at a scale the oracle finishes in seconds (the full sizes run in bench.py / scripts) -----------
+def _config3_like(scale, seed=3):
+    lens = [int(3.1e9 / scale * x / sum(sim.CHM13_PROPS)) for x in sim.CHM13_PROPS]
+    return sim.genome(seed, lens, sat_frac=0.06, segdup_frac=0.05)
+
+
+def test_config3_scaled_human_like_genome():
+    p = Params()
+    g, go, names = _config3_like(10)                        # 310 Mbp, 24 contigs, satellites + segmental duplications
+    ix, oix = build_both(p, names, g, go)
+    rb, ro, rn, tr = sim.reads(3, g, go, 20000, 24000, 3000, contig_names=names)
+    hits = compare_hits(ix, oix, rb, ro, rn)
+    assert ix.map_batch_packed(PackedSeqs(rb), ro).tobytes() == hits.tobytes()
+    ok = (hits["mapped"] == 1) & (hits["ref_idx"] == tr["contig"]) & (hits["rc"] == tr["strand"])
+    assert ok.mean() > 0.97 and ((hits["mapq"] == 60) & ~ok).sum() <= 2
+    ix.close()
+
+
+def test_config4_scaled_repeat_family_genome():
+    p = Params()
+    g, go, names = sim.genome(4, [22000000] * 10, repeat_frac=0.85, n_families=300)      # 220 Mbp, 85 % repeats
+    ix, oix = build_both(p, names, g, go)
+    assert ix.n_keys > 1.05 * ix.n_unique                    # many tombstones
+    rb, ro, rn, _ = sim.reads(4, g, go, 10000, 24000, 3000, contig_names=names)
+    hits = compare_hits(ix, oix, rb, ro, rn)
+    assert ix.map_batch_packed(PackedSeqs(rb), ro).tobytes() == hits.tobytes()
+    ix.close()
+
+
+@pytest.mark.parametrize("k,l,d", [(3, 25, 0.02), (7, 31, 0.005), (5, 28, 0.01)])
+def test_config5_grid_points(k, l, d):
+    p = Params(k=k, l=l, density=d)
+    g, go, names = _config3_like(40)                        # 77 Mbp
+    ix, oix = build_both(p, names, g, go)
+    rb, ro, rn, _ = sim.reads(5, g, go, 4000, 24000, 3000, contig_names=names)
+    compare_hits(ix, oix, rb, ro, rn)
+    ix.close()
