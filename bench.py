@@ -407,19 +407,19 @@ def main():
     scan_launches_ascii = L.mq_scan_kernel_launches(h) - sk0
     hits_b = np.zeros(n_reads, HIT_DTYPE)
     assert L.mq_dev_download(h, hits_b.ctypes.data, d_hits, n_reads * 48) == 0
-    paths_identical = hits_b.tobytes() == hits.tobytes()
+    path_diff = {"ascii_resident": int((hits_b != hits).sum())}
 
     # e2e: through the C ABI with pinned HOST ASCII buffers
     h_hits[:] = 0
     t_e2e = timed(lambda: ix.map_batch(h_seqs[:n_bases], h_offs, out=h_hits_v), args.steps, args.warmup, device_events=False)
     e2e_stage = {s: ix.last_ms(s) for s in ("h2d", "scan", "gather", "probe", "chain", "d2h")}
-    paths_identical &= h_hits_v.tobytes() == hits.tobytes()
+    path_diff["e2e_ascii"] = int((h_hits_v != hits).sum())
 
     # e2e_prepacked: pinned host buffers in the packed format
     h_hits[:] = 0
     t_e2e_pre = timed(lambda: ix.map_batch_packed(pk, h_offs, out=h_hits_v), args.steps, args.warmup, device_events=False)
     e2e_pre_stage = {s: ix.last_ms(s) for s in ("h2d", "scan", "gather", "probe", "chain", "d2h")}
-    paths_identical &= h_hits_v.tobytes() == hits.tobytes()
+    path_diff["e2e_prepacked"] = int((h_hits_v != hits).sum())
 
     # e2e_packed: ASCII in host memory -> mq_pack on this rank's host threads -> mq_map_batch_packed, chunk-pipelined
     t_e2e_pack = None; pack_gbs = None
@@ -461,7 +461,7 @@ def main():
         h_hits[:] = 0
         ps = min(args.steps, 5)
         t_e2e_pack = timed(step_pack_inside, ps, 1, device_events=False) * (args.steps / ps)
-        paths_identical &= h_hits_v.tobytes() == hits.tobytes()
+        path_diff["e2e_packed"] = int((h_hits_v != hits).sum())
         t0 = time.perf_counter(); pack_chunk(0, 0); pack_gbs = int(ro[cuts[1]] - ro[cuts[0]]) / (time.perf_counter() - t0) / 1e9
         for _, _, _, ptrs in bufs:
             for q in ptrs:
@@ -469,14 +469,20 @@ def main():
     clk = clocks.stop()
 
     # ---- parity against the CPU oracle (untimed) + CPU baseline -----------------------------------------------------
-    parity = {"paths_identical": bool(paths_identical)}
+    paths_identical = not any(path_diff.values())
+    parity = {"paths_identical": bool(paths_identical), "reads_differing_from_packed_resident": path_diff}
     cpu_line = None
     if rank == 0 and (args.check or not args.no_cpu_baseline):
         all_threads = host_threads() if world == 1 else threads
         oix, onb, o_unique, t_oindex = oracle_index(cfg, g, go, names, all_threads)
         nchk = min(args.check, n_reads)
         oh = oix.map_batch(rb[:int(ro[nchk])], ro[:nchk + 1], threads=all_threads)
-        parity.update(checked_reads=int(nchk), hits_identical=bool(oh.tobytes() == hits[:nchk].tobytes()),
+        bad = np.nonzero(oh != hits[:nchk])[0]
+        if bad.size:
+            print(f"[parity] {bad.size} of {nchk} reads differ from the oracle; first: read {bad[0]} len {int(ro[bad[0] + 1] - ro[bad[0]])} "
+                  f"gpu {hits[bad[0]]} oracle {oh[bad[0]]} ascii-resident {hits_b[bad[0]]}", file=sys.stderr)
+        parity.update(checked_reads=int(nchk), hits_identical=bool(oh.tobytes() == hits[:nchk].tobytes()), reads_differing_from_oracle=int(bad.size),
+                      ascii_resident_differing_from_oracle=int((oh != hits_b[:nchk]).sum()),
                       index_identical=bool(o_unique == n_unique and oix.slots() == ix.n_keys and np.array_equal(onb, ix.nb_mers())),
                       oracle_index_s=t_oindex)
         if world == 1 and not args.no_cpu_baseline:

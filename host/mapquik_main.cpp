@@ -2,11 +2,13 @@
 //
 // Mirrors the reference's command line, console lines and PAF output (src/main.rs:77-272,
 // src/closures.rs:22-211) for the seeding->chaining path:
-//     mapquik <reads.fa|fq[.gz]> --reference <ref.fa[.gz]> [-k K] [-l L] [-d D] [-c C] [-s S] [-g G]
+//     mapquik <reads.fa|fq[.gz|.lz4]> --reference <ref.fa[.gz|.lz4]> [-k K] [-l L] [-d D] [-c C] [-s S] [-g G]
 //             [-p PREFIX] [--nohpc] [--threads N] [-b B] [-q Q] [--low-memory] [--nosimd]
-//             [--parallelfastx] [--debug] [--gpu ID] [--save-index F] [--load-index F] [--rescue k,l,d]
-// Host I/O: one reader thread parses + upper-cases records straight into pinned batch buffers while the main
-// thread maps the previous batch on the GPU and writes its PAF lines in input order (closures.rs:117-123).
+//             [--parallelfastx] [--debug] [--gpu ID | --gpus N] [--ascii] [--save-index F] [--load-index F] [--rescue k,l,d]
+// Host I/O: one reader thread parses records straight into pinned batch buffers while the main thread maps the previous
+// batch on the GPU(s) and writes its PAF lines in input order (closures.rs:117-123).  Where the reference upper-cases a
+// copy of every record (closures.rs:63,106), the block-parallel parser PACKS it (mq_pack_at: 2-bit codes + exception
+// intervals, upper-casing folded in), so a quarter of the bytes cross PCIe; --ascii keeps one byte per base.
 // All compute happens in the library.
 #include "../include/mapquik_b200.h"
 
@@ -16,6 +18,7 @@
 #include <sys/stat.h>
 #include <unistd.h>
 #include <zlib.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <chrono>
@@ -32,11 +35,12 @@
 namespace {
 
 struct Opt {
-    std::string reads, reference, prefix, save_index, load_index, rescue;
+    std::string reads, reference, prefix, save_index, load_index, rescue, devices;
     bool has_prefix = false, debug = false, low_memory = false, nosimd = false, nohpc = false, pfx = false, parse_only = false;
     long k = -1, l = -1, c = -1, s = -1, g = -1, threads = -1, b = -1, q = -1;
     double density = -1;
-    int gpu = 0;
+    int gpu = 0, gpus = 0;
+    bool ascii = false;
 };
 
 [[noreturn]] void die(const std::string &m) { fprintf(stderr, "%s\n", m.c_str()); exit(1); }
@@ -54,6 +58,51 @@ inline void copy_upper(uint8_t *dst, const char *src, size_t n) {
 
 // growable byte buffer in pinned host memory (mq_host_alloc) so that mq_map_batch uploads at full PCIe speed
 bool g_use_pinned = true;        // --parse-only (a host-only self-test) uses plain malloc instead
+bool g_pack = true;              // block-parallel parser emits the packed input format (off: --ascii, --parse-only)
+
+// ---- lz4 frame input (main.rs:68,71).  liblz4 ships without headers here, so the four entry points of its stable
+// frame API are resolved at run time; a missing library is reported when an .lz4 file is actually opened.
+struct Lz4Api {
+    size_t (*create)(void **, unsigned) = nullptr;
+    size_t (*free_ctx)(void *) = nullptr;
+    size_t (*decompress)(void *, void *, size_t *, const void *, size_t *, const void *) = nullptr;
+    unsigned (*is_error)(size_t) = nullptr;
+    bool ok = false;
+    Lz4Api() {
+        void *h = dlopen("liblz4.so.1", RTLD_NOW);
+        if (!h) h = dlopen("liblz4.so", RTLD_NOW);
+        if (!h) return;
+        create = (decltype(create))dlsym(h, "LZ4F_createDecompressionContext");
+        free_ctx = (decltype(free_ctx))dlsym(h, "LZ4F_freeDecompressionContext");
+        decompress = (decltype(decompress))dlsym(h, "LZ4F_decompress");
+        is_error = (decltype(is_error))dlsym(h, "LZ4F_isError");
+        ok = create && free_ctx && decompress && is_error;
+    }
+};
+struct Lz4Reader {
+    static Lz4Api &api() { static Lz4Api a; return a; }
+    int fd; void *ctx = nullptr; std::vector<char> in; size_t ipos = 0, ilen = 0; bool in_eof = false;
+    explicit Lz4Reader(int fd_) : fd(fd_), in(4u << 20) {
+        if (!api().ok) die("cannot read .lz4 input: liblz4 not found");
+        if (api().is_error(api().create(&ctx, 100))) die("LZ4F_createDecompressionContext failed");
+    }
+    ~Lz4Reader() { if (ctx) api().free_ctx(ctx); }
+    long read(char *dst, size_t cap) {          // decompressed bytes (0 at end of stream)
+        size_t out = 0;
+        while (out == 0) {
+            if (ipos == ilen && !in_eof) {
+                ssize_t r = ::read(fd, in.data(), in.size());
+                if (r <= 0) in_eof = true; else { ipos = 0; ilen = (size_t)r; }
+            }
+            if (ipos == ilen && in_eof) return 0;
+            size_t dn = cap, sn = ilen - ipos;
+            const size_t rc = api().decompress(ctx, dst, &dn, in.data() + ipos, &sn, nullptr);
+            if (api().is_error(rc)) die("corrupt lz4 stream");
+            ipos += sn; out = dn;
+        }
+        return (long)out;
+    }
+};
 struct PinnedBuf {
     uint8_t *p = nullptr; size_t size = 0, cap = 0;
     static uint8_t *alloc(size_t n) { return g_use_pinned ? (uint8_t *)mq_host_alloc(n) : (uint8_t *)malloc(n); }
@@ -78,6 +127,7 @@ struct PinnedBuf {
 // views into a large refillable buffer; only lines that straddle a refill are copied.
 struct Fastx {
     gzFile f = nullptr; int fd = -1; bool fasta;     // plain files bypass zlib (read(2) straight into the buffer)
+    std::unique_ptr<Lz4Reader> lz4;
     std::vector<char> buf; size_t pos = 0, len = 0; bool eof = false;
     std::string spill;            // storage for a line that straddled a refill
     size_t file_bytes = ~(size_t)0 >> 1;   // on-disk size of a plain file (bounds the batch allocation)
@@ -93,6 +143,8 @@ struct Fastx {
             if (!f) die("Error opening compressed file: " + path);
             gzbuffer(f, 1 << 20);
             fd = -1;
+        } else if (path.size() > 4 && path.compare(path.size() - 4, 4, ".lz4") == 0) {   // main.rs:68
+            lz4.reset(new Lz4Reader(fd));
         } else {
             posix_fadvise(fd, 0, 0, POSIX_FADV_SEQUENTIAL);
             struct stat st; if (fstat(fd, &st) == 0 && S_ISREG(st.st_mode)) { file_bytes = (size_t)st.st_size; regular = true; }
@@ -102,7 +154,7 @@ struct Fastx {
     ~Fastx() { if (f) gzclose(f); if (fd >= 0) close(fd); }
     bool refill() {
         if (eof) return false;
-        long r = f ? (long)gzread(f, buf.data(), (unsigned)buf.size()) : (long)read(fd, buf.data(), buf.size());
+        long r = f ? (long)gzread(f, buf.data(), (unsigned)buf.size()) : lz4 ? lz4->read(buf.data(), buf.size()) : (long)read(fd, buf.data(), buf.size());
         if (r <= 0) { eof = true; return false; }
         pos = 0; len = (size_t)r;
         return true;
@@ -125,8 +177,8 @@ struct Fastx {
         if (n && ptr[n - 1] == '\r') n--;
         return true;
     }
-    static std::string id_of(const char *p, size_t n) {       // record.id(): up to the first whitespace
-        size_t e = 1; while (e < n && p[e] != ' ' && p[e] != '\t') e++;
+    static std::string id_of(const char *p, size_t n) {       // seq_io record.id(): the header up to the first SPACE
+        size_t e = 1; while (e < n && p[e] != ' ') e++;
         return std::string(p + 1, e - 1);
     }
     // next record: id + upper-cased sequence appended to seq
@@ -154,7 +206,17 @@ struct Fastx {
 // one batch of records; two of them rotate between the reader thread and the GPU
 struct Batch {
     PinnedBuf seqs; std::vector<uint64_t> offs{0}; std::vector<std::string> ids; bool last = false;
-    void clear() { seqs.clear(); offs.assign(1, 0); ids.clear(); last = false; }
+    // packed form (block-parallel parser): 2-bit codes, block bitmap, exception intervals -- seqs is then unused
+    bool packed = false; PinnedBuf words, flags; std::vector<mq_exc> exc; uint64_t n_bases = 0;
+    void clear() { seqs.clear(); words.clear(); flags.clear(); exc.clear(); packed = false; n_bases = 0; offs.assign(1, 0); ids.clear(); last = false; }
+    mq_packed view() const { mq_packed v; v.words = (const uint32_t *)words.p; v.flags = (const uint32_t *)flags.p; v.exc = exc.data(); v.n_exc = exc.size(); v.n_bases = n_bases; return v; }
+    // ASCII bytes of record i (rescue pass, --parse-only)
+    void record_bytes(size_t i, std::vector<uint8_t> &out) const {
+        const size_t n = (size_t)(offs[i + 1] - offs[i]);
+        out.resize(n);
+        if (!packed) { memcpy(out.data(), seqs.p + offs[i], n); return; }
+        mq_unpack((const uint32_t *)words.p, exc.data(), exc.size(), offs[i], n, out.data());
+    }
 };
 struct BatchQueue {          // single producer / single consumer over two slots
     std::mutex m; std::condition_variable cv; Batch slot[2]; int filled[2] = {0, 0};
@@ -258,14 +320,45 @@ struct BlockParser {
                 continue;
             }
             lap("records");
-            // (3) copy + upper-case into the pinned batch
-            B.seqs.reserve(std::max(dst, block_bytes) + 64); B.seqs.size = dst;     // sequence bytes never exceed the block: one allocation per slot
-            lap("reserve");
-            if (!jobs.empty()) {
-                const int T2 = (int)std::max<size_t>(1, std::min<size_t>((size_t)g_parse_threads, dst / (4u << 20) + 1));
-                std::vector<size_t> cut(T2 + 1, jobs.size()); cut[0] = 0;
-                { size_t j = 0; for (int t = 1; t < T2; t++) { const size_t want = dst * (size_t)t / T2; while (j < jobs.size() && jobs[j].dst < want) j++; cut[t] = j; } }
-                parallel_for(T2, [&](int t) { for (size_t j = cut[t]; j < cut[t + 1]; j++) copy_upper(B.seqs.p + jobs[j].dst, raw + jobs[j].src, jobs[j].len); });
+            // (3) copy into the pinned batch: packed (2 bits per base, upper-casing folded in) or upper-cased ASCII
+            const int T2 = (int)std::max<size_t>(1, std::min<size_t>((size_t)g_parse_threads, dst / (4u << 20) + 1));
+            std::vector<size_t> cut(T2 + 1, jobs.size()); cut[0] = 0;
+            { size_t j = 0; for (int t = 1; t < T2; t++) { const size_t want = dst * (size_t)t / T2; while (j < jobs.size() && jobs[j].dst < want) j++; cut[t] = j; } }
+            if (g_pack) {
+                const size_t cap_bases = std::max(dst, block_bytes) + 64;
+                const size_t wbytes = (size_t)mq_packed_words(cap_bases) * 4, fbytes = (size_t)mq_packed_flag_words(cap_bases) * 4;
+                B.words.reserve(wbytes); B.flags.reserve(fbytes);            // sized once per slot
+                B.words.size = (size_t)mq_packed_words(dst) * 4; B.flags.size = (size_t)mq_packed_flag_words(dst) * 4;
+                B.packed = true; B.n_bases = dst;
+                lap("reserve");
+                std::vector<std::vector<mq_exc>> ex(T2);
+                parallel_for(T2, [&](int t) {
+                    // zero my share of the destination first: mq_pack_at ORs the edge words of a range in
+                    const size_t w0 = B.words.size * (size_t)t / T2 & ~(size_t)3, w1 = t + 1 == T2 ? B.words.size : (B.words.size * (size_t)(t + 1) / T2 & ~(size_t)3);
+                    memset(B.words.p + w0, 0, w1 - w0);
+                    if (t == 0) memset(B.flags.p, 0, B.flags.size);
+                });
+                parallel_for(T2, [&](int t) {
+                    std::vector<mq_exc> tmp(256);
+                    for (size_t j = cut[t]; j < cut[t + 1]; j++) {
+                        uint64_t ne = 0;
+                        int rc = mq_pack_at((const uint8_t *)raw + jobs[j].src, jobs[j].len, jobs[j].dst, (uint32_t *)B.words.p, (uint32_t *)B.flags.p,
+                                            tmp.data(), tmp.size(), &ne, 1);
+                        if (rc == MQ_ERR_RANGE) {      // more exception intervals than the scratch list holds: the codes are in place, list them again
+                            tmp.resize((size_t)ne + 16);
+                            rc = mq_pack_at((const uint8_t *)raw + jobs[j].src, jobs[j].len, jobs[j].dst, (uint32_t *)B.words.p, (uint32_t *)B.flags.p,
+                                            tmp.data(), tmp.size(), &ne, 1);
+                        }
+                        if (rc != MQ_OK) die("mq_pack_at failed");
+                        ex[t].insert(ex[t].end(), tmp.begin(), tmp.begin() + (size_t)ne);
+                    }
+                });
+                for (auto &v : ex) B.exc.insert(B.exc.end(), v.begin(), v.end());     // thread order == position order
+            } else {
+                B.seqs.reserve(std::max(dst, block_bytes) + 64); B.seqs.size = dst;     // sequence bytes never exceed the block: one allocation per slot
+                lap("reserve");
+                if (!jobs.empty())
+                    parallel_for(T2, [&](int t) { for (size_t j = cut[t]; j < cut[t + 1]; j++) copy_upper(B.seqs.p + jobs[j].dst, raw + jobs[j].src, jobs[j].len); });
             }
             lap("copy");
             {   // the consumed part of the mapping is not needed again: drop it from this process's resident set
@@ -339,9 +432,19 @@ void ck(mq_ctx *c, int rc, const char *what) {
 int main(int argc, char **argv) {
     auto t_start = std::chrono::steady_clock::now();
     Opt o;
+    // structopt also takes `-k5` and `--density=0.01`: split those spellings into flag + value first
+    std::vector<std::string> args;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
-        auto val = [&](const char *name) -> std::string { if (i + 1 >= argc) die(std::string("missing value for ") + name); return argv[++i]; };
+        const size_t eq = a.find('=');
+        if (a.size() > 2 && a[0] == '-' && a[1] == '-' && eq != std::string::npos) { args.push_back(a.substr(0, eq)); args.push_back(a.substr(eq + 1)); }
+        else if (a.size() > 2 && a[0] == '-' && a[1] != '-' && strchr("kldcsgpbq", a[1]) && (isdigit((unsigned char)a[2]) || a[2] == '.' || a[1] == 'p')) {
+            args.push_back(a.substr(0, 2)); args.push_back(a.substr(2));
+        } else args.push_back(a);
+    }
+    for (size_t i = 0; i < args.size(); i++) {
+        std::string a = args[i];
+        auto val = [&](const char *name) -> std::string { if (i + 1 >= args.size()) die(std::string("missing value for ") + name); return args[++i]; };
         if (a == "--debug") o.debug = true;
         else if (a == "--low-memory") o.low_memory = true;
         else if (a == "--nosimd") o.nosimd = true;
@@ -359,25 +462,31 @@ int main(int argc, char **argv) {
         else if (a == "-b" || a == "--b") o.b = atol(val("b").c_str());
         else if (a == "-q" || a == "--q") o.q = atol(val("q").c_str());
         else if (a == "--gpu") o.gpu = atoi(val("gpu").c_str());
+        else if (a == "--gpus") o.gpus = atoi(val("gpus").c_str());           // extension: devices 0..N-1 in one run (mq_create_multi)
+        else if (a == "--devices") o.devices = val("devices");               // extension: explicit device list "0,1,3" (a device may repeat)
+        else if (a == "--ascii") o.ascii = true;                             // extension: one byte per base to the GPU instead of the packed format
         else if (a == "--save-index") o.save_index = val("save-index");      // extensions: the reference has no on-disk index
         else if (a == "--load-index") o.load_index = val("load-index");
         else if (a == "--parse-only") o.parse_only = true;                  // (testing) parse the reads, print a digest, exit
         else if (a == "--rescue") o.rescue = val("rescue");                  // "k,l,density": second pass over the unmapped reads
-        else if (a == "-h" || a == "--help") { printf("mapquik <reads> --reference <ref> [-k -l -d -c -s -g -p --nohpc --threads --gpu]\n"); return 0; }
+        else if (a == "-h" || a == "--help") { printf("mapquik <reads> --reference <ref> [-k -l -d -c -s -g -p --nohpc --threads --gpu ID | --gpus N --ascii]\n"); return 0; }
         else if (!a.empty() && a[0] == '-') die("unknown option " + a);
         else o.reads = a;
     }
     if (o.reads.empty()) die("Please specify an input file.");
     if (o.threads > 0) g_parse_threads = (int)std::min<long>(o.threads, 64);
+    if (o.ascii) g_pack = false;
     if (o.parse_only) {
-        g_use_pinned = false;
+        g_use_pinned = false; g_pack = getenv("MQ_CLI_PACK") != nullptr;     // the digest is over the ASCII bytes either way
         // FNV-1a over "id\n" + sequence + "\n" of every record: identical for every container format / block size
         uint64_t h = 1469598103934665603ull, nrec = 0, nbase = 0;
         auto mixb = [&](const uint8_t *p, size_t n) { for (size_t i = 0; i < n; i++) { h ^= p[i]; h *= 1099511628211ull; } };
+        std::vector<uint8_t> rec;
         for_each_batch(o.reads, is_fasta_name(o.reads), 256u << 20, [&](Batch &B) {
             for (size_t i = 0; i < B.ids.size(); i++) {
                 mixb((const uint8_t *)B.ids[i].data(), B.ids[i].size()); mixb((const uint8_t *)"\n", 1);
-                mixb(B.seqs.p + B.offs[i], (size_t)(B.offs[i + 1] - B.offs[i])); mixb((const uint8_t *)"\n", 1);
+                B.record_bytes(i, rec);
+                mixb(rec.data(), rec.size()); mixb((const uint8_t *)"\n", 1);
                 nrec++; nbase += B.offs[i + 1] - B.offs[i];
             }
         });
@@ -408,7 +517,11 @@ int main(int argc, char **argv) {
     mq_params p; p.k = (uint32_t)k; p.l = (uint32_t)l; p.density = density; p.use_hpc = o.nohpc ? 0 : 1;
     p.c = (uint32_t)c; p.s = (uint32_t)s; p.g = (uint32_t)g;
     mq_ctx *ctx = nullptr;
-    ck(nullptr, mq_create(&ctx, &p, o.gpu), "mq_create");
+    std::vector<int> devs;
+    for (int d = 0; d < o.gpus; d++) devs.push_back(d);
+    if (!o.devices.empty()) { devs.clear(); for (const char *q = o.devices.c_str(); *q;) { devs.push_back(atoi(q)); while (*q && *q != ',') q++; if (*q) q++; } }
+    auto create = [&](mq_ctx **out, const mq_params *pp) { return devs.size() > 1 ? mq_create_multi(out, pp, devs.data(), (int)devs.size()) : mq_create(out, pp, devs.size() == 1 ? devs[0] : o.gpu); };
+    ck(nullptr, create(&ctx, &p), "mq_create");
 
     std::string paf_name = prefix + ".paf";
     FILE *paf = fopen(paf_name.c_str(), "w");
@@ -437,7 +550,8 @@ int main(int argc, char **argv) {
     } else {
         for_each_batch(o.reference, ref_fasta, o.low_memory ? (64u << 20) : (128u << 20), [&](Batch &B) {
             std::vector<uint64_t> nb(B.ids.size());
-            ck(ctx, mq_index_add(ctx, B.seqs.p, B.offs.data(), (uint32_t)B.ids.size(), (uint32_t)ref_names.size(), nb.data()), "mq_index_add");
+            if (B.packed) { const mq_packed v = B.view(); ck(ctx, mq_index_add_packed(ctx, &v, B.offs.data(), (uint32_t)B.ids.size(), (uint32_t)ref_names.size(), nb.data()), "mq_index_add_packed"); }
+            else ck(ctx, mq_index_add(ctx, B.seqs.p, B.offs.data(), (uint32_t)B.ids.size(), (uint32_t)ref_names.size(), nb.data()), "mq_index_add");
             for (size_t i = 0; i < B.ids.size(); i++) {
                 printf("Indexed reference %s: %llu k-min-mers.\n", B.ids[i].c_str(), (unsigned long long)nb[i]);        // closures.rs:58
                 ref_names.push_back(B.ids[i]); ref_lens.push_back(B.offs[i + 1] - B.offs[i]);
@@ -456,17 +570,19 @@ int main(int argc, char **argv) {
     auto t_map = std::chrono::steady_clock::now();
     PinnedBuf un_seqs; std::vector<uint64_t> un_offs{0}; std::vector<std::string> un_ids;      // unmapped reads (--rescue)
     {
-        std::vector<mq_hit> hits; std::vector<char> line(1 << 16);
+        std::vector<mq_hit> hits; std::vector<char> line(1 << 16); std::vector<uint8_t> rec_tmp;
         // 64 MB batches: two pinned slots cost ~70 ms to allocate (256 MB ones cost 0.33 s, more than parsing 1 GB), and the
         // GPU side of a batch (H2D 1.3 ms + kernels) hides behind the parser either way
         for_each_batch(o.reads, reads_fasta, 64u << 20, [&](Batch &B) {
             hits.resize(B.ids.size());
-            ck(ctx, mq_map_batch(ctx, B.seqs.p, B.offs.data(), (uint32_t)B.ids.size(), hits.data()), "mq_map_batch");
+            if (B.packed) { const mq_packed v = B.view(); ck(ctx, mq_map_batch_packed(ctx, &v, B.offs.data(), (uint32_t)B.ids.size(), hits.data()), "mq_map_batch_packed"); }
+            else ck(ctx, mq_map_batch(ctx, B.seqs.p, B.offs.data(), (uint32_t)B.ids.size(), hits.data()), "mq_map_batch");
             for (size_t i = 0; i < B.ids.size(); i++) {                  // input order, closures.rs:117-123
                 if (!hits[i].mapped) {
                     if (!o.rescue.empty()) {                             // keep the read for the second pass
                         const size_t n = (size_t)(B.offs[i + 1] - B.offs[i]);
-                        un_seqs.reserve(un_seqs.size + n); memcpy(un_seqs.p + un_seqs.size, B.seqs.p + B.offs[i], n); un_seqs.size += n;
+                        B.record_bytes(i, rec_tmp);
+                        un_seqs.reserve(un_seqs.size + n); memcpy(un_seqs.p + un_seqs.size, rec_tmp.data(), n); un_seqs.size += n;
                         un_offs.push_back(un_seqs.size); un_ids.push_back(B.ids[i]);
                     }
                     continue;
@@ -500,10 +616,11 @@ int main(int argc, char **argv) {
         if (!un_ids.empty()) {
             mq_params p2 = p; p2.k = (uint32_t)k2; p2.l = (uint32_t)l2; p2.density = d2;
             mq_ctx *c2 = nullptr;
-            ck(nullptr, mq_create(&c2, &p2, o.gpu), "mq_create (rescue)");
+            ck(nullptr, create(&c2, &p2), "mq_create (rescue)");
             std::vector<std::string> names2; std::vector<uint64_t> lens2;
             for_each_batch(o.reference, ref_fasta, o.low_memory ? (64u << 20) : (128u << 20), [&](Batch &B) {
-                ck(c2, mq_index_add(c2, B.seqs.p, B.offs.data(), (uint32_t)B.ids.size(), (uint32_t)names2.size(), nullptr), "mq_index_add (rescue)");
+                if (B.packed) { const mq_packed v = B.view(); ck(c2, mq_index_add_packed(c2, &v, B.offs.data(), (uint32_t)B.ids.size(), (uint32_t)names2.size(), nullptr), "mq_index_add_packed (rescue)"); }
+                else ck(c2, mq_index_add(c2, B.seqs.p, B.offs.data(), (uint32_t)B.ids.size(), (uint32_t)names2.size(), nullptr), "mq_index_add (rescue)");
                 for (size_t i = 0; i < B.ids.size(); i++) { names2.push_back(B.ids[i]); lens2.push_back(B.offs[i + 1] - B.offs[i]); }
             });
             ck(c2, mq_index_freeze(c2, lens2.data(), (uint32_t)lens2.size(), nullptr, nullptr), "mq_index_freeze (rescue)");

@@ -14,10 +14,26 @@ pub struct MqHit {
     pub q_start: u64, pub q_end: u64, pub r_start: u64, pub r_end: u64, pub score: u64,
 }
 
+/// one interval of bytes other than A/C/G/T inside a packed sequence array (include/mapquik_b200.h `mq_exc`)
+#[repr(C)]
+#[derive(Clone, Copy, Default, Debug)]
+pub struct MqExc { pub start: u64, pub len: u32, pub byte: u32 }
+
+/// packed sequence array (`mq_packed`): 2-bit codes, block bitmap, exception intervals
+#[repr(C)]
+pub struct MqPacked { pub words: *const u32, pub flags: *const u32, pub exc: *const MqExc, pub n_exc: u64, pub n_bases: u64 }
+
 pub enum MqCtx {}
 
 extern "C" {
     pub fn mq_create(out: *mut *mut MqCtx, p: *const MqParams, device: c_int) -> c_int;
+    pub fn mq_create_multi(out: *mut *mut MqCtx, p: *const MqParams, devices: *const c_int, n_devices: c_int) -> c_int;
+    pub fn mq_packed_words(n_bases: u64) -> u64;
+    pub fn mq_packed_flag_words(n_bases: u64) -> u64;
+    pub fn mq_pack_at(ascii: *const u8, n_bases: u64, at_base: u64, words: *mut u32, flags: *mut u32, exc: *mut MqExc, exc_cap: u64,
+                      n_exc: *mut u64, fold_case: c_int) -> c_int;
+    pub fn mq_index_add_packed(c: *mut MqCtx, seqs: *const MqPacked, offs: *const u64, n: u32, first_ref_idx: u32, nb_mers_out: *mut u64) -> c_int;
+    pub fn mq_map_batch_packed(c: *mut MqCtx, seqs: *const MqPacked, offs: *const u64, n: u32, out: *mut MqHit) -> c_int;
     pub fn mq_destroy(c: *mut MqCtx);
     pub fn mq_strerror(code: c_int) -> *const c_char;
     pub fn mq_last_error(c: *const MqCtx) -> *const c_char;
@@ -47,6 +63,13 @@ impl GpuIndex {
     pub fn new(params: MqParams, device: i32) -> Self {
         let mut ctx: *mut MqCtx = std::ptr::null_mut();
         check(std::ptr::null(), unsafe { mq_create(&mut ctx, &params, device) }, "mq_create");
+        GpuIndex { ctx, ref_lens: Vec::new() }
+    }
+    /// The same over several GPUs of the box (closures.rs:85,183 fan out over threads; here over devices): the library
+    /// partitions the reference by base range, exchanges the minimizer stores GPU to GPU at `freeze`, shards the reads.
+    pub fn new_multi(params: MqParams, devices: &[i32]) -> Self {
+        let mut ctx: *mut MqCtx = std::ptr::null_mut();
+        check(std::ptr::null(), unsafe { mq_create_multi(&mut ctx, &params, devices.as_ptr(), devices.len() as c_int) }, "mq_create_multi");
         GpuIndex { ctx, ref_lens: Vec::new() }
     }
     /// ≙ mers::ref_extract for a batch of upper-cased records (closures.rs:48,63); returns the k-min-mer count of each
@@ -82,3 +105,41 @@ impl GpuReadOnlyIndex {
     }
 }
 impl Drop for GpuReadOnlyIndex { fn drop(&mut self) { unsafe { mq_destroy(self.ctx) } } }
+
+/// A batch buffer the record closures append to INSTEAD of `record.seq().to_ascii_uppercase()` (closures.rs:63,106):
+/// the one pass the reference spends on upper-casing a copy packs the record to 2 bits per base (upper-casing folded
+/// in), so a quarter of the bytes cross PCIe.  `mq_pack_at` may be called concurrently for disjoint ranges, i.e. from
+/// seq_io's worker closures once each record has been given its destination offset.
+pub struct PackedBatch { pub words: Vec<u32>, pub flags: Vec<u32>, pub exc: Vec<MqExc>, pub offs: Vec<u64> }
+impl PackedBatch {
+    pub fn with_capacity(bases: u64) -> Self {
+        let (w, f) = unsafe { (mq_packed_words(bases), mq_packed_flag_words(bases)) };
+        PackedBatch { words: vec![0u32; w as usize], flags: vec![0u32; f as usize], exc: Vec::new(), offs: vec![0] }
+    }
+    pub fn push_record(&mut self, seq: &[u8]) {
+        let at = *self.offs.last().unwrap();
+        let mut tmp = vec![MqExc::default(); 64];
+        let mut n = 0u64;
+        let mut rc = unsafe { mq_pack_at(seq.as_ptr(), seq.len() as u64, at, self.words.as_mut_ptr(), self.flags.as_mut_ptr(), tmp.as_mut_ptr(), tmp.len() as u64, &mut n, 1) };
+        if rc == -5 {   // MQ_ERR_RANGE: more intervals than the scratch list holds; the codes are in place, list them again
+            tmp.resize(n as usize, MqExc::default());
+            rc = unsafe { mq_pack_at(seq.as_ptr(), seq.len() as u64, at, self.words.as_mut_ptr(), self.flags.as_mut_ptr(), tmp.as_mut_ptr(), tmp.len() as u64, &mut n, 1) };
+        }
+        check(std::ptr::null(), rc, "mq_pack_at");
+        self.exc.extend_from_slice(&tmp[..n as usize]);
+        self.offs.push(at + seq.len() as u64);
+    }
+    fn view(&self) -> MqPacked {
+        MqPacked { words: self.words.as_ptr(), flags: self.flags.as_ptr(), exc: self.exc.as_ptr(), n_exc: self.exc.len() as u64, n_bases: *self.offs.last().unwrap() }
+    }
+}
+impl GpuReadOnlyIndex {
+    /// ≙ mers::find_matches for a packed batch
+    pub fn find_matches_packed(&self, b: &PackedBatch) -> Vec<MqHit> {
+        let n = (b.offs.len() - 1) as u32;
+        let mut hits = vec![MqHit::default(); n as usize];
+        let v = b.view();
+        check(self.ctx, unsafe { mq_map_batch_packed(self.ctx, &v, b.offs.as_ptr(), n, hits.as_mut_ptr()) }, "mq_map_batch_packed");
+        hits
+    }
+}

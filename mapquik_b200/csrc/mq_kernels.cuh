@@ -22,7 +22,10 @@ namespace mq {
 // ------------------------------------------------------------------------------------------------
 // constants
 // ------------------------------------------------------------------------------------------------
-constexpr uint32_t EV_CAP       = 256;             // staged events per tile before overflow pool
+#ifndef MQ_CS_MAX
+#define MQ_CS_MAX 128
+#endif
+constexpr uint32_t EV_CAP       = 2 * MQ_CS_MAX;   // staged events per tile before overflow pool (a tile holds 32 * MQ_CS_MAX bases)
 constexpr uint64_t EMPTY_KEY    = 0xFFFFFFFFFFFFFFFFull;
 constexpr int      MQ_MAX_K_    = 32;
 
@@ -151,9 +154,6 @@ __global__ void __launch_bounds__(SCAN_BLK) k_tile_prefix(uint32_t *cnt, uint32_
 // ------------------------------------------------------------------------------------------------
 // tiles: a warp-tile covers up to TW_MAX raw bases of one record, on a 16-base aligned grid
 // ------------------------------------------------------------------------------------------------
-#ifndef MQ_CS_MAX
-#define MQ_CS_MAX 128
-#endif
 constexpr int CS_MAX   = MQ_CS_MAX;         // raw bases per lane chunk (<= 128, multiple of 16)
 constexpr int TW_MAX   = 32 * CS_MAX;       // raw bases per warp tile
 // tiles of record [gs, ge) (host and device use the same formula)
@@ -334,12 +334,12 @@ struct Entry { uint32_t id, start, end, offrc; };
 __device__ __forceinline__ bool table_get(const Table &t, uint64_t key, Entry *e) {
     uint64_t i = key == EMPTY_KEY ? t.mask + 1 : (key & t.mask);
     for (;;) {
-        const uint4 *p = (const uint4 *)&t.slots[i];
-        uint4 a = __ldg(p), b = __ldg(p + 1);
-        uint64_t k = (uint64_t)a.x | ((uint64_t)a.y << 32);
+        // the whole 32-byte slot (= one DRAM sector) in ONE request: sm_100 has 256-bit global loads
+        uint64_t k, w1, w2, w3;
+        asm volatile("ld.global.nc.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(k), "=l"(w1), "=l"(w2), "=l"(w3) : "l"(&t.slots[i]));
         if (k == key) {
-            if (b.z != 1u) return false;                    // count != 1: tombstone (or untouched spare slot)
-            e->id = a.z; e->start = a.w; e->end = b.x; e->offrc = b.y;
+            if ((uint32_t)w3 != 1u) return false;           // count != 1: tombstone (or untouched spare slot)
+            e->id = (uint32_t)w1; e->start = (uint32_t)(w1 >> 32); e->end = (uint32_t)w2; e->offrc = (uint32_t)(w2 >> 32);
             return true;
         }
         if (k == EMPTY_KEY) return false;

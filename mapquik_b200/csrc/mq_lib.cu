@@ -38,7 +38,14 @@ struct DBuf {
 };
 struct HBuf { void *p = nullptr; size_t cap = 0; };      // pinned host memory
 
-constexpr uint64_t SUB_BASES = 128ull << 20;            // bases per pipelined mapping sub-batch
+#ifndef MQ_SUB_MBASES
+#define MQ_SUB_MBASES 128
+#endif
+#ifndef MQ_SUB_MBASES_LIGHT
+#define MQ_SUB_MBASES_LIGHT 512
+#endif
+constexpr uint64_t SUB_BASES = (uint64_t)MQ_SUB_MBASES << 20;             // bases per pipelined mapping sub-batch (ASCII from the host: 1 byte per base over PCIe)
+constexpr uint64_t SUB_BASES_LIGHT = (uint64_t)MQ_SUB_MBASES_LIGHT << 20; // ... when the upload is light or absent (packed, device-resident): fewer, fuller launches
 constexpr uint64_t ADD_BASES = 256ull << 20;            // bases per pipelined index-build piece batch
 constexpr size_t   PAD = 256;                          // zeroed slack behind sequence buffers (word loads past the end)
 
@@ -76,6 +83,7 @@ struct mq_ctx {
     cudaStream_t stream = nullptr, copy_stream = nullptr, d2h_stream = nullptr;
     uint64_t bound = 0;
     ScanTables tab{};
+    DBuf d_warm;                  // 256 x uint4: the four-step warm-up table of the scan kernel
     int scan_ctas_per_sm[4] = {0, 0, 0, 0};
     std::string err;
     uint64_t launches = 0, scan_kernel_launches = 0;
@@ -219,6 +227,19 @@ void fill_tables(ScanTables &T, uint32_t l) {
     for (uint32_t q = 0; q < 86; q++) T.sel55[q] = selector((q & 1u) | ((q >> 1) & 2u) | ((q >> 2) & 4u) | ((q >> 3) & 8u));
 }
 
+// C[idx] of warm_row (mq_scan.cuh): the state after the four steps in = c3, c2, c1, c0 (out = phantom 'A') from state 0
+void fill_warm_table(const ScanTables &T, uint32_t out[256][4]) {
+    for (uint32_t idx = 0; idx < 256; idx++) {
+        uint64_t F = 0, R = 0;
+        for (int b = 3; b >= 0; b--) {
+            const uint32_t c = (idx >> (2 * b)) & 3u;
+            F = ((F >> 1) | (F << 63)) ^ T.pairF[c];
+            R = ((R << 1) | (R >> 63)) ^ T.pairR[c];
+        }
+        out[idx][0] = (uint32_t)F; out[idx][1] = (uint32_t)(F >> 32); out[idx][2] = (uint32_t)R; out[idx][3] = (uint32_t)(R >> 32);
+    }
+}
+
 // ---- tile tables (host) ------------------------------------------------------------------------------
 // layout of a slot's meta block; offsets in bytes, all 16-byte aligned
 struct MetaLayout {
@@ -272,7 +293,7 @@ int ensure_workspace(mq_ctx *c, uint32_t n, uint32_t n_tiles, uint64_t bases, bo
 template <bool HPC, bool PACKED>
 int launch_scan_t(mq_ctx *c, const ScanArgs &a) {
     const int vi = (HPC ? 1 : 0) | (PACKED ? 2 : 0);
-    const size_t smem = (size_t)SCAN_WARPS * WARP_BYTES;
+    const size_t smem = (size_t)SCAN_WARPS * warp_bytes(PACKED);
     auto kern = k_scan_minimizers<HPC, PACKED>;
     if (c->scan_ctas_per_sm[vi] == 0) {      // persistent grid = every CTA the chip can hold
         int nb = 0;
@@ -299,7 +320,7 @@ int enqueue_scan(mq_ctx *c, const BatchDev &b) {
     a.lane_cnt = c->d_lane_cnt.as<uint16_t>(); a.tile_cnt = c->d_tile_cnt.as<uint32_t>();
     a.ovf_count = &b.sc->ovf_count; a.ovf_cap = c->ovf_cap;
     a.ovf_tile = c->d_ovf_tile.as<uint32_t>(); a.ovf_meta = c->d_ovf_meta.as<uint32_t>(); a.ovf_hash = c->d_ovf_hash.as<uint64_t>();
-    a.tile_ticket = &b.sc->scan_ticket; a.emit_range = b.emit;
+    a.tile_ticket = &b.sc->scan_ticket; a.emit_range = b.emit; a.warm = c->d_warm.as<uint4>();
     {
         StageTimer t(c, "scan");
         {
@@ -510,9 +531,10 @@ int map_pipeline(mq_ctx *c, const SeqInput &in, const uint64_t *offs, uint32_t n
     if ((rc = init_streams(c))) return rc;
     // sub-batch boundaries
     std::vector<uint32_t> cut{0};
+    const uint64_t sub = (in.packed || in.resident) ? SUB_BASES_LIGHT : SUB_BASES;
     for (uint32_t i0 = 0; i0 < n;) {
         uint32_t i1 = i0 + 1;
-        while (i1 < n && offs[i1 + 1] - offs[i0] <= SUB_BASES) i1++;
+        while (i1 < n && offs[i1 + 1] - offs[i0] <= sub) i1++;
         cut.push_back(i1); i0 = i1;
     }
     const size_t ns = cut.size() - 1;
@@ -722,6 +744,12 @@ static int create_one(mq_ctx **out, const mq_params *p, int device) {
     // random 32-byte probes into a multi-GB table: fetch one sector per miss, not two
     cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32); cudaGetLastError();
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return MQ_ERR_CUDA; }
+    uint32_t warm[256][4];
+    fill_warm_table(c->tab, warm);
+    if (cudaMalloc(&c->d_warm.p, sizeof warm) != cudaSuccess || cudaMemcpy(c->d_warm.p, warm, sizeof warm, cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaGetLastError(); cudaStreamDestroy(c->stream); delete c; return MQ_ERR_CUDA;
+    }
+    c->d_warm.cap = sizeof warm;
     *out = c;
     return MQ_OK;
 }
@@ -772,7 +800,7 @@ void mq_destroy(mq_ctx *c) {
     timers_collect(c);
     DBuf *bufs[] = {&c->d_ev_hash, &c->d_ev_meta, &c->d_lane_cnt, &c->d_tile_cnt, &c->d_blk, &c->d_ovf_tile, &c->d_ovf_meta, &c->d_ovf_hash,
                     &c->d_pos, &c->d_hash, &c->d_seq_off, &c->d_matches, &c->d_nmatch, &c->d_big_list, &c->d_misc, &c->st_pos, &c->st_hash,
-                    &c->d_table, &c->d_ref_lens};
+                    &c->d_table, &c->d_ref_lens, &c->d_warm};
     for (DBuf *b : bufs) dfree(*b);
     for (auto &s : c->slot) {
         dfree(s.d_in); dfree(s.d_meta); dfree(s.d_hits); dfree(s.d_sc); hfree(s.h_meta); hfree(s.h_sc);
@@ -1106,7 +1134,7 @@ int freeze_local(mq_ctx *c, const uint64_t *ref_lens, uint32_t n_refs) {
     if ((rc = ensure(c, c->d_ref_lens, ((size_t)n_refs + 1) * 8))) return rc;
     if ((rc = ensure(c, c->d_misc, ((size_t)n_rec + 2) * 4 * 3 + 64))) return rc;
     uint32_t *d_rec_off = c->d_misc.as<uint32_t>(), *d_rec_id = d_rec_off + n_rec + 2;
-    unsigned long long *d_cnt = (unsigned long long *)(d_rec_id + n_rec + 2 + ((n_rec & 1) ? 1 : 0));   // 8-byte aligned
+    unsigned long long *d_cnt = (unsigned long long *)(d_rec_id + n_rec + 2);   // 2 * (n_rec + 2) words in: 8-byte aligned
     {
         StageTimer t(c, "insert");
         if (n_refs) CK(cudaMemcpyAsync(c->d_ref_lens.p, ref_lens, (size_t)n_refs * 8, cudaMemcpyHostToDevice, c->stream));

