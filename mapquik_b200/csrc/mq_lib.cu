@@ -224,7 +224,10 @@ void fill_tables(ScanTables &T, uint32_t l) {
         return sel;
     };
     for (uint32_t p = 0; p < 16; p++) T.sel[p] = selector(p);
-    for (uint32_t q = 0; q < 86; q++) T.sel55[q] = selector((q & 1u) | ((q >> 1) & 2u) | ((q >> 2) & 4u) | ((q >> 3) & 8u));
+    for (uint32_t q = 0; q < 86; q++) {       // run bits at even positions -> selector | run bits << 16 | 8 * count << 24
+        const uint32_t p = (q & 1u) | ((q >> 1) & 2u) | ((q >> 2) & 4u) | ((q >> 3) & 8u);
+        T.sel55[q] = selector(p) | (p << 16) | ((uint32_t)__builtin_popcount(p) * 8u << 24);
+    }
 }
 
 // C[idx] of warm_row (mq_scan.cuh): the state after the four steps in = c3, c2, c1, c0 (out = phantom 'A') from state 0
@@ -293,7 +296,7 @@ int ensure_workspace(mq_ctx *c, uint32_t n, uint32_t n_tiles, uint64_t bases, bo
 template <bool HPC, bool PACKED>
 int launch_scan_t(mq_ctx *c, const ScanArgs &a) {
     const int vi = (HPC ? 1 : 0) | (PACKED ? 2 : 0);
-    const size_t smem = (size_t)SCAN_WARPS * warp_bytes(PACKED);
+    const size_t smem = (size_t)SCAN_WARPS * WARP_BYTES;
     auto kern = k_scan_minimizers<HPC, PACKED>;
     if (c->scan_ctas_per_sm[vi] == 0) {      // persistent grid = every CTA the chip can hold
         int nb = 0;

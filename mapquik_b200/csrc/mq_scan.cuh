@@ -51,7 +51,7 @@ struct ScanTables {                         // byte offsets are used directly by
     uint64_t F0, R0;                        // @384: hash state of a window of l phantom 'A's
     uint32_t sel[16];                       // @400: PRMT selectors compacting the run-start bytes of a word (index = 4 run bits)
     uint32_t opq[8];                        // @464: 2^31, 2, bound_hi, &T -- read back through volatile loads (see hash_step)
-    uint32_t sel55[86];                     // @496: the same selectors indexed by run bits at even positions (mask 0x55)
+    uint32_t sel55[86];                     // @496: indexed by run bits at even positions (mask 0x55): selector | run bits << 16 | 8 * count << 24
 };
 static_assert(offsetof(ScanTables, sel) == 400 && offsetof(ScanTables, opq) == 464 && offsetof(ScanTables, sel55) == 496, "the kernel addresses these fields by byte offset");
 
@@ -199,10 +199,9 @@ __device__ __forceinline__ bool any_flag(const ScanArgs &a, uint64_t x0, uint64_
 constexpr int ROWS      = STRIDE / 4 + 2;                            // words per lane column: symbols + context + zero, + 2 spare rows
 constexpr int OFF_HALO  = ROWS * 128;                                // u8[48]  halo stream (contiguous; only lane 31 reads it)
 constexpr int OFF_NSYM  = OFF_HALO + 48;                             // u32[33] symbols per stream (32 = halo)
-constexpr int OFF_RUNM  = OFF_NSYM + 144;                            // run masks, row-interleaved: ASCII u16 x 2 per word (groups 2j, 2j+1
-                                                                     // of lane L at row j); PACKED one u32 per group (even bits), row g
-__host__ __device__ constexpr int off_cum(bool packed) { return OFF_RUNM + (packed ? GPL_MAX : GPL_MAX / 2) * 128; }   // u8 symbol counts before each group, 4 per word, row-interleaved
-__host__ __device__ constexpr int warp_bytes(bool packed) { return (off_cum(packed) + (GPL_MAX / 4) * 128 + 15) & ~15; }
+constexpr int OFF_RUNM  = OFF_NSYM + 144;                            // u16 run masks: word j (groups 2j, 2j+1) of lane L at row j
+constexpr int OFF_CUM   = OFF_RUNM + (GPL_MAX / 2) * 128;            // u8 symbol counts before each group, 4 per word, row-interleaved
+constexpr int WARP_BYTES = (OFF_CUM + (GPL_MAX / 4) * 128 + 15) & ~15;
 // Parked candidates live in the lane's OWN column, from the top row downwards, three rows each (hash lo, hash hi,
 // ordinal): the scan walks its column from the top down, so the rows above the outgoing-symbol words are dead by the
 // time candidates appear, and the list costs no shared memory of its own.
@@ -231,20 +230,11 @@ __device__ __forceinline__ uint32_t select16(uint32_t m, uint32_t k) {
     c = m & 1u;                   if (k >= c) { pos += 1; }
     return pos;
 }
-// the same for a 32-bit mask whose set bits sit at even positions (bit 2j <=> base j): returns j
-__device__ __forceinline__ uint32_t select_even32(uint32_t m, uint32_t k) {
-    uint32_t pos = 0, c;
-    c = __popc(m & 0xFFFFu);      if (k >= c) { k -= c; pos += 8; m >>= 16; }
-    c = __popc(m & 0xFFu);        if (k >= c) { k -= c; pos += 4; m >>= 8; }
-    c = __popc(m & 0xFu);         if (k >= c) { k -= c; pos += 2; m >>= 4; }
-    c = m & 1u;                   if (k >= c) { pos += 1; }
-    return pos;
-}
 // raw offset (inside the lane chunk) of the symbol with ordinal o: group = #(cum[g] <= o) - 1.
 // cum[] holds the symbol count before each 16-base group; unused entries hold a sentinel no ordinal reaches (a chunk
 // with unused groups has <= CS_MAX - 16 symbols).  With chunks of <= 128 bases every value is < 0x80, so "byte <= o" is
 // one SWAR subtraction: bit 7 of (0x80|o) - byte; longer chunks use the byte-wise compare instruction.
-template <bool PACKED> __device__ __forceinline__ uint32_t raw_offset(uint32_t runm_l, uint32_t cum_l, uint32_t o) {
+__device__ __forceinline__ uint32_t raw_offset(uint32_t runm_l, uint32_t cum_l, uint32_t o) {
     uint32_t g = 0;
     const uint32_t ob = o * 0x01010101u;
 #pragma unroll
@@ -255,7 +245,6 @@ template <bool PACKED> __device__ __forceinline__ uint32_t raw_offset(uint32_t r
     }
     g -= 1;
     const uint32_t base = lds8(cum_l + (g >> 2) * 128u + (g & 3u));
-    if (PACKED) return 16u * g + select_even32(lds32(runm_l + g * 128u), o - base);
     return 16u * g + select16(lds16(runm_l + (g >> 1) * 128u + (g & 1u) * 2u), o - base);
 }
 
@@ -276,7 +265,6 @@ __device__ __forceinline__ void emit_event(uint32_t x, uint64_t h, uint32_t lane
 }
 
 // resolve and emit the candidates parked in rows (cpz, top] of the lane's column, oldest first
-template <bool PACKED>
 __device__ __noinline__ uint32_t flush_candidates(uint32_t top, uint32_t cpz, uint32_t j0, uint32_t runm_l, uint32_t cum_l,
                                                   uint32_t c_lo, uint32_t xlo, uint32_t xlim, uint32_t lane, uint32_t ev_a, uint32_t tile,
                                                   const ScanArgs &a, uint64_t bound, int o2, uint64_t *evh, uint32_t *evm) {
@@ -286,7 +274,7 @@ __device__ __noinline__ uint32_t flush_candidates(uint32_t top, uint32_t cpz, ui
         if (h >= bound) continue;                      // parked on the hi-word pre-filter only: exact test here
         const uint32_t o = lds32(p - 256u);
         if ((int)o > o2) continue;                     // a context symbol, or a window the record end leaves incomplete
-        const uint32_t x = c_lo + raw_offset<PACKED>(runm_l, cum_l, o);
+        const uint32_t x = c_lo + raw_offset(runm_l, cum_l, o);
         if (x - xlo < xlim - xlo) { emit_event(x, h, lane, j, ev_a, tile, a, evh, evm); j++; }
     }
     return j;
@@ -335,17 +323,38 @@ __device__ __forceinline__ void stage_chunk(const ScanArgs &a, uint64_t tlo, uin
     const uint32_t lo_x = max(own_lo, c_lo), hi_x = min(own_hi, c_lo + Cs);
     uint32_t g0 = gpl, g1 = gpl;
     if (lo_x < hi_x) { g0 = (lo_x - c_lo + 15) >> 4; g1 = (hi_x - c_lo) >> 4; if (g1 < g0) g1 = g0; }
-    uint32_t ca = cum_l, ra = runm_l;
     constexpr bool FASTP = PACKED && !FLAG;              // packed fast path: 2-bit arithmetic, no byte reconstruction
-    uint4 nxt = make_uint4(0, 0, 0, 0); uint32_t nxw = 0;
-    if (g0 < g1) { if (FASTP) nxw = __ldg(a.packed + (cx >> 4) + g0); else nxt = src_u128<PACKED>(a, cx + 16 * g0); }   // prefetch: one group ahead
-    for (uint32_t g = 0; g < gpl; g++) {
+    // bookkeeping of group g: symbol count before it (cum), its 16 run bits (runm); both row-interleaved
+    auto open_group = [&](uint32_t g) { sts8(cum_l + (g >> 2) * 128u + (g & 3u), q.n8 >> 3); };
+    auto close_group = [&](uint32_t g, uint32_t rm) { sts16(runm_l + (g >> 1) * 128u + (g & 1u) * 2u, rm); };
+    // a group outside the record holds no symbol; one cut by a record boundary goes word by word with masked run bits
+    auto edge_group = [&](uint32_t g, bool after_packed_fast) {
         uint32_t rm = 0;
-        sts8(ca, q.n8 >> 3);
-        if (g >= g0 && g < g1) {
-            if (FASTP) {
-                const uint32_t x = nxw;
-                if (g + 1 < g1) nxw = __ldg(a.packed + (cx >> 4) + g + 1);
+        open_group(g);
+        const uint32_t xg = c_lo + 16 * g;
+        if (xg < own_hi && xg + 16 > own_lo) {
+            if (after_packed_fast) prev = prmt(0x47544341u, 0u, 0x4440u | ((prev >> 1) & 3u));   // code -> letter (one byte)
+            const uint4 v = src_u128<PACKED>(a, cx + 16 * g);
+            const uint32_t uw[4] = {v.x, v.y, v.z, v.w};
+            const bool rec_start = tlo + own_lo == gs;
+#pragma unroll
+            for (int w = 0; w < 4; w++) stage_cut_word<HPC, FLAG>(uw[w], prev, xg + 4 * w, own_lo, own_hi, rec_start, ta, q, rm, bad, w);
+        }
+        close_group(g, rm);
+    };
+    if (FASTP) {
+        // the whole chunk (<= GPL_MAX words) is requested up front; only this part is unrolled
+        uint32_t pw[GPL_MAX];
+#pragma unroll
+        for (int g = 0; g < GPL_MAX; g++) pw[g] = ((uint32_t)g >= g0 && (uint32_t)g < g1) ? __ldg(a.packed + (cx >> 4) + g) : 0u;
+        for (uint32_t g = 0; g < g0; g++) edge_group(g, false);
+#pragma unroll
+        for (int gi = 0; gi < GPL_MAX; gi++) {
+            const uint32_t g = (uint32_t)gi;
+            if (g >= g0 && g < g1) {
+                uint32_t rm = 0;
+                open_group(g);
+                const uint32_t x = pw[gi];
                 if (g == gforce) prev = (~x & 3u) << 1;
                 // run starts of 16 bases: a base starts a run iff its code differs from the code before it
                 uint32_t m = 0x55555555u;
@@ -356,12 +365,22 @@ __device__ __forceinline__ void stage_chunk(const ScanArgs &a, uint64_t tlo, uin
                     const uint32_t b = (x >> (8 * w)) & 0xFFu;
                     uint32_t t = (b | (b << 12)) & 0x000F000Fu;                       // codes 0,1 | 2,3 into separate half-words
                     t = ((t | (t << 6)) & 0x03030303u) << SYM_SH;                     // one code per byte, pre-scaled
-                    const uint32_t p55 = (m >> (8 * w)) & 0x55u;
-                    const uint32_t comp = prmt(t, 0u, lds32(ta + 496 + 4 * p55));     // run-start bytes first, zero fill
-                    push(q, comp, __popc(p55) << 3);
+                    // table row of the byte's four run bits: PRMT selector | run bits << 16 | 8 * count << 24
+                    const uint32_t e = lds32(ta + 496 + ((m >> (8 * w)) & 0x55u) * 4u);
+                    push(q, prmt(t, 0u, e), e >> 24);                                 // run-start bytes first, zero fill
+                    rm |= ((e >> 16) & 0xFu) << (4 * w);
                 }
-                rm = m;
-            } else {
+                close_group(g, rm);
+            }
+        }
+        for (uint32_t g = g1; g < gpl; g++) edge_group(g, g == g1 && g1 > g0);
+    } else {
+        uint4 nxt = make_uint4(0, 0, 0, 0);
+        if (g0 < g1) nxt = src_u128<PACKED>(a, cx + 16 * g0);   // prefetch: one group ahead
+        for (uint32_t g = 0; g < gpl; g++) {
+            if (g >= g0 && g < g1) {
+                uint32_t rm = 0;
+                open_group(g);
                 const uint4 v = nxt;
                 if (g + 1 < g1) nxt = src_u128<PACKED>(a, cx + 16 * (g + 1));
                 if (g == gforce) prev = (v.x & 0xFFu) ^ 0xFFu;
@@ -381,29 +400,9 @@ __device__ __forceinline__ void stage_chunk(const ScanArgs &a, uint64_t tlo, uin
                     push(q, comp, __popc(p) << 3);
                     rm |= p << (4 * w);
                 }
-                if (PACKED) {                              // PACKED keeps its run masks at even bit positions
-                    uint32_t e = (rm | (rm << 8)) & 0x00FF00FFu; e = (e | (e << 4)) & 0x0F0F0F0Fu; e = (e | (e << 2)) & 0x33333333u;
-                    rm = (e | (e << 1)) & 0x55555555u;
-                }
-            }
-        } else {
-            const uint32_t xg = c_lo + 16 * g;
-            if (xg < own_hi && xg + 16 > own_lo) {       // cut by a record boundary
-                if (FASTP && g > 0 && g - 1 >= g0 && g - 1 < g1) prev = prmt(0x47544341u, 0u, (prev >> 1) & 3u);   // code -> letter
-                const uint4 v = src_u128<PACKED>(a, cx + 16 * g);
-                const uint32_t uw[4] = {v.x, v.y, v.z, v.w};
-                const bool rec_start = tlo + own_lo == gs;
-#pragma unroll
-                for (int w = 0; w < 4; w++) stage_cut_word<HPC, FLAG>(uw[w], prev, xg + 4 * w, own_lo, own_hi, rec_start, ta, q, rm, bad, w);
-                if (PACKED) {
-                    uint32_t e = (rm | (rm << 8)) & 0x00FF00FFu; e = (e | (e << 4)) & 0x0F0F0F0Fu; e = (e | (e << 2)) & 0x33333333u;
-                    rm = (e | (e << 1)) & 0x55555555u;
-                }
-            }
+                close_group(g, rm);
+            } else edge_group(g, false);
         }
-        if (PACKED) { sts32(ra, rm); ra += 128u; }
-        else { sts16(ra, rm); ra += (g & 1u) ? 126u : 2u; }
-        ca += ((g & 3u) == 3u) ? 125u : 1u;
     }
     bad_out = bad;
 }
@@ -428,7 +427,7 @@ __device__ __forceinline__ void step_generic(Hash2 &s, uint32_t sb, int o, int l
         const uint32_t cpz = cq + ck;                                                                         \
         sts32(cpz, fmin ? H.flo : H.rlo); sts32(cpz - 128u, min(H.fhi, H.rhi)); sts32(cpz - 256u, (uint32_t)(ORD)); \
         cq -= 384u;                                                                                           \
-        if (cq <= (LIVE)) { nloc = flush_candidates<PACKED>(ctop, cq + ck, nloc, runm_l, cum_l, c_lo, xlo, xlim, lane, ev_a, tile, a, bound, o2, evh, evm); cq = ctop - ck; } \
+        if (cq <= (LIVE)) { nloc = flush_candidates(ctop, cq + ck, nloc, runm_l, cum_l, c_lo, xlo, xlim, lane, ev_a, tile, a, bound, o2, evh, evm); cq = ctop - ck; } \
     }
 
 // HPC and the input format are compile-time flags (four instantiations)
@@ -442,12 +441,12 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32, 32 / SCAN_WARPS) k_scan_minim
     if (threadIdx.x == 0) { T.opq[0] = 0x80000000u; T.opq[1] = 2u; T.opq[2] = (uint32_t)(a.bound >> 32); T.opq[3] = smem_addr(&T); }
     __syncthreads();
     const uint32_t lane = lane_id(), wid = threadIdx.x >> 5;
-    const uint32_t ws_a = smem_addr(smem_raw + (size_t)wid * warp_bytes(PACKED));
+    const uint32_t ws_a = smem_addr(smem_raw + (size_t)wid * WARP_BYTES);
     const uint32_t sb = ws_a + 4 * lane;                              // my stream: column `lane` of the rows
     const uint32_t ha = ws_a + OFF_HALO;
     const uint32_t nsym_a = ws_a + OFF_NSYM;
     const uint32_t runm_l = ws_a + OFF_RUNM + 4 * lane;
-    const uint32_t cum_l = ws_a + off_cum(PACKED) + 4 * lane;
+    const uint32_t cum_l = ws_a + OFF_CUM + 4 * lane;
     const uint32_t ctop = sb + CAND_TOP;                              // first candidate slot: the top row of my column
     // right neighbour's stream: column lane+1, or the contiguous halo for lane 31
     const uint32_t nb_a = lane < 31 ? sb + 4 : ha, nb_st = lane < 31 ? 128u : 4u;
@@ -648,7 +647,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32, 32 / SCAN_WARPS) k_scan_minim
                 hash_step(H, f0, r0); MQ_CANDIDATE(4 * w, wa)
             }
         }
-        if (cq != ctop - ck) nloc = flush_candidates<PACKED>(ctop, cq + ck, nloc, runm_l, cum_l, c_lo, xlo, xlim, lane, ev_a, tile, a, bound, o2, evh, evm);
+        if (cq != ctop - ck) nloc = flush_candidates(ctop, cq + ck, nloc, runm_l, cum_l, c_lo, xlo, xlim, lane, ev_a, tile, a, bound, o2, evh, evm);
         __syncwarp();
         a.lane_cnt[(uint64_t)tile * 32 + lane] = (uint16_t)nloc;
         if (lane == 0) a.tile_cnt[tile] = lds32(ev_a);
