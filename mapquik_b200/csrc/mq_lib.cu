@@ -419,11 +419,16 @@ int init_streams(mq_ctx *c) {
 // Stage pieces [i0, i1) into slot s: build offsets + tile tables on the host, upload sequence slice and tables on the
 // copy stream.  The slice of the caller's array starts at `origin` (16-base aligned for ASCII, 2048 for packed), piece
 // offsets are relative to it.  Fills bd.
-int stage_pieces(mq_ctx *c, Slot2 &s, const SeqInput &in, const Piece *pc, uint32_t i0, uint32_t i1, uint32_t min_len, bool pieces,
-                 BatchDev &bd) {
+// Records are either pieces pc[i0..i1) or, when pc is NULL, the plain records offs[i] .. offs[i+1] (the mapping path:
+// no per-call piece array for millions of reads).
+int stage_pieces(mq_ctx *c, Slot2 &s, const SeqInput &in, const Piece *pc, const uint64_t *offs, uint32_t i0, uint32_t i1, uint32_t min_len,
+                 bool pieces, BatchDev &bd) {
     const uint32_t n = i1 - i0;
+    auto rec_lo = [&](uint32_t i) { return pc ? pc[i].lo : offs[i]; };
+    auto rec_hi = [&](uint32_t i) { return pc ? pc[i].hi : offs[i + 1]; };
     uint64_t lo = ~0ull, hi = 0;
-    for (uint32_t i = i0; i < i1; i++) { lo = std::min(lo, pc[i].lo); hi = std::max(hi, pc[i].hi); }
+    if (pc) for (uint32_t i = i0; i < i1; i++) { lo = std::min(lo, pc[i].lo); hi = std::max(hi, pc[i].hi); }
+    else if (n) { lo = offs[i0]; hi = offs[i1]; }
     if (n == 0 || lo > hi) { lo = hi = 0; }
     const uint64_t origin = in.packed ? (lo & ~2047ull) : (lo & ~15ull);
     // exception intervals overlapping the slice
@@ -436,7 +441,7 @@ int stage_pieces(mq_ctx *c, Slot2 &s, const SeqInput &in, const Piece *pc, uint3
     const size_t flag_words = (in.packed && !in.resident) ? (size_t)((hi - origin + 2047) / 2048 + 1) : 0;
     // tile counts first (they size the meta block)
     uint64_t n_tiles64 = 0;
-    for (uint32_t i = i0; i < i1; i++) n_tiles64 += tiles_of_record(pc[i].lo - origin, pc[i].hi - origin, min_len);
+    for (uint32_t i = i0; i < i1; i++) n_tiles64 += tiles_of_record(rec_lo(i) - origin, rec_hi(i) - origin, min_len);
     if (n_tiles64 >= (1ull << 31)) { c->err = "batch too large (tile count)"; return MQ_ERR_RANGE; }
     const uint32_t n_tiles = (uint32_t)n_tiles64;
     const MetaLayout ml(n, n_tiles, pieces, flag_words, (size_t)(e1 - e0));
@@ -452,15 +457,15 @@ int stage_pieces(mq_ctx *c, Slot2 &s, const SeqInput &in, const Piece *pc, uint3
     // n+1 boundaries only when contiguous.  Segment batches therefore hold ONE piece each (see add_pieces).
     uint32_t t = 0;
     for (uint32_t i = 0; i < n; i++) {
-        const Piece &q = pc[i0 + i];
-        h_offs[i] = q.lo - origin;
+        const uint64_t qlo = rec_lo(i0 + i) - origin, qhi = rec_hi(i0 + i) - origin;
+        h_offs[i] = qlo;
         h_ft[i] = t;
-        const uint32_t nt = tiles_of_record(q.lo - origin, q.hi - origin, min_len);
+        const uint32_t nt = tiles_of_record(qlo, qhi, min_len);
         for (uint32_t k = 0; k < nt; k++) h_ts[t + k] = i;
         t += nt;
-        if (pieces) { h_pb[i] = q.pos_base; h_em[2 * i] = q.emit_lo; h_em[2 * i + 1] = q.emit_hi; }
+        if (pieces) { const Piece &q = pc[i0 + i]; h_pb[i] = q.pos_base; h_em[2 * i] = q.emit_lo; h_em[2 * i + 1] = q.emit_hi; }
     }
-    h_offs[n] = n ? pc[i1 - 1].hi - origin : 0;
+    h_offs[n] = n ? rec_hi(i1 - 1) - origin : 0;
     h_ft[n] = t;
     if (flag_words) memcpy(hm + ml.flags, in.flags + (origin >> 11), flag_words * 4);
     if (e1 > e0) {
@@ -533,16 +538,16 @@ int map_pipeline(mq_ctx *c, const SeqInput &in, const uint64_t *offs, uint32_t n
     int rc;
     if ((rc = init_streams(c))) return rc;
     // sub-batch boundaries
+    // sub-batch boundaries; the first one is an eighth of the size so that the GPU starts while the host prepares the next
     std::vector<uint32_t> cut{0};
     const uint64_t sub = (in.packed || in.resident) ? SUB_BASES_LIGHT : SUB_BASES;
     for (uint32_t i0 = 0; i0 < n;) {
-        uint32_t i1 = i0 + 1;
-        while (i1 < n && offs[i1 + 1] - offs[i0] <= sub) i1++;
+        const uint64_t want = offs[i0] + (i0 == 0 ? sub / 8 : sub);
+        uint32_t i1 = (uint32_t)(std::upper_bound(offs + i0 + 1, offs + n + 1, want) - offs) - 1;
+        if (i1 <= i0) i1 = i0 + 1;
         cut.push_back(i1); i0 = i1;
     }
     const size_t ns = cut.size() - 1;
-    std::vector<Piece> pieces(n);
-    for (uint32_t i = 0; i < n; i++) pieces[i] = Piece{offs[i], offs[i + 1], 0, 0, 0, 0, 0};
     const uint32_t min_len = c->p.l + c->p.k - 1;
 
     // finish the sub-batch a slot holds: wait for its hits, look at its status, redo it if a buffer was too small
@@ -577,7 +582,7 @@ int map_pipeline(mq_ctx *c, const SeqInput &in, const uint64_t *offs, uint32_t n
         if ((rc = retire(s))) return rc;
         const uint32_t m = cut[i + 1] - cut[i];
         BatchDev bd;
-        if ((rc = stage_pieces(c, s, in, pieces.data(), cut[i], cut[i + 1], min_len, false, bd))) return rc;
+        if ((rc = stage_pieces(c, s, in, nullptr, offs, cut[i], cut[i + 1], min_len, false, bd))) return rc;
         if ((rc = ensure_workspace(c, m, bd.n_tiles, bd.bases, true))) return rc;
         HitRec *dh;
         if (d_out) dh = (HitRec *)d_out + cut[i];
@@ -678,7 +683,7 @@ int add_pieces(mq_ctx *c, const SeqInput &in, std::vector<Piece> &pcs, std::vect
     auto stage = [&](size_t b) -> int {
         const bool seg = pcs[bt[b][0]].emit_hi != 0;
         BatchDev bd;
-        return stage_pieces(c, c->slot[b & 1], in, pcs.data(), (uint32_t)bt[b][0], (uint32_t)bt[b][1], seg ? 0 : c->p.l + c->p.k - 1, seg, bd);
+        return stage_pieces(c, c->slot[b & 1], in, pcs.data(), nullptr, (uint32_t)bt[b][0], (uint32_t)bt[b][1], seg ? 0 : c->p.l + c->p.k - 1, seg, bd);
     };
     if (!bt.empty() && (rc = stage(0))) return rc;
     for (size_t b = 0; b < bt.size(); b++) {
@@ -1445,9 +1450,7 @@ static int scan_batch_sync(mq_ctx *c, const SeqInput &in, const uint64_t *offs, 
                            std::vector<uint32_t> *so) {
     int rc;
     if ((rc = init_streams(c))) return rc;
-    std::vector<Piece> pcs(n);
-    for (uint32_t i = 0; i < n; i++) pcs[i] = Piece{offs[i], offs[i + 1], 0, 0, 0, 0, 0};
-    if ((rc = stage_pieces(c, c->slot[0], in, pcs.data(), 0, n, min_len, false, bd))) return rc;
+    if ((rc = stage_pieces(c, c->slot[0], in, nullptr, offs, 0, n, min_len, false, bd))) return rc;
     return scan_sync(c, c->slot[0], bd, M, so);
 }
 

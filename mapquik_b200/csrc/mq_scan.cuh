@@ -168,20 +168,29 @@ __device__ __forceinline__ bool block_flag(const ScanArgs &a, uint64_t x) {
     const uint64_t blk = x >> 6;
     return (__ldg(a.flags + (blk >> 5)) >> (blk & 31)) & 1u;
 }
-// four bytes at the 4-aligned base index x
-template <bool PACKED> __device__ __forceinline__ uint32_t src_u32(const ScanArgs &a, uint64_t x) {
-    if (!PACKED) return __ldg((const uint32_t *)(a.seqs + x));
+// The packed decoders are deliberately NOT inlined: they serve the rare paths only (record edges, tiles with a non-ACGT
+// byte, the halo), and inlined copies at every call site made the packed kernel 70 % larger than the ASCII one -- enough
+// to stall its warps on instruction fetch (ncu: 3.9 warps per issue waiting for "no instruction").
+__device__ __noinline__ uint32_t packed_u32(const ScanArgs &a, uint64_t x) {
     const uint32_t w = __ldg(a.packed + (x >> 4));
     uint32_t u = decode4(w >> (2u * ((uint32_t)x & 15u)));
     if (block_flag(a, x)) u = overlay4(a, x, u);
     return u;
 }
-template <bool PACKED> __device__ __forceinline__ uint4 src_u128(const ScanArgs &a, uint64_t x) {
-    if (!PACKED) return __ldg((const uint4 *)(a.seqs + x));
+__device__ __noinline__ uint4 packed_u128(const ScanArgs &a, uint64_t x) {
     const uint32_t w = __ldg(a.packed + (x >> 4));
     uint4 v = make_uint4(decode4(w), decode4(w >> 8), decode4(w >> 16), decode4(w >> 24));
     if (block_flag(a, x)) { v.x = overlay4(a, x, v.x); v.y = overlay4(a, x + 4, v.y); v.z = overlay4(a, x + 8, v.z); v.w = overlay4(a, x + 12, v.w); }
     return v;
+}
+// four bytes at the 4-aligned base index x
+template <bool PACKED> __device__ __forceinline__ uint32_t src_u32(const ScanArgs &a, uint64_t x) {
+    if (!PACKED) return __ldg((const uint32_t *)(a.seqs + x));
+    return packed_u32(a, x);
+}
+template <bool PACKED> __device__ __forceinline__ uint4 src_u128(const ScanArgs &a, uint64_t x) {
+    if (!PACKED) return __ldg((const uint4 *)(a.seqs + x));
+    return packed_u128(a, x);
 }
 template <bool PACKED> __device__ __forceinline__ uint32_t src_u8(const ScanArgs &a, uint64_t x) {
     if (!PACKED) return a.seqs[x];
@@ -298,6 +307,25 @@ __device__ __forceinline__ void stage_cut_word(uint32_t u, uint32_t &prev, uint3
     rm |= p << (4 * w);
 }
 
+// What the packed fast path wants in flight before the block-bitmap vote decides that the tile may take it: the word
+// before the chunk (its top code is the run context) and the first two words of the chunk's in-record groups.
+struct PackedPre { uint32_t w_prev = 0, w0 = 0, w1 = 0; };
+__device__ __forceinline__ PackedPre packed_prefetch(const ScanArgs &a, uint64_t tlo, uint64_t gs, uint32_t c_lo, uint32_t gpl, uint32_t own_lo,
+                                                     uint32_t own_hi) {
+    PackedPre p;
+    const uint32_t Cs = gpl << 4;
+    const uint64_t cx = tlo + c_lo;
+    const uint32_t *wp = a.packed + (cx >> 4);
+    if ((c_lo > own_lo && c_lo < own_hi) || (c_lo == own_lo && tlo + own_lo > gs)) p.w_prev = __ldg(wp - 1);
+    const uint32_t lo_x = max(own_lo, c_lo), hi_x = min(own_hi, c_lo + Cs);
+    if (lo_x < hi_x) {
+        const uint32_t g0 = (lo_x - c_lo + 15) >> 4, g1 = (hi_x - c_lo) >> 4;
+        if (g0 < g1) p.w0 = __ldg(wp + g0);
+        if (g0 + 1 < g1) p.w1 = __ldg(wp + g0 + 1);
+    }
+    return p;
+}
+
 // Stage + compact one lane chunk; leaves the append cursor in q (pending word NOT yet stored).
 // Groups [g0, g1) lie completely inside the record: fast path.  The (at most two) groups cut by a record boundary go
 // through stage_cut_word; groups outside the record hold no symbol.
@@ -307,14 +335,15 @@ __device__ __forceinline__ void stage_cut_word(uint32_t u, uint32_t &prev, uint3
 template <bool HPC, bool PACKED, bool FLAG>
 __device__ __forceinline__ void stage_chunk(const ScanArgs &a, uint64_t tlo, uint64_t gs, uint32_t c_lo, uint32_t gpl, uint32_t own_lo,
                                             uint32_t own_hi, uint32_t sb, uint32_t cum_l, uint32_t runm_l, uint32_t ta,
-                                            Pend &q, uint32_t &bad_out) {
+                                            Pend &q, uint32_t &bad_out, const PackedPre &pre = PackedPre{}) {
     const uint32_t Cs = gpl << 4;
     uint32_t bad = 0;
     q.P = 0; q.n8 = 0; q.wp = sb;
     const uint64_t cx = tlo + c_lo;                      // base index of my first byte
-    uint32_t prev = 0;                                   // byte before the next word (ASCII letter)
-    if (c_lo > own_lo && c_lo < own_hi) prev = src_u8<PACKED>(a, cx - 1);  // byte before my chunk (same record)
-    else if (c_lo == own_lo && tlo + own_lo > gs) prev = src_u8<PACKED>(a, cx - 1);
+    uint32_t prev = 0;                                   // byte before the next word (ASCII letter; packed fast path: code << 1)
+    constexpr bool FASTP = PACKED && !FLAG;              // packed fast path: 2-bit arithmetic, no byte reconstruction
+    if ((c_lo > own_lo && c_lo < own_hi) || (c_lo == own_lo && tlo + own_lo > gs))     // byte before my chunk (same record)
+        prev = FASTP ? (pre.w_prev >> 30) << 1 : src_u8<PACKED>(a, cx - 1);
     // a record that starts exactly at one of my group boundaries starts a run whatever the byte before it was
     const uint32_t gforce = (tlo + own_lo == gs && own_lo >= c_lo && own_lo < c_lo + Cs && ((own_lo - c_lo) & 15u) == 0u)
                                 ? (own_lo - c_lo) >> 4 : 0xFFFFFFFFu;
@@ -323,7 +352,6 @@ __device__ __forceinline__ void stage_chunk(const ScanArgs &a, uint64_t tlo, uin
     const uint32_t lo_x = max(own_lo, c_lo), hi_x = min(own_hi, c_lo + Cs);
     uint32_t g0 = gpl, g1 = gpl;
     if (lo_x < hi_x) { g0 = (lo_x - c_lo + 15) >> 4; g1 = (hi_x - c_lo) >> 4; if (g1 < g0) g1 = g0; }
-    constexpr bool FASTP = PACKED && !FLAG;              // packed fast path: 2-bit arithmetic, no byte reconstruction
     // bookkeeping of group g: symbol count before it (cum), its 16 run bits (runm); both row-interleaved
     auto open_group = [&](uint32_t g) { sts8(cum_l + (g >> 2) * 128u + (g & 3u), q.n8 >> 3); };
     auto close_group = [&](uint32_t g, uint32_t rm) { sts16(runm_l + (g >> 1) * 128u + (g & 1u) * 2u, rm); };
@@ -343,18 +371,16 @@ __device__ __forceinline__ void stage_chunk(const ScanArgs &a, uint64_t tlo, uin
         close_group(g, rm);
     };
     if (FASTP) {
-        // the whole chunk (<= GPL_MAX words) is requested up front; only this part is unrolled
-        uint32_t pw[GPL_MAX];
-#pragma unroll
-        for (int g = 0; g < GPL_MAX; g++) pw[g] = ((uint32_t)g >= g0 && (uint32_t)g < g1) ? __ldg(a.packed + (cx >> 4) + g) : 0u;
-        for (uint32_t g = 0; g < g0; g++) edge_group(g, false);
-#pragma unroll
-        for (int gi = 0; gi < GPL_MAX; gi++) {
-            const uint32_t g = (uint32_t)gi;
+        // two words (32 bases) ahead; the first two arrive prefetched (requested before the bitmap vote)
+        const uint32_t *wp = a.packed + (cx >> 4);
+        uint32_t nx0 = pre.w0, nx1 = pre.w1;
+        for (uint32_t g = 0; g < gpl; g++) {
             if (g >= g0 && g < g1) {
                 uint32_t rm = 0;
                 open_group(g);
-                const uint32_t x = pw[gi];
+                const uint32_t x = nx0;
+                nx0 = nx1;
+                if (g + 2 < g1) nx1 = __ldg(wp + g + 2);
                 if (g == gforce) prev = (~x & 3u) << 1;
                 // run starts of 16 bases: a base starts a run iff its code differs from the code before it
                 uint32_t m = 0x55555555u;
@@ -371,9 +397,8 @@ __device__ __forceinline__ void stage_chunk(const ScanArgs &a, uint64_t tlo, uin
                     rm |= ((e >> 16) & 0xFu) << (4 * w);
                 }
                 close_group(g, rm);
-            }
+            } else edge_group(g, g == g1 && g1 > g0);
         }
-        for (uint32_t g = g1; g < gpl; g++) edge_group(g, g == g1 && g1 > g0);
     } else {
         uint4 nxt = make_uint4(0, 0, 0, 0);
         if (g0 < g1) nxt = src_u128<PACKED>(a, cx + 16 * g0);   // prefetch: one group ahead
@@ -490,8 +515,9 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32, 32 / SCAN_WARPS) k_scan_minim
         if (PACKED) {
             // the block bitmap decides: my chunk and the byte before it, clipped to the record
             const uint64_t r0 = max(tlo + c_lo, gs + 1) - 1, r1 = min(tlo + c_lo + Cs, ge);
+            const PackedPre pre = packed_prefetch(a, tlo, gs, c_lo, gpl, own_lo, own_hi);     // in flight while the bitmap is read
             generic = __any_sync(0xffffffffu, any_flag(a, r0, r1));
-            if (!generic) stage_chunk<HPC, true, false>(a, tlo, gs, c_lo, gpl, own_lo, own_hi, sb, cum_l, runm_l, ta, q, bad);
+            if (!generic) stage_chunk<HPC, true, false>(a, tlo, gs, c_lo, gpl, own_lo, own_hi, sb, cum_l, runm_l, ta, q, bad, pre);
         } else {
             stage_chunk<HPC, false, false>(a, tlo, gs, c_lo, gpl, own_lo, own_hi, sb, cum_l, runm_l, ta, q, bad);
             generic = __any_sync(0xffffffffu, bad != 0);       // some byte is not A/C/G/T: stage again with per-symbol flags
