@@ -307,25 +307,6 @@ __device__ __forceinline__ void stage_cut_word(uint32_t u, uint32_t &prev, uint3
     rm |= p << (4 * w);
 }
 
-// What the packed fast path wants in flight before the block-bitmap vote decides that the tile may take it: the word
-// before the chunk (its top code is the run context) and the first two words of the chunk's in-record groups.
-struct PackedPre { uint32_t w_prev = 0, w0 = 0, w1 = 0; };
-__device__ __forceinline__ PackedPre packed_prefetch(const ScanArgs &a, uint64_t tlo, uint64_t gs, uint32_t c_lo, uint32_t gpl, uint32_t own_lo,
-                                                     uint32_t own_hi) {
-    PackedPre p;
-    const uint32_t Cs = gpl << 4;
-    const uint64_t cx = tlo + c_lo;
-    const uint32_t *wp = a.packed + (cx >> 4);
-    if ((c_lo > own_lo && c_lo < own_hi) || (c_lo == own_lo && tlo + own_lo > gs)) p.w_prev = __ldg(wp - 1);
-    const uint32_t lo_x = max(own_lo, c_lo), hi_x = min(own_hi, c_lo + Cs);
-    if (lo_x < hi_x) {
-        const uint32_t g0 = (lo_x - c_lo + 15) >> 4, g1 = (hi_x - c_lo) >> 4;
-        if (g0 < g1) p.w0 = __ldg(wp + g0);
-        if (g0 + 1 < g1) p.w1 = __ldg(wp + g0 + 1);
-    }
-    return p;
-}
-
 // Stage + compact one lane chunk; leaves the append cursor in q (pending word NOT yet stored).
 // Groups [g0, g1) lie completely inside the record: fast path.  The (at most two) groups cut by a record boundary go
 // through stage_cut_word; groups outside the record hold no symbol.
@@ -335,15 +316,15 @@ __device__ __forceinline__ PackedPre packed_prefetch(const ScanArgs &a, uint64_t
 template <bool HPC, bool PACKED, bool FLAG>
 __device__ __forceinline__ void stage_chunk(const ScanArgs &a, uint64_t tlo, uint64_t gs, uint32_t c_lo, uint32_t gpl, uint32_t own_lo,
                                             uint32_t own_hi, uint32_t sb, uint32_t cum_l, uint32_t runm_l, uint32_t ta,
-                                            Pend &q, uint32_t &bad_out, const PackedPre &pre = PackedPre{}) {
+                                            Pend &q, uint32_t &bad_out) {
     const uint32_t Cs = gpl << 4;
     uint32_t bad = 0;
     q.P = 0; q.n8 = 0; q.wp = sb;
     const uint64_t cx = tlo + c_lo;                      // base index of my first byte
-    uint32_t prev = 0;                                   // byte before the next word (ASCII letter; packed fast path: code << 1)
+    uint32_t prev = 0;                                   // byte before the next word (ASCII letter)
     constexpr bool FASTP = PACKED && !FLAG;              // packed fast path: 2-bit arithmetic, no byte reconstruction
     if ((c_lo > own_lo && c_lo < own_hi) || (c_lo == own_lo && tlo + own_lo > gs))     // byte before my chunk (same record)
-        prev = FASTP ? (pre.w_prev >> 30) << 1 : src_u8<PACKED>(a, cx - 1);
+        prev = src_u8<PACKED>(a, cx - 1);
     // a record that starts exactly at one of my group boundaries starts a run whatever the byte before it was
     const uint32_t gforce = (tlo + own_lo == gs && own_lo >= c_lo && own_lo < c_lo + Cs && ((own_lo - c_lo) & 15u) == 0u)
                                 ? (own_lo - c_lo) >> 4 : 0xFFFFFFFFu;
@@ -371,16 +352,14 @@ __device__ __forceinline__ void stage_chunk(const ScanArgs &a, uint64_t tlo, uin
         close_group(g, rm);
     };
     if (FASTP) {
-        // two words (32 bases) ahead; the first two arrive prefetched (requested before the bitmap vote)
         const uint32_t *wp = a.packed + (cx >> 4);
-        uint32_t nx0 = pre.w0, nx1 = pre.w1;
+        uint32_t nxw = g0 < g1 ? __ldg(wp + g0) : 0u;          // prefetch: one word (16 bases) ahead
         for (uint32_t g = 0; g < gpl; g++) {
             if (g >= g0 && g < g1) {
                 uint32_t rm = 0;
                 open_group(g);
-                const uint32_t x = nx0;
-                nx0 = nx1;
-                if (g + 2 < g1) nx1 = __ldg(wp + g + 2);
+                const uint32_t x = nxw;
+                if (g + 1 < g1) nxw = __ldg(wp + g + 1);
                 if (g == gforce) prev = (~x & 3u) << 1;
                 // run starts of 16 bases: a base starts a run iff its code differs from the code before it
                 uint32_t m = 0x55555555u;
@@ -515,9 +494,8 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32, 32 / SCAN_WARPS) k_scan_minim
         if (PACKED) {
             // the block bitmap decides: my chunk and the byte before it, clipped to the record
             const uint64_t r0 = max(tlo + c_lo, gs + 1) - 1, r1 = min(tlo + c_lo + Cs, ge);
-            const PackedPre pre = packed_prefetch(a, tlo, gs, c_lo, gpl, own_lo, own_hi);     // in flight while the bitmap is read
             generic = __any_sync(0xffffffffu, any_flag(a, r0, r1));
-            if (!generic) stage_chunk<HPC, true, false>(a, tlo, gs, c_lo, gpl, own_lo, own_hi, sb, cum_l, runm_l, ta, q, bad, pre);
+            if (!generic) stage_chunk<HPC, true, false>(a, tlo, gs, c_lo, gpl, own_lo, own_hi, sb, cum_l, runm_l, ta, q, bad);
         } else {
             stage_chunk<HPC, false, false>(a, tlo, gs, c_lo, gpl, own_lo, own_hi, sb, cum_l, runm_l, ta, q, bad);
             generic = __any_sync(0xffffffffu, bad != 0);       // some byte is not A/C/G/T: stage again with per-symbol flags
