@@ -194,7 +194,8 @@ def run_reference(args, cfg, rank):
         "impl": "reference", "metric": "reads/sec mapped (seeding->chaining hot path)", "value": rps, "unit": "reads/s",
         "n_gpus": args.gpus, "ranks_working": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": cfg["scaling"], "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": cfg["workload"], "k": 5, "l": 31, "density": 0.01, "hpc": True, "reads_per_step": n_sample},
+        "config": {"workload": cfg["workload"], "reads_total": cfg["n_reads"], "k": 5, "l": 31, "density": 0.01, "hpc": True},
+        "reads_per_step": n_sample,
         "gbp_per_s": float(ro[-1]) / dt / 1e9, "index_build_s": t_index,
         "cpu_baseline": {"value": rps, "unit": "reads/s", "cores": threads, "kind": "port",
                          "sample": f"first {n_sample} of the workload's {cfg['n_reads']} reads per step ({float(ro[-1]) / 1e9:.2f} Gbp), all host "
@@ -308,7 +309,9 @@ def main():
 
     # ---- workload ---------------------------------------------------------------------------------------------------
     t_gen = time.perf_counter()
-    g, go, names = make_genome(cfg)
+    g0, go, names = make_genome(cfg)
+    g, pg = pinned_array(L, g0.size + 64)                      # the reference sits in pinned host memory, like the CLI's parser slots
+    g = g[:g0.size]; g[:] = g0; del g0
     if cfg["scaling"] == "strong":
         total_reads = args.reads or cfg["n_reads"]
         lo, hi = total_reads * rank // world, total_reads * (rank + 1) // world
@@ -346,6 +349,19 @@ def main():
         ib = {"scan_s": tb - ta, "exchange_s": 0.0, "exchange_bytes": 0, "freeze_s": time.perf_counter() - tb}
     barrier()
     index_build_s = time.perf_counter() - t0
+    # the same build from the packed reference (what the CLI's packing parser hands over); second build: allocations are warm
+    index_build_packed_s = None
+    if world == 1:
+        pgen = PackedSeqs(g, n_threads=threads, pinned=True)
+        for rep_ in range(2):
+            ix2 = Index(p, device=local_rank)
+            t1 = time.perf_counter()
+            ix2.add_batch_packed(names, pgen, go)
+            nu2 = ix2.freeze()
+            index_build_packed_s = time.perf_counter() - t1
+            assert nu2 == n_unique and ix2.n_keys == ix.n_keys, "packed index build differs"
+            ix2.close()
+        pgen.close()
 
     # ---- device-resident inputs ---------------------------------------------------------------------------------
     d_hits = L.mq_dev_alloc(h, max(n_reads * 48, 16))
@@ -542,7 +558,7 @@ def main():
                        "input_format": "value: 2-bit packed reads resident in HBM; value_ascii: ASCII reads resident"},
             "gbp_per_s": gbps(t_dev),
             "value_ascii": rps(t_dev_ascii), "gbp_per_s_ascii": gbps(t_dev_ascii),
-            "index_build_s": index_build_s,
+            "index_build_s": index_build_s, "index_build_packed_s": index_build_packed_s,
             "index_build": {"scan_s": ib_scan, "exchange_s": ib_exch, "exchange_bytes": ib["exchange_bytes"], "freeze_s": ib_freeze,
                             "exchange_gb_per_s": (ib["exchange_bytes"] / ib_exch / 1e9) if ib_exch > 0 else None},
             "n_unique_kminmers": int(n_unique), "table_bytes": int(ix.table_bytes()),
@@ -579,7 +595,7 @@ def main():
             line["cpu_baseline"] = cpu_line
         print(json.dumps(line), flush=True)
 
-    for ptr in (p1, p2, p3):
+    for ptr in (p1, p2, p3, pg):
         L.mq_host_free(ptr)
     pk.close()
     for d in (d_seqs, d_hits, d_w, d_f, d_e):

@@ -28,7 +28,7 @@ def test_reference_arm_line():
     assert "workload" in d["config"] and "model" not in d["config"]
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert d["value"] > 0 and d["mapped_reads"] == 25000 and d["config"]["reads_per_step"] == 25000
+    assert d["value"] > 0 and d["mapped_reads"] == 25000 and d["reads_per_step"] == 25000
     assert d["upstream"]["found"] in (True, False)
 
 
