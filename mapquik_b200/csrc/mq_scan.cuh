@@ -273,10 +273,15 @@ __device__ __forceinline__ void emit_event(uint32_t x, uint64_t h, uint32_t lane
     }
 }
 
-// resolve and emit the candidates parked in rows (cpz, top] of the lane's column, oldest first
-__device__ __noinline__ uint32_t flush_candidates(uint32_t top, uint32_t cpz, uint32_t j0, uint32_t runm_l, uint32_t cum_l,
-                                                  uint32_t c_lo, uint32_t xlo, uint32_t xlim, uint32_t lane, uint32_t ev_a, uint32_t tile,
-                                                  const ScanArgs &a, uint64_t bound, int o2, uint64_t *evh, uint32_t *evm) {
+// Resolve and emit the candidates parked in rows (cpz, top] of the lane's column, oldest first.  Deliberately few
+// arguments: whatever can be re-derived from the warp's shared-memory base, the lane id and the kernel parameters is
+// re-derived here, so that it does not occupy registers across the hot loop (64-register budget).
+__device__ __noinline__ uint32_t flush_candidates(uint32_t ws_a, uint32_t cpz, uint32_t j0, uint32_t c_lo, uint32_t xlo, uint32_t xlim,
+                                                  uint32_t ev_a, uint32_t tile, const ScanArgs &a, int o2) {
+    const uint32_t lane = lane_id();
+    const uint32_t top = ws_a + 4 * lane + CAND_TOP, runm_l = ws_a + OFF_RUNM + 4 * lane, cum_l = ws_a + OFF_CUM + 4 * lane;
+    const uint64_t bound = a.bound;
+    uint64_t *const evh = a.ev_hash + (uint64_t)tile * EV_CAP; uint32_t *const evm = a.ev_meta + (uint64_t)tile * EV_CAP;
     uint32_t j = j0;
     for (uint32_t p = top; p > cpz; p -= 384u) {
         const uint64_t h = ((uint64_t)lds32(p - 128u) << 32) | lds32(p);
@@ -431,7 +436,7 @@ __device__ __forceinline__ void step_generic(Hash2 &s, uint32_t sb, int o, int l
         const uint32_t cpz = cq + ck;                                                                         \
         sts32(cpz, fmin ? H.flo : H.rlo); sts32(cpz - 128u, min(H.fhi, H.rhi)); sts32(cpz - 256u, (uint32_t)(ORD)); \
         cq -= 384u;                                                                                           \
-        if (cq <= (LIVE)) { nloc = flush_candidates(ctop, cq + ck, nloc, runm_l, cum_l, c_lo, xlo, xlim, lane, ev_a, tile, a, bound, o2, evh, evm); cq = ctop - ck; } \
+        if (cq <= (LIVE)) { nloc = flush_candidates(ws_a, cq + ck, nloc, c_lo, xlo, xlim, ev_a, tile, a, o2); cq = ctop - ck; } \
     }
 
 // HPC and the input format are compile-time flags (four instantiations)
@@ -457,10 +462,8 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32, 32 / SCAN_WARPS) k_scan_minim
     // scalars read back through volatile shared loads so that ptxas keeps them in registers instead of re-deriving
     // them (S2UR/ULEA/LDCU) inside the hot loop
     const uint32_t ta = lds32(smem_addr(&T) + 464 + 12);
-    const uint32_t bound_hi = lds32(ta + 464 + 8);
     const uint32_t ev_a = smem_addr(&ev_cnt[wid]);
     const uint32_t l = a.l;
-    const uint64_t bound = a.bound;
 
     for (;;) {
         uint32_t tile = 0;
@@ -485,7 +488,6 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32, 32 / SCAN_WARPS) k_scan_minim
         const uint32_t own_lo = gs > tlo ? (uint32_t)(gs - tlo) : 0u;
         const uint32_t own_hi = (ge - tlo) < TWs ? (uint32_t)(ge - tlo) : TWs;
         uint32_t xlo, xlim; emit_window(a, sq, gs, tlo, &xlo, &xlim);
-        uint64_t *const evh = a.ev_hash + (uint64_t)tile * EV_CAP; uint32_t *const evm = a.ev_meta + (uint64_t)tile * EV_CAP;
 
         // ---- stage + compact my chunk: one byte per homopolymer-run start ---------------------------
         const uint32_t c_lo = lane * Cs;                       // x' of my first byte
@@ -608,6 +610,9 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32, 32 / SCAN_WARPS) k_scan_minim
         H.flo = (uint32_t)st.F; H.fhi = (uint32_t)(st.F >> 32); H.rlo = (uint32_t)st.R; H.rhi = (uint32_t)(st.R >> 32);
         const uint32_t lr = (l >> 2) * 128u, ck = lr + 384u;
         uint32_t cq = ctop - ck;
+        // read here, per tile, so that its live range does not span the staging code: with the 64-register budget ptxas
+        // otherwise spills it and reloads it from local memory at every step of the hot loop (seen in the packed variant)
+        const uint32_t bound_hi = lds32(ta + 464 + 8);
         if (anyN) {
             const uint32_t live0 = sb + 128u * ((uint32_t)lim >> 2) + 256u - ck;   // everything up to row lim/4 stays live
             int o = lim - 1;
@@ -651,7 +656,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32, 32 / SCAN_WARPS) k_scan_minim
                 hash_step(H, f0, r0); MQ_CANDIDATE(4 * w, wa)
             }
         }
-        if (cq != ctop - ck) nloc = flush_candidates(ctop, cq + ck, nloc, runm_l, cum_l, c_lo, xlo, xlim, lane, ev_a, tile, a, bound, o2, evh, evm);
+        if (cq != ctop - ck) nloc = flush_candidates(ws_a, cq + ck, nloc, c_lo, xlo, xlim, ev_a, tile, a, o2);
         __syncwarp();
         a.lane_cnt[(uint64_t)tile * 32 + lane] = (uint16_t)nloc;
         if (lane == 0) a.tile_cnt[tile] = lds32(ev_a);
