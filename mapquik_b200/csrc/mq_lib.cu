@@ -102,6 +102,7 @@ struct mq_ctx {
     std::vector<std::array<uint64_t, 3>> dir;          // (ref_idx, seg_start, count)
     // frozen index
     DBuf d_table, d_ref_lens; uint64_t tmask = 0; bool frozen = false; uint32_t n_refs = 0;
+    DBuf d_bloom; uint32_t bloom_wmask = 0;      // presence filter in front of the table (mq_kernels.cuh), L2-resident
     std::vector<uint64_t> nb_mers; uint64_t n_unique = 0, n_keys = 0;
     HBuf h_pin;                   // bounce buffer (index save / load)
     // timings
@@ -368,7 +369,7 @@ int enqueue_probe_chain(mq_ctx *c, const BatchDev &b, HitRec *d_hits) {
         a.n_reads = n; a.k = c->p.k; a.l = c->p.l; a.matches = c->d_matches.as<MatchRec>(); a.n_matches = c->d_nmatch.as<uint32_t>();
         a.read_ticket = &b.sc->probe_ticket;
         const uint32_t grid = std::min<uint32_t>((n + 3) / 4, (uint32_t)c->n_sm * 16);
-        k_probe_match<<<grid, 128, 0, c->stream>>>(a, t);
+        k_probe_match<<<grid, 128, 0, c->stream>>>(a, t, Bloom{c->d_bloom.as<unsigned long long>(), c->bloom_wmask});
         c->launches++;
         CK(cudaGetLastError());
     }
@@ -750,7 +751,7 @@ static int create_one(mq_ctx **out, const mq_params *p, int device) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->n_sm = prop.multiProcessorCount;
     // random 32-byte probes into a multi-GB table: fetch one sector per miss, not two
-    cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32); cudaGetLastError();
+    cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32); cudaGetLastError();      // a hint; the device may keep its own
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return MQ_ERR_CUDA; }
     uint32_t warm[256][4];
     fill_warm_table(c->tab, warm);
@@ -808,7 +809,7 @@ void mq_destroy(mq_ctx *c) {
     timers_collect(c);
     DBuf *bufs[] = {&c->d_ev_hash, &c->d_ev_meta, &c->d_lane_cnt, &c->d_tile_cnt, &c->d_blk, &c->d_ovf_tile, &c->d_ovf_meta, &c->d_ovf_hash,
                     &c->d_pos, &c->d_hash, &c->d_seq_off, &c->d_matches, &c->d_nmatch, &c->d_big_list, &c->d_misc, &c->st_pos, &c->st_hash,
-                    &c->d_table, &c->d_ref_lens, &c->d_warm};
+                    &c->d_table, &c->d_ref_lens, &c->d_warm, &c->d_bloom};
     for (DBuf *b : bufs) dfree(*b);
     for (auto &s : c->slot) {
         dfree(s.d_in); dfree(s.d_meta); dfree(s.d_hits); dfree(s.d_sc); hfree(s.h_meta); hfree(s.h_sc);
@@ -1085,6 +1086,38 @@ int mq_store_import(mq_ctx *c, const void *d_pos, const void *d_hash, uint64_t n
 
 namespace {
 
+// Presence filter over the valid entries of the frozen table + an L2 access-policy window that keeps it resident.
+// ~6 bits per key (power of two), at least 8 KB.  MQ_NO_BLOOM=1 in the environment leaves it out (A/B measurements).
+int build_bloom(mq_ctx *c) {
+    dfree(c->d_bloom); c->bloom_wmask = 0;
+    if (const char *e = getenv("MQ_NO_BLOOM")) if (e[0] == '1') return MQ_OK;
+    uint64_t bits = 1ull << 16;
+    while (bits < 4 * c->n_unique && bits < (1ull << 33)) bits <<= 1;
+    const uint64_t words = bits / 64;
+    int rc;
+    if ((rc = ensure(c, c->d_bloom, words * 8))) return rc;
+    c->bloom_wmask = (uint32_t)(words - 1);
+    CK(cudaMemsetAsync(c->d_bloom.p, 0, words * 8, c->stream));
+    k_bloom_build<<<c->n_sm * 8, 256, 0, c->stream>>>(c->d_table.as<Slot>(), c->tmask + 2, c->d_bloom.as<unsigned long long>(), c->bloom_wmask);
+    c->launches++;
+    CK(cudaGetLastError());
+    // keep it in L2 while reads stream through: persisting lines for the filter, streaming for everything else on this stream
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, c->device) == cudaSuccess && prop.persistingL2CacheMaxSize > 0 && prop.accessPolicyMaxWindowSize > 0) {
+        const size_t want = std::min<size_t>(words * 8, (size_t)prop.persistingL2CacheMaxSize);
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+        cudaStreamAttrValue av{};
+        av.accessPolicyWindow.base_ptr = c->d_bloom.p;
+        av.accessPolicyWindow.num_bytes = std::min<size_t>(words * 8, (size_t)prop.accessPolicyMaxWindowSize);
+        av.accessPolicyWindow.hitRatio = want >= words * 8 ? 1.0f : (float)want / (float)(words * 8);
+        av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &av);
+        cudaGetLastError();
+    }
+    return MQ_OK;
+}
+
 // build the table of this context from its store (which must hold the minimizers of the WHOLE reference)
 int freeze_local(mq_ctx *c, const uint64_t *ref_lens, uint32_t n_refs) {
     cudaSetDevice(c->device);
@@ -1166,6 +1199,7 @@ int freeze_local(mq_ctx *c, const uint64_t *ref_lens, uint32_t n_refs) {
         CK(cudaMemcpyAsync(hc, d_cnt, 16, cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
         c->n_unique = hc[0]; c->n_keys = hc[1];
+        if ((rc = build_bloom(c))) return rc;
     }
     c->n_refs = n_refs; c->frozen = true;
     dfree(c->st_pos); dfree(c->st_hash); c->st_n = 0;
@@ -1345,6 +1379,8 @@ static int index_load_one(mq_ctx *c, const char *path, uint64_t *ref_lens_out, u
     if (h.n_refs && cudaMemcpy(c->d_ref_lens.p, lens.data(), h.n_refs * 8, cudaMemcpyHostToDevice) != cudaSuccess) { c->err = "H2D ref_lens"; return MQ_ERR_CUDA; }
     c->tmask = h.slots - 2; c->n_refs = (uint32_t)h.n_refs; c->n_unique = h.n_unique; c->n_keys = h.n_keys;
     c->nb_mers.assign(nb.begin(), nb.end());
+    if ((rc = build_bloom(c))) return rc;
+    CK(cudaStreamSynchronize(c->stream));
     c->frozen = true;
     return MQ_OK;
 }

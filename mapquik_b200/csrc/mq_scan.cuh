@@ -168,10 +168,10 @@ __device__ __forceinline__ bool block_flag(const ScanArgs &a, uint64_t x) {
     const uint64_t blk = x >> 6;
     return (__ldg(a.flags + (blk >> 5)) >> (blk & 31)) & 1u;
 }
-// The packed decoders are deliberately NOT inlined: they serve the rare paths only (record edges, tiles with a non-ACGT
-// byte, the halo), and inlined copies at every call site made the packed kernel 70 % larger than the ASCII one -- enough
+// The 16-base packed decoder is deliberately NOT inlined: it serves the rare paths only (record edges, tiles with a
+// non-ACGT byte), and inlined copies at every call site made the packed kernel 70 % larger than the ASCII one -- enough
 // to stall its warps on instruction fetch (ncu: 3.9 warps per issue waiting for "no instruction").
-__device__ __noinline__ uint32_t packed_u32(const ScanArgs &a, uint64_t x) {
+__device__ __forceinline__ uint32_t packed_u32(const ScanArgs &a, uint64_t x) {   // small, and inlined loads can overlap
     const uint32_t w = __ldg(a.packed + (x >> 4));
     uint32_t u = decode4(w >> (2u * ((uint32_t)x & 15u)));
     if (block_flag(a, x)) u = overlay4(a, x, u);
@@ -312,6 +312,22 @@ __device__ __forceinline__ void stage_cut_word(uint32_t u, uint32_t &prev, uint3
     rm |= p << (4 * w);
 }
 
+// What the packed fast path wants in flight BEFORE the block-bitmap vote decides that the tile may take it (otherwise the
+// bitmap read, the context word and the first data word are three exposed memory latencies in a row): the word before
+// the chunk (its top code is the run context) and the first word of the chunk's in-record groups.
+__device__ __forceinline__ void packed_prefetch(const ScanArgs &a, uint64_t tlo, uint64_t gs, uint32_t c_lo, uint32_t gpl, uint32_t own_lo,
+                                                uint32_t own_hi, uint32_t &w_prev, uint32_t &w0) {
+    const uint32_t Cs = gpl << 4;
+    const uint32_t *wp = a.packed + ((tlo + c_lo) >> 4);
+    w_prev = 0; w0 = 0;
+    if ((c_lo > own_lo && c_lo < own_hi) || (c_lo == own_lo && tlo + own_lo > gs)) w_prev = __ldg(wp - 1);
+    const uint32_t lo_x = max(own_lo, c_lo), hi_x = min(own_hi, c_lo + Cs);
+    if (lo_x < hi_x) {
+        const uint32_t g0 = (lo_x - c_lo + 15) >> 4, g1 = (hi_x - c_lo) >> 4;
+        if (g0 < g1) w0 = __ldg(wp + g0);
+    }
+}
+
 // Stage + compact one lane chunk; leaves the append cursor in q (pending word NOT yet stored).
 // Groups [g0, g1) lie completely inside the record: fast path.  The (at most two) groups cut by a record boundary go
 // through stage_cut_word; groups outside the record hold no symbol.
@@ -321,7 +337,7 @@ __device__ __forceinline__ void stage_cut_word(uint32_t u, uint32_t &prev, uint3
 template <bool HPC, bool PACKED, bool FLAG>
 __device__ __forceinline__ void stage_chunk(const ScanArgs &a, uint64_t tlo, uint64_t gs, uint32_t c_lo, uint32_t gpl, uint32_t own_lo,
                                             uint32_t own_hi, uint32_t sb, uint32_t cum_l, uint32_t runm_l, uint32_t ta,
-                                            Pend &q, uint32_t &bad_out) {
+                                            Pend &q, uint32_t &bad_out, uint32_t pre_prev = 0, uint32_t pre_w0 = 0) {
     const uint32_t Cs = gpl << 4;
     uint32_t bad = 0;
     q.P = 0; q.n8 = 0; q.wp = sb;
@@ -329,7 +345,7 @@ __device__ __forceinline__ void stage_chunk(const ScanArgs &a, uint64_t tlo, uin
     uint32_t prev = 0;                                   // byte before the next word (ASCII letter)
     constexpr bool FASTP = PACKED && !FLAG;              // packed fast path: 2-bit arithmetic, no byte reconstruction
     if ((c_lo > own_lo && c_lo < own_hi) || (c_lo == own_lo && tlo + own_lo > gs))     // byte before my chunk (same record)
-        prev = src_u8<PACKED>(a, cx - 1);
+        prev = FASTP ? prmt(0x47544341u, 0u, 0x4440u | (pre_prev >> 30)) : src_u8<PACKED>(a, cx - 1);   // fast path: its word came prefetched
     // a record that starts exactly at one of my group boundaries starts a run whatever the byte before it was
     const uint32_t gforce = (tlo + own_lo == gs && own_lo >= c_lo && own_lo < c_lo + Cs && ((own_lo - c_lo) & 15u) == 0u)
                                 ? (own_lo - c_lo) >> 4 : 0xFFFFFFFFu;
@@ -358,7 +374,7 @@ __device__ __forceinline__ void stage_chunk(const ScanArgs &a, uint64_t tlo, uin
     };
     if (FASTP) {
         const uint32_t *wp = a.packed + (cx >> 4);
-        uint32_t nxw = g0 < g1 ? __ldg(wp + g0) : 0u;          // prefetch: one word (16 bases) ahead
+        uint32_t nxw = pre_w0;                                 // one word (16 bases) ahead; the first one came prefetched
         for (uint32_t g = 0; g < gpl; g++) {
             if (g >= g0 && g < g1) {
                 uint32_t rm = 0;
@@ -496,8 +512,10 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32, 32 / SCAN_WARPS) k_scan_minim
         if (PACKED) {
             // the block bitmap decides: my chunk and the byte before it, clipped to the record
             const uint64_t r0 = max(tlo + c_lo, gs + 1) - 1, r1 = min(tlo + c_lo + Cs, ge);
+            uint32_t w_prev, w0;
+            packed_prefetch(a, tlo, gs, c_lo, gpl, own_lo, own_hi, w_prev, w0);       // in flight while the bitmap is read
             generic = __any_sync(0xffffffffu, any_flag(a, r0, r1));
-            if (!generic) stage_chunk<HPC, true, false>(a, tlo, gs, c_lo, gpl, own_lo, own_hi, sb, cum_l, runm_l, ta, q, bad);
+            if (!generic) stage_chunk<HPC, true, false>(a, tlo, gs, c_lo, gpl, own_lo, own_hi, sb, cum_l, runm_l, ta, q, bad, w_prev, w0);
         } else {
             stage_chunk<HPC, false, false>(a, tlo, gs, c_lo, gpl, own_lo, own_hi, sb, cum_l, runm_l, ta, q, bad);
             generic = __any_sync(0xffffffffu, bad != 0);       // some byte is not A/C/G/T: stage again with per-symbol flags
