@@ -9,7 +9,8 @@ HiFi-like reads, length N(24 kb, 3 kb), 99.5 % identity, seed 3 -> 48 Gbp per st
 are sharded over the ranks (contiguous blocks, no data-path collective), the index is built partitioned by reference
 base range, the per-rank minimizer stores are exchanged over NCCL (in place, exact sizes) and every rank freezes the
 whole index.  A "step" is one pass of the whole hot path (S1 scan -> k-min-mers -> probe -> Match -> chain -> mq_hit)
-over all reads.  `--config 2` is round 1's workload (E. coli-sized genome, 100,000 x 10 kb reads per rank, weak scaling).
+over all reads.  `--config 2` is round 1's workload (E. coli-sized genome, 100,000 x 10 kb reads per rank, weak scaling),
+`--config 4` the maize-like repetitive genome (2.2 Gbp, 85 % repeat families, 1,000,000 x 24 kb reads, strong scaling).
 
 Printed JSON (one line, rank 0), see the contract in the task statement:
   value          reads/s with the reads resident in HBM in the library's packed input format (mq_map_batch_packed_device)
@@ -43,8 +44,11 @@ CONFIGS = {
             n_reads=2000000, mean=24000.0, sd=3000.0, min_len=1000, err=0.005, scaling="strong", sat=0.06, segdup=0.05),
     2: dict(workload="ecoli_4.64Mbp_x_100k_hifi_reads_10kb_99.5pct (BASELINE configs[1])", seed=2, genome_bp=4641652,
             n_reads=100000, mean=10000.0, sd=1500.0, min_len=1000, err=0.005, scaling="weak", sat=0.0, segdup=0.0),
+    4: dict(workload="synthetic_maize_like_2.2Gbp_10contigs_85pct_repeat_families_x_1M_hifi_reads_24kb_99.5pct (BASELINE configs[3])", seed=4,
+            genome_bp=2.2e9, n_reads=1000000, mean=24000.0, sd=3000.0, min_len=1000, err=0.005, scaling="strong", sat=0.0, segdup=0.0,
+            repeat=0.85, families=300, contigs=10),
 }
-CPU_SAMPLE_READS = {3: 400000, 2: 100000}       # reads per CPU-arm step (bounded sample of the workload)
+CPU_SAMPLE_READS = {3: 400000, 2: 100000, 4: 400000}       # reads per CPU-arm step (bounded sample of the workload)
 PACK_CHUNK_BASES = 1 << 30
 
 
@@ -58,6 +62,8 @@ def host_threads():
 
 def make_genome(cfg):
     from mapquik_b200 import sim
+    if cfg.get("repeat"):
+        return sim.genome(cfg["seed"], [int(cfg["genome_bp"] / cfg["contigs"])] * cfg["contigs"], repeat_frac=cfg["repeat"], n_families=cfg["families"])
     if cfg["genome_bp"] > 1e8:
         lens = [int(cfg["genome_bp"] * x / sum(sim.CHM13_PROPS)) for x in sim.CHM13_PROPS]
         return sim.genome(cfg["seed"], lens, sat_frac=cfg["sat"], segdup_frac=cfg["segdup"])
@@ -276,7 +282,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", type=int, default=3, choices=[3, 2])
+    ap.add_argument("--config", type=int, default=3, choices=[3, 2, 4])
     ap.add_argument("--reads", type=int, default=0, help="total reads per step (config 3) / per rank (config 2); default: the named workload")
     ap.add_argument("--check", type=int, default=20000, help="reads compared with the CPU oracle inside the run (untimed)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
