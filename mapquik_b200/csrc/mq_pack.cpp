@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 #include <vector>
@@ -73,8 +74,39 @@ __attribute__((target("avx2"))) size_t pack_groups_avx2(const uint8_t *src, size
     return g;
 }
 bool have_avx2() { static const bool h = __builtin_cpu_supports("avx2"); return h; }
+
+// Groups of 64 bases (AVX-512 VBMI): one 128-entry byte table (two registers) maps a letter to its code or to 0x80, so the
+// validity test, the case fold and the code extraction are ONE permute; bytes >= 0x80 are caught by OR-ing the input in.
+// Four codes per byte with two multiply-adds, sixteen bytes out with one down-convert.  `stream`: the destination is
+// 16-byte aligned and will not be read by this core again (pinned staging for a DMA) -> non-temporal store, no
+// read-for-ownership of the destination lines.
+__attribute__((target("avx512f,avx512bw,avx512vl,avx512vbmi"))) size_t pack_groups_avx512(const uint8_t *src, size_t groups, uint32_t *wout, bool fc, bool stream) {
+    alignas(64) uint8_t lut[128];
+    memset(lut, 0x80, sizeof lut);
+    lut['A'] = 0; lut['C'] = 1; lut['T'] = 2; lut['G'] = 3;
+    if (fc) { lut['a'] = 0; lut['c'] = 1; lut['t'] = 2; lut['g'] = 3; }
+    const __m512i t0 = _mm512_load_si512(lut), t1 = _mm512_load_si512(lut + 64);
+    const __m512i k0401 = _mm512_set1_epi16(0x0401), k1001 = _mm512_set1_epi32(0x00100001);
+    size_t g = 0;
+    for (; g < groups; g++) {
+        const __m512i v = _mm512_loadu_si512(src + 64 * g);
+        const __m512i c = _mm512_permutex2var_epi8(t0, v, t1);            // index = low 7 bits of the letter
+        if (_mm512_movepi8_mask(_mm512_or_si512(c, v))) break;             // a byte >= 0x80, or one the table rejects
+        const __m128i out = _mm512_cvtepi32_epi8(_mm512_madd_epi16(_mm512_maddubs_epi16(c, k0401), k1001));
+        if (stream) _mm_stream_si128((__m128i *)(wout + 4 * g), out);
+        else _mm_storeu_si128((__m128i *)(wout + 4 * g), out);
+    }
+    if (stream) _mm_sfence();
+    return g;
+}
+bool have_avx512() {
+    static const bool h = __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512vl") &&
+                          __builtin_cpu_supports("avx512vbmi") && !getenv("MQ_PACK_NO_AVX512");
+    return h;
+}
 #else
 bool have_avx2() { return false; }
+bool have_avx512() { return false; }
 #endif
 
 inline uint64_t pack32_plain(const uint8_t *src, bool fc, bool *bad) {
@@ -92,15 +124,22 @@ void pack_range(const uint8_t *src, uint64_t n, uint64_t at, uint32_t *words, ui
     const uint64_t head = std::min<uint64_t>(n, (32 - (at & 31)) & 31);      // up to a 32-base boundary (two whole words)
     pack_scalar(src, head, at, words, flags, ex, fc);
     i = head;
-    const bool avx = have_avx2();
+    const bool avx = have_avx2(), avx512 = have_avx512();
     while (i + 32 <= n) {
-        const uint64_t b = at + i;
 #if defined(__x86_64__)
+        // code words are never shared with a neighbouring range (ranges start on 32-base boundaries here): plain stores
+        if (avx512 && i + 64 <= n) {
+            uint32_t *w = words + ((at + i) >> 4);
+            const size_t done = pack_groups_avx512(src + i, (size_t)((n - i) / 64), w, fc, ((uintptr_t)w & 15) == 0);
+            i += 64 * done;
+            if (i + 32 > n) break;
+            if (done) continue;                   // stopped at an exception: 32 bases the narrow way, then wide again
+        }
         if (avx) {
-            // the very first and last word pair of the range may share a flag word, never a code word: plain stores are safe
-            const size_t done = pack_groups_avx2(src + i, (size_t)((n - i) / 32), words + (b >> 4), fc);
+            const size_t done = pack_groups_avx2(src + i, avx512 ? 1 : (size_t)((n - i) / 32), words + ((at + i) >> 4), fc);
             i += 32 * done;
             if (i + 32 > n) break;
+            if (avx512 && done) continue;
         }
 #endif
         // a group with a byte other than A/C/G/T (or no AVX2): one group the plain way
@@ -151,7 +190,10 @@ int mq_pack(const uint8_t *ascii, uint64_t n_bases, uint32_t *words, uint32_t *f
             const uint64_t u0 = units * t / n_threads, u1 = units * (t + 1) / n_threads;
             const uint64_t b0 = u0 * 2048, b1 = std::min(n_bases, u1 * 2048);
             if (b1 <= b0) return;
-            memset(words + (b0 >> 4), 0, ((b1 + 15) / 16 - (b0 >> 4)) * 4);
+            // b0 is a multiple of 2048: whole 32-base groups are written with plain stores, only the words of the
+            // trailing partial group are OR-ed into and must start out as zero
+            const uint64_t tail = b0 + ((b1 - b0) & ~31ull);
+            memset(words + (tail >> 4), 0, ((b1 + 15) / 16 - (tail >> 4)) * 4);
             memset(flags + u0, 0, (u1 - u0) * 4);
             pack_range(ascii + b0, b1 - b0, b0, words, flags, sinks[t], fold_case != 0);
         };

@@ -58,6 +58,20 @@ def test_pack_fold_case():
     assert bytes(q.unpack()) == bytes(a)          # lower case is NOT folded unless asked (the ABI contract)
 
 
+@pytest.mark.parametrize("n", [64, 200, 100003])
+def test_pack_fold_case_long(n):
+    """the wide (64 bases per step) packer folds case through its lookup table; bytes >= 0x80 must never alias a letter"""
+    rng = np.random.default_rng(n)
+    a = messy(rng, n)
+    low = rng.random(n) < 0.5
+    a = np.where(low & (a >= 65) & (a <= 90), a + 32, a).astype(np.uint8)
+    a[rng.integers(0, n, 5)] = np.frombuffer(b"\xc1\xe1\xc7\xd4\xf4", np.uint8)     # 'A' | 0x80, 'a' | 0x80, ...
+    p = PackedSeqs(a, fold_case=True)
+    assert bytes(p.unpack()) == bytes(a.tobytes().upper())
+    q = PackedSeqs(a, fold_case=False)
+    assert np.array_equal(q.unpack(), a)
+
+
 def test_pack_giant_run_is_one_interval():
     a = np.concatenate([np.frombuffer(b"ACGT" * 10, np.uint8), np.full(3_000_001, ord("N"), np.uint8), np.frombuffer(b"TTGA", np.uint8)])
     p = PackedSeqs(a, n_threads=1)
