@@ -15,7 +15,10 @@ over all reads.  `--config 2` is round 1's workload (E. coli-sized genome, 100,0
 Printed JSON (one line, rank 0), see the contract in the task statement:
   value          reads/s with the reads resident in HBM in the library's packed input format (mq_map_batch_packed_device)
   value_ascii    the same with ASCII reads resident (mq_map_batch_device)
-  e2e            through mq_map_batch with pinned HOST ASCII buffers: H2D of the sequences, D2H of the hits inside
+  e2e            through mq_map_batch with pinned HOST ASCII buffers, H2D of the sequences and D2H of the hits inside; the
+                 library may use the rank's host threads (mq_set_host_threads, the reference's --threads) to pack part
+                 of the batch on the fly, so fewer than 1 byte per base cross the link (bytes counted by the library)
+  e2e_ascii_link_only  the same call with host threads off: every base crosses the link as one byte
   e2e_prepacked  through mq_map_batch_packed with pinned host buffers the caller's parser packed (what the CLI does)
   e2e_packed     ASCII in host memory, mq_pack on all host threads of the rank + mq_map_batch_packed, pipelined by chunk,
                  all of it inside the timed region
@@ -431,11 +434,23 @@ def main():
     assert L.mq_dev_download(h, hits_b.ctypes.data, d_hits, n_reads * 48) == 0
     path_diff = {"ascii_resident": int((hits_b != hits).sum())}
 
-    # e2e: through the C ABI with pinned HOST ASCII buffers
+    # e2e_link_only: mq_map_batch on pinned HOST ASCII buffers, every base crosses the PCIe link as one byte
     h_hits[:] = 0
+    ix.set_host_threads(0)
+    t_e2e_link = timed(lambda: ix.map_batch(h_seqs[:n_bases], h_offs, out=h_hits_v), args.steps, args.warmup, device_events=False)
+    e2e_link_stage = {s: ix.last_ms(s) for s in ("h2d", "scan", "gather", "probe", "chain", "d2h")}
+    h2d_link = ix.last_counter("h2d_bytes")
+    path_diff["e2e_ascii_link_only"] = int((h_hits_v != hits).sum())
+
+    # e2e: the same call on the same buffers with this rank's host threads at the library's disposal (the reference's
+    # --threads): sub-batches packed on the fly from the back of the batch while ASCII ones cross the link from the front
+    h_hits[:] = 0
+    ix.set_host_threads(threads)
     t_e2e = timed(lambda: ix.map_batch(h_seqs[:n_bases], h_offs, out=h_hits_v), args.steps, args.warmup, device_events=False)
     e2e_stage = {s: ix.last_ms(s) for s in ("h2d", "scan", "gather", "probe", "chain", "d2h")}
+    h2d_e2e = ix.last_counter("h2d_bytes"); packed_bases_e2e = ix.last_counter("host_packed_bases")
     path_diff["e2e_ascii"] = int((h_hits_v != hits).sum())
+    ix.set_host_threads(0)
 
     # e2e_prepacked: pinned host buffers in the packed format
     h_hits[:] = 0
@@ -524,14 +539,16 @@ def main():
          np.maximum(hits["r_start"], truth["start"]).astype(np.int64) > 0.1 * truth["len"])
 
     # ---- max / sum over ranks ----------------------------------------------------------------------------------------
-    times = [t_dev, t_dev_ascii, t_e2e, t_e2e_pre, t_e2e_pack or 0.0, index_build_s, ib["scan_s"], ib["exchange_s"], ib["freeze_s"]]
+    times = [t_dev, t_dev_ascii, t_e2e, t_e2e_pre, t_e2e_pack or 0.0, index_build_s, ib["scan_s"], ib["exchange_s"], ib["freeze_s"], t_e2e_link]
     sums = [float(hits["mapped"].sum()), float(n_bases), float(ok.sum()), float(((hits["mapq"] == 60) & ~ok).sum()), float(paths_identical),
-            float(launches), float(n_min), float(scan_ms), float(scan_launches), float(scan_ms_ascii), float(scan_launches_ascii)]
+            float(launches), float(n_min), float(scan_ms), float(scan_launches), float(scan_ms_ascii), float(scan_launches_ascii),
+            float(h2d_e2e), float(packed_bases_e2e), float(h2d_link)]
     if world > 1:
         tt = torch.tensor(times, dtype=torch.float64, device=device); dist.all_reduce(tt, op=dist.ReduceOp.MAX); times = tt.tolist()
         ss = torch.tensor(sums, dtype=torch.float64, device=device); dist.all_reduce(ss, op=dist.ReduceOp.SUM); sums = ss.tolist()
-    t_dev, t_dev_ascii, t_e2e, t_e2e_pre, t_e2e_pack_m, index_build_s, ib_scan, ib_exch, ib_freeze = times
-    mapped_total, bases_total, ok_total, wrong_q60, paths_ok, launches_t, n_min_t, scan_ms_t, scan_l_t, scan_ms_a, scan_l_a = sums
+    t_dev, t_dev_ascii, t_e2e, t_e2e_pre, t_e2e_pack_m, index_build_s, ib_scan, ib_exch, ib_freeze, t_e2e_link = times
+    (mapped_total, bases_total, ok_total, wrong_q60, paths_ok, launches_t, n_min_t, scan_ms_t, scan_l_t, scan_ms_a, scan_l_a,
+     h2d_e2e_t, packed_bases_t, h2d_link_t) = sums
 
     if rank == 0:
         peak, peak_src = peaks()
@@ -570,9 +587,16 @@ def main():
             "n_unique_kminmers": int(n_unique), "table_bytes": int(ix.table_bytes()),
             "mapped_fraction": mapped_total / total_reads, "correct_fraction": ok_total / total_reads, "wrong_q60": int(wrong_q60),
             "parity": parity,
-            "e2e": {"value": rps(t_e2e), "unit": "reads/s", "h2d_bytes_per_step": int(bases_total + (total_reads + world) * 8),
+            "e2e": {"value": rps(t_e2e), "unit": "reads/s", "h2d_bytes_per_step": int(h2d_e2e_t),
                     "d2h_bytes_per_step": int(total_reads * 48), "gbp_per_s": gbps(t_e2e), "stage_ms_last_step_rank0": e2e_stage,
-                    "input": "upper-cased ASCII in pinned host memory (mq_map_batch)"},
+                    "host_threads_per_rank": threads, "bases_packed_on_host_fraction": packed_bases_t / max(bases_total, 1),
+                    "h2d_bytes_per_base": h2d_e2e_t / max(bases_total, 1),
+                    "input": "upper-cased ASCII in pinned host memory through mq_map_batch with mq_set_host_threads(host threads of the rank): "
+                             "sub-batches packed on the fly from the back of the batch, ASCII sub-batches over the link from the front; "
+                             "h2d bytes counted by the library (last step)"},
+            "e2e_ascii_link_only": {"value": rps(t_e2e_link), "unit": "reads/s", "h2d_bytes_per_step": int(h2d_link_t),
+                                    "d2h_bytes_per_step": int(total_reads * 48), "gbp_per_s": gbps(t_e2e_link), "stage_ms_last_step_rank0": e2e_link_stage,
+                                    "input": "the same call with mq_set_host_threads(0): every base crosses PCIe as one byte"},
             "e2e_prepacked": {"value": rps(t_e2e_pre), "unit": "reads/s", "h2d_bytes_per_step": int(pk.nbytes * world + (total_reads + world) * 8),
                               "d2h_bytes_per_step": int(total_reads * 48), "gbp_per_s": gbps(t_e2e_pre), "stage_ms_last_step_rank0": e2e_pre_stage,
                               "h2d_bytes_per_base": (pk.nbytes + (n_reads + 1) * 8) / max(n_bases, 1),

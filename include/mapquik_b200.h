@@ -217,6 +217,16 @@ uint64_t mq_launch_count(mq_ctx *);
 void *mq_stream(mq_ctx *);                /* cudaStream_t the kernels run on */
 int mq_sync(mq_ctx *);
 uint64_t mq_scan_kernel_launches(mq_ctx *);     /* launches of the dominant kernel (k_scan_minimizers) */
+/* Host threads the mapping calls may use ([multi]: shared out over the devices).  The reference maps on `--threads` CPU
+ * threads (main.rs:138-141,212, closures.rs:85,183); here they only ever touch the INPUT: with n > 0, mq_map_batch on ASCII host
+ * buffers feeds the GPU from both ends of the batch -- ASCII sub-batches go over the PCIe link as they are (1 byte per
+ * base) while the host threads pack sub-batches from the other end to 2 bits per base in pinned staging (the mq_pack
+ * arithmetic) that cross the link at a quarter of the bytes; the split balances itself.  Results are identical either
+ * way.  0 (the default) = never touch the input on the host. */
+int mq_set_host_threads(mq_ctx *, int n);
+/* counters of the last mapping call: "h2d_bytes" (bytes it uploaded), "sub_batches", "host_packed_sub_batches",
+ * "host_packed_bases" (how much of the input took the packed route); [multi]: summed over the devices */
+uint64_t mq_last_counter(mq_ctx *, const char *name);
 uint64_t mq_minimizer_count(mq_ctx *, int reset); /* minimizers produced since the last reset */
 /* device-memory helpers: keep inputs resident in HBM for mq_map_batch_device */
 void *mq_dev_alloc(mq_ctx *, size_t bytes);

@@ -43,6 +43,7 @@ EXPORTS = ["mq_create", "mq_destroy", "mq_strerror", "mq_last_error", "mq_abi_ve
            "mq_store_import", "mq_index_freeze", "mq_index_nb_mers", "mq_map_batch", "mq_map_batch_device",
            "mq_format_paf", "mq_minimizers", "mq_kminmers", "mq_index_get", "mq_matches", "mq_last_ms",
            "mq_launch_count", "mq_stream", "mq_sync", "mq_table_bytes", "mq_table_slots", "mq_scan_kernel_launches",
+           "mq_set_host_threads", "mq_last_counter",
            "mq_minimizer_count", "mq_dev_alloc", "mq_dev_free", "mq_dev_upload", "mq_dev_download", "mq_dev_memset",
            "mq_region_begin", "mq_region_end_ms", "mq_index_save", "mq_index_load", "mq_total_ms",
            "mq_create_multi", "mq_device_count", "mq_packed_words", "mq_packed_flag_words", "mq_pack", "mq_pack_at",
@@ -110,6 +111,8 @@ def lib():
     L.mq_table_bytes.restype = C.c_uint64; L.mq_table_bytes.argtypes = [vp]
     L.mq_table_slots.restype = C.c_uint64; L.mq_table_slots.argtypes = [vp]
     L.mq_scan_kernel_launches.restype = C.c_uint64; L.mq_scan_kernel_launches.argtypes = [vp]
+    L.mq_set_host_threads.restype = C.c_int; L.mq_set_host_threads.argtypes = [vp, C.c_int]
+    L.mq_last_counter.restype = C.c_uint64; L.mq_last_counter.argtypes = [vp, C.c_char_p]
     L.mq_minimizer_count.restype = C.c_uint64; L.mq_minimizer_count.argtypes = [vp, C.c_int]
     L.mq_dev_alloc.restype = vp; L.mq_dev_alloc.argtypes = [vp, C.c_size_t]
     L.mq_dev_free.restype = None; L.mq_dev_free.argtypes = [vp, vp]

@@ -17,11 +17,14 @@
 #include <algorithm>
 #include <array>
 #include <chrono>
+#include <condition_variable>
 #include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <memory>
+#include <mutex>
 #include <numeric>
 #include <string>
 #include <thread>
@@ -71,11 +74,20 @@ struct Slot2 {                 // resources of one in-flight sub-batch
     HBuf h_sc;                 // BatchScalars read back
     cudaEvent_t ev_copied = nullptr, ev_comp = nullptr, ev_done = nullptr;
     bool busy = false;
+    int pack_buf = -1;         // staging buffer of the on-the-fly packer this sub-batch was uploaded from (released on retire)
     BatchDev bd;               // what the slot holds (device view; stays valid until the slot is staged again)
     uint32_t i0 = 0, i1 = 0;   // records [i0, i1) of the call
 };
 
+// pinned staging of one sub-batch packed on the fly by host threads (mq_set_host_threads)
+struct PackBuf { HBuf words, flags; std::vector<mq_exc> exc; int state = 0; };   // 0 free, 1 being packed, 2 ready, 3 uploading
+constexpr int N_PACK_BUFS = 4;
+
 }  // namespace
+
+// mq_pack.cpp
+void mq_pack_units(const uint8_t *ascii, uint64_t n_bases, uint64_t u0, uint64_t u1, uint32_t *words, uint32_t *flags,
+                   std::vector<mq_exc> &exc, bool fold_case);
 
 struct mq_ctx {
     mq_params p{};
@@ -97,6 +109,11 @@ struct mq_ctx {
     uint64_t mini_cap = 0;        // entries d_pos / d_hash / d_matches can hold
     double mini_rate = 0;         // learned upper estimate of minimizers per base (grows on overflow)
     Slot2 slot[2];
+    // on-the-fly packing of ASCII host input (mq_set_host_threads)
+    int host_threads = 0;
+    uint64_t sub_bases = SUB_BASES, sub_bases_light = SUB_BASES_LIGHT;     // MQ_SUB_BASES (test knob, read at mq_create) shrinks both
+    PackBuf pack_buf[N_PACK_BUFS];
+    uint64_t ctr_h2d_bytes = 0, ctr_host_packed_bases = 0, ctr_host_packed_subs = 0, ctr_subs = 0;   // of the last mapping call
     // minimizer store (reference side)
     DBuf st_pos, st_hash; uint64_t st_n = 0;
     std::vector<std::array<uint64_t, 3>> dir;          // (ref_idx, seg_start, count)
@@ -393,6 +410,7 @@ int enqueue_probe_chain(mq_ctx *c, const BatchDev &b, HitRec *d_hits) {
 // ---- input descriptions ---------------------------------------------------------------------------------
 struct SeqInput {               // what a batch of sequences looks like to the staging code
     bool packed = false, resident = false;           // resident: pointers are device pointers of this ctx
+    uint64_t base = 0;                               // packed host input: words / flags / exc describe bases from `base` on (multiple of 2048)
     const uint8_t *seqs = nullptr;
     const uint32_t *words = nullptr, *flags = nullptr; const mq_exc *exc = nullptr; uint64_t n_exc = 0;
 };
@@ -434,9 +452,10 @@ int stage_pieces(mq_ctx *c, Slot2 &s, const SeqInput &in, const Piece *pc, const
     const uint64_t origin = in.packed ? (lo & ~2047ull) : (lo & ~15ull);
     // exception intervals overlapping the slice
     uint64_t e0 = 0, e1 = 0;
+    const uint64_t rel = origin - in.base;          // of the slice, in the coordinates of the packed arrays
     if (in.packed && in.n_exc && !in.resident) {
-        e0 = std::partition_point(in.exc, in.exc + in.n_exc, [&](const mq_exc &e) { return e.start + e.len <= origin; }) - in.exc;
-        e1 = std::partition_point(in.exc, in.exc + in.n_exc, [&](const mq_exc &e) { return e.start < hi; }) - in.exc;
+        e0 = std::partition_point(in.exc, in.exc + in.n_exc, [&](const mq_exc &e) { return e.start + e.len <= rel; }) - in.exc;
+        e1 = std::partition_point(in.exc, in.exc + in.n_exc, [&](const mq_exc &e) { return e.start < hi - in.base; }) - in.exc;
         if (e1 < e0) e1 = e0;
     }
     const size_t flag_words = (in.packed && !in.resident) ? (size_t)((hi - origin + 2047) / 2048 + 1) : 0;
@@ -468,12 +487,12 @@ int stage_pieces(mq_ctx *c, Slot2 &s, const SeqInput &in, const Piece *pc, const
     }
     h_offs[n] = n ? rec_hi(i1 - 1) - origin : 0;
     h_ft[n] = t;
-    if (flag_words) memcpy(hm + ml.flags, in.flags + (origin >> 11), flag_words * 4);
+    if (flag_words) memcpy(hm + ml.flags, in.flags + (rel >> 11), flag_words * 4);
     if (e1 > e0) {
         ExcRec *he = (ExcRec *)(hm + ml.exc);
         for (uint64_t e = e0; e < e1; e++) {     // slice coordinates
-            const uint64_t st = std::max(in.exc[e].start, origin), en = in.exc[e].start + in.exc[e].len;
-            he[e - e0] = ExcRec{st - origin, (uint32_t)(en - st), in.exc[e].byte};
+            const uint64_t st = std::max(in.exc[e].start, rel), en = in.exc[e].start + in.exc[e].len;
+            he[e - e0] = ExcRec{st - rel, (uint32_t)(en - st), in.exc[e].byte};
         }
     }
     const uint64_t span = hi - origin;            // bases of the slice
@@ -493,17 +512,20 @@ int stage_pieces(mq_ctx *c, Slot2 &s, const SeqInput &in, const Piece *pc, const
         } else if (in.packed) {
             const size_t wbytes = (size_t)((span + 15) / 16) * 4;
             if ((rc = ensure(c, s.d_in, wbytes + PAD))) return rc;
-            if (wbytes) CK(cudaMemcpyAsync(s.d_in.p, in.words + (origin >> 4), wbytes, cudaMemcpyHostToDevice, c->copy_stream));
+            if (wbytes) CK(cudaMemcpyAsync(s.d_in.p, in.words + (rel >> 4), wbytes, cudaMemcpyHostToDevice, c->copy_stream));
+            c->ctr_h2d_bytes += wbytes;
             CK(cudaMemsetAsync((uint8_t *)s.d_in.p + wbytes, 0, PAD, c->copy_stream));
             bd.packed = s.d_in.as<uint32_t>(); bd.flags = (const uint32_t *)(dm + ml.flags);
             bd.exc = (const ExcRec *)(dm + ml.exc); bd.n_exc = (uint32_t)(e1 - e0);
         } else {
             if ((rc = ensure(c, s.d_in, span + PAD))) return rc;
             if (span) CK(cudaMemcpyAsync(s.d_in.p, in.seqs + origin, span, cudaMemcpyHostToDevice, c->copy_stream));
+            c->ctr_h2d_bytes += span;
             CK(cudaMemsetAsync((uint8_t *)s.d_in.p + span, 0, PAD, c->copy_stream));
             bd.seqs = s.d_in.as<uint8_t>();
         }
         CK(cudaMemcpyAsync(s.d_meta.p, s.h_meta.p, ml.total, cudaMemcpyHostToDevice, c->copy_stream));
+        c->ctr_h2d_bytes += ml.total;
     }
     CK(cudaEventRecord(s.ev_copied, c->copy_stream));
     s.bd = bd; s.i0 = i0; s.i1 = i1;
@@ -533,15 +555,114 @@ int check_offs(mq_ctx *c, const uint64_t *offs, uint32_t n) {
     return MQ_OK;
 }
 
+// ---- on-the-fly packing of ASCII host input -------------------------------------------------------------
+// mq_map_batch on ASCII host buffers is bound by the PCIe link (1 byte per base).  With host threads at its disposal
+// (mq_set_host_threads: the reference's --threads, main.rs:138-141) the pipeline feeds the GPU from BOTH ends of the batch:
+// the main thread uploads ASCII sub-batches from the front as fast as the link takes them, while the host threads pack
+// sub-batches from the back, 2 bits per base, into pinned staging buffers (a team: every thread packs 1/T of the
+// sub-batch, so one is ready every couple of milliseconds) that are uploaded at a quarter of the bytes.  Whoever gets
+// to a sub-batch first takes it; the two fronts meet wherever link and host threads balance.  Results do not depend
+// on which route a read took (the packed format is exactly the ASCII sequence, tests/test_pack.py).
+struct HostPacker {
+    struct Job { uint32_t sub; int buf; int done = 0; uint64_t base = 0, n_bases = 0; std::vector<std::vector<mq_exc>> part_exc; };
+    mq_ctx *c; const uint8_t *seqs; const uint64_t *offs; const std::vector<uint32_t> &cut;
+    int T;
+    std::mutex mu; std::condition_variable cv;
+    std::vector<Job> jobs;                 // in claim order (reserved: references stay valid)
+    std::vector<size_t> ready;             // job indices, oldest first
+    size_t front = 0, back;                // unclaimed sub-batches: [front, back)
+    size_t packing = 0;                    // jobs claimed and not yet ready
+    bool stop = false, failed = false;
+    std::vector<std::thread> th;
+
+    HostPacker(mq_ctx *c_, const uint8_t *seqs_, const uint64_t *offs_, const std::vector<uint32_t> &cut_, int T_)
+        : c(c_), seqs(seqs_), offs(offs_), cut(cut_), T(T_), back(cut_.size() - 1) { jobs.reserve(cut_.size()); }
+    ~HostPacker() { finish(); }
+    void start() { for (int t = 0; t < T; t++) th.emplace_back([this, t] { run(t); }); }
+    void finish() {
+        { std::lock_guard<std::mutex> lk(mu); stop = true; }
+        cv.notify_all();
+        for (auto &x : th) x.join();
+        th.clear();
+    }
+    void run(int t) {
+        for (size_t seq = 0;; seq++) {
+            Job *job = nullptr;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                for (;;) {
+                    if (stop || failed) return;
+                    if (jobs.size() > seq) break;
+                    if (front >= back) return;                     // nothing left to claim
+                    int b = -1;
+                    for (int i = 0; i < N_PACK_BUFS; i++) if (c->pack_buf[i].state == 0) { b = i; break; }
+                    if (b >= 0) {
+                        back--;
+                        Job j; j.sub = (uint32_t)back; j.buf = b;
+                        j.base = offs[cut[back]] & ~2047ull; j.n_bases = offs[cut[back + 1]] - j.base;
+                        j.part_exc.resize(T);
+                        jobs.push_back(std::move(j));
+                        c->pack_buf[b].state = 1; packing++;
+                        cv.notify_all();
+                        break;
+                    }
+                    cv.wait(lk);                                   // every staging buffer is in use
+                }
+                job = &jobs[seq];
+            }
+            PackBuf &pb = c->pack_buf[job->buf];
+            const uint64_t units = (job->n_bases + 2047) / 2048;
+            bool ok = true;
+            try {
+                mq_pack_units(seqs + job->base, job->n_bases, units * t / T, units * (t + 1) / T, (uint32_t *)pb.words.p, (uint32_t *)pb.flags.p,
+                              job->part_exc[t], false);
+            } catch (...) { ok = false; }
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                if (!ok) failed = true;
+                if (++job->done == T) {
+                    pb.exc.clear();
+                    for (auto &v : job->part_exc) pb.exc.insert(pb.exc.end(), v.begin(), v.end());
+                    ((uint32_t *)pb.flags.p)[units] = 0; ((uint32_t *)pb.flags.p)[units + 1] = 0;     // the stager reads one word past the slice
+                    pb.state = 2; packing--;
+                    ready.push_back(seq);
+                }
+            }
+            cv.notify_all();
+        }
+    }
+    // next sub-batch for the uploader: a packed one if one is ready, else the next ASCII one from the front.
+    // Returns false when every sub-batch has been handed out.  *job_out = nullptr for an ASCII sub-batch.
+    bool next(uint32_t *sub, const Job **job_out) {
+        std::unique_lock<std::mutex> lk(mu);
+        for (;;) {
+            if (!ready.empty()) {
+                const Job &j = jobs[ready.front()];
+                ready.erase(ready.begin());
+                c->pack_buf[j.buf].state = 3;
+                *sub = j.sub; *job_out = &j;
+                return true;
+            }
+            if (front < back) { *sub = (uint32_t)front++; *job_out = nullptr; return true; }
+            if (packing == 0 || failed) return false;
+            cv.wait(lk);
+        }
+    }
+    void release(int buf) {
+        { std::lock_guard<std::mutex> lk(mu); c->pack_buf[buf].state = 0; }
+        cv.notify_all();
+    }
+};
+
 // ---- mapping pipeline -------------------------------------------------------------------------------------
 // reads [0, n) of `in` with host offsets `offs`; hits go to out (host) or d_out (device, resident path)
 int map_pipeline(mq_ctx *c, const SeqInput &in, const uint64_t *offs, uint32_t n, mq_hit *out, mq_hit *d_out) {
     int rc;
     if ((rc = init_streams(c))) return rc;
-    // sub-batch boundaries
+    c->ctr_h2d_bytes = c->ctr_host_packed_bases = c->ctr_host_packed_subs = c->ctr_subs = 0;
     // sub-batch boundaries; the first one is an eighth of the size so that the GPU starts while the host prepares the next
     std::vector<uint32_t> cut{0};
-    const uint64_t sub = (in.packed || in.resident) ? SUB_BASES_LIGHT : SUB_BASES;
+    const uint64_t sub = (in.packed || in.resident) ? c->sub_bases_light : c->sub_bases;
     for (uint32_t i0 = 0; i0 < n;) {
         const uint64_t want = offs[i0] + (i0 == 0 ? sub / 8 : sub);
         uint32_t i1 = (uint32_t)(std::upper_bound(offs + i0 + 1, offs + n + 1, want) - offs) - 1;
@@ -550,6 +671,21 @@ int map_pipeline(mq_ctx *c, const SeqInput &in, const uint64_t *offs, uint32_t n
     }
     const size_t ns = cut.size() - 1;
     const uint32_t min_len = c->p.l + c->p.k - 1;
+    c->ctr_subs = ns;
+
+    // host threads pack sub-batches from the back while the link carries ASCII ones from the front
+    std::unique_ptr<HostPacker> hp;
+    if (!in.packed && !in.resident && c->host_threads > 0 && ns >= 3) {
+        uint64_t maxb = 0;
+        for (size_t i = 0; i < ns; i++) maxb = std::max<uint64_t>(maxb, offs[cut[i + 1]] - (offs[cut[i]] & ~2047ull));
+        for (auto &pb : c->pack_buf) {
+            if ((rc = ensure_host(c, pb.words, (size_t)mq_packed_words(maxb) * 4))) return rc;
+            if ((rc = ensure_host(c, pb.flags, (size_t)mq_packed_flag_words(maxb) * 4))) return rc;
+            pb.state = 0;
+        }
+        hp.reset(new HostPacker(c, in.seqs, offs, cut, c->host_threads));
+        hp->start();
+    }
 
     // finish the sub-batch a slot holds: wait for its hits, look at its status, redo it if a buffer was too small
     auto retire = [&](Slot2 &s) -> int {
@@ -575,18 +711,30 @@ int map_pipeline(mq_ctx *c, const SeqInput &in, const uint64_t *offs, uint32_t n
             CK(cudaStreamSynchronize(c->stream));
             c->last_minimizers += hs->n_minimizers;
         }
+        if (s.pack_buf >= 0 && hp) { hp->release(s.pack_buf); s.pack_buf = -1; }
         return MQ_OK;
     };
 
     for (size_t i = 0; i < ns; i++) {
         Slot2 &s = c->slot[i & 1];
         if ((rc = retire(s))) return rc;
-        const uint32_t m = cut[i + 1] - cut[i];
+        uint32_t j = (uint32_t)i;                    // the sub-batch this iteration stages
+        const HostPacker::Job *job = nullptr;
+        if (hp && !hp->next(&j, &job)) { c->err = "packing the input on the host failed (out of memory)"; return MQ_ERR_NOMEM; }
+        const uint32_t m = cut[j + 1] - cut[j];
         BatchDev bd;
-        if ((rc = stage_pieces(c, s, in, nullptr, offs, cut[i], cut[i + 1], min_len, false, bd))) return rc;
+        if (job) {
+            const PackBuf &pb = c->pack_buf[job->buf];
+            SeqInput pin; pin.packed = true; pin.base = job->base;
+            pin.words = (const uint32_t *)pb.words.p; pin.flags = (const uint32_t *)pb.flags.p; pin.exc = pb.exc.data(); pin.n_exc = pb.exc.size();
+            s.pack_buf = job->buf;
+            c->ctr_host_packed_bases += offs[cut[j + 1]] - offs[cut[j]]; c->ctr_host_packed_subs++;
+            rc = stage_pieces(c, s, pin, nullptr, offs, cut[j], cut[j + 1], min_len, false, bd);
+        } else rc = stage_pieces(c, s, in, nullptr, offs, cut[j], cut[j + 1], min_len, false, bd);
+        if (rc) return rc;
         if ((rc = ensure_workspace(c, m, bd.n_tiles, bd.bases, true))) return rc;
         HitRec *dh;
-        if (d_out) dh = (HitRec *)d_out + cut[i];
+        if (d_out) dh = (HitRec *)d_out + cut[j];
         else { if ((rc = ensure(c, s.d_hits, (size_t)m * sizeof(HitRec)))) return rc; dh = s.d_hits.as<HitRec>(); }
         CK(cudaStreamWaitEvent(c->stream, s.ev_copied, 0));
         if ((rc = enqueue_scan(c, bd))) return rc;
@@ -595,7 +743,7 @@ int map_pipeline(mq_ctx *c, const SeqInput &in, const uint64_t *offs, uint32_t n
         CK(cudaStreamWaitEvent(c->d2h_stream, s.ev_comp, 0));
         {
             StageTimer t(c, "d2h", c->d2h_stream);
-            if (!d_out) CK(cudaMemcpyAsync(out + cut[i], dh, (size_t)m * sizeof(HitRec), cudaMemcpyDeviceToHost, c->d2h_stream));
+            if (!d_out) CK(cudaMemcpyAsync(out + cut[j], dh, (size_t)m * sizeof(HitRec), cudaMemcpyDeviceToHost, c->d2h_stream));
             CK(cudaMemcpyAsync(s.h_sc.p, s.d_sc.p, sizeof(BatchScalars), cudaMemcpyDeviceToHost, c->d2h_stream));
         }
         CK(cudaEventRecord(s.ev_done, c->d2h_stream));
@@ -747,6 +895,10 @@ static int create_one(mq_ctx **out, const mq_params *p, int device) {
     mq_ctx *c = new (std::nothrow) mq_ctx();
     if (!c) return MQ_ERR_NOMEM;
     c->p = *p; c->device = device; c->bound = hash_bound(p->density);
+    if (const char *e = getenv("MQ_SUB_BASES")) {        // tests: many small sub-batches from small inputs
+        const uint64_t v = strtoull(e, nullptr, 10);
+        if (v >= 4096) c->sub_bases = c->sub_bases_light = v;
+    }
     fill_tables(c->tab, p->l);
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->n_sm = prop.multiProcessorCount;
@@ -820,6 +972,7 @@ void mq_destroy(mq_ctx *c) {
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     if (c->region_a) { cudaEventDestroy(c->region_a); cudaEventDestroy(c->region_b); }
     hfree(c->h_pin);
+    for (auto &pb : c->pack_buf) { hfree(pb.words); hfree(pb.flags); }
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
     cudaStreamDestroy(c->stream);
@@ -856,6 +1009,28 @@ double mq_last_ms(mq_ctx *c, const char *stage) {
     if (!strcmp(stage, "total")) { double s = 0; for (auto &kv : c->ms) if (kv.first != "scan_kernel") s += kv.second; return s; }
     auto it = c->ms.find(stage);
     return it == c->ms.end() ? 0.0 : it->second;
+}
+int mq_set_host_threads(mq_ctx *c, int n) {
+    if (!c || n < 0) return MQ_ERR_ARG;
+    if (n > 256) n = 256;
+    c->host_threads = n;
+    const int G = (int)c->kids.size();
+    for (int g = 0; g < G; g++) c->kids[g]->host_threads = n / G + (g < n % G ? 1 : 0);      // a multi-GPU context shares them out
+    return MQ_OK;
+}
+uint64_t mq_last_counter(mq_ctx *c, const char *name) {
+    if (!c || !name) return 0;
+    auto one = [&](const mq_ctx *k) -> uint64_t {
+        if (!strcmp(name, "h2d_bytes")) return k->ctr_h2d_bytes;
+        if (!strcmp(name, "host_packed_bases")) return k->ctr_host_packed_bases;
+        if (!strcmp(name, "host_packed_sub_batches")) return k->ctr_host_packed_subs;
+        if (!strcmp(name, "sub_batches")) return k->ctr_subs;
+        return 0;
+    };
+    if (c->kids.empty()) return one(c);
+    uint64_t s = 0;
+    for (const mq_ctx *k : c->kids) s += one(k);
+    return s;
 }
 uint64_t mq_scan_kernel_launches(mq_ctx *c) { if (!c) return 0; uint64_t s = c->scan_kernel_launches; for (mq_ctx *k : c->kids) s += k->scan_kernel_launches; return s; }
 uint64_t mq_minimizer_count(mq_ctx *c, int reset) {

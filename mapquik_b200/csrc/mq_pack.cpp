@@ -158,6 +158,24 @@ void pack_range(const uint8_t *src, uint64_t n, uint64_t at, uint32_t *words, ui
 
 }  // namespace
 
+// Internal (not part of the C ABI): pack the 2048-base units [u0, u1) of a destination whose base 0 is ascii[0];
+// n_bases = total bases of the destination.  Units are whole flag words, so concurrent callers on disjoint unit ranges
+// share no word: nothing needs to be zeroed beforehand.  Used by mq_pack's threads and by the on-the-fly packer of
+// mq_map_batch (mq_lib.cu).
+void mq_pack_units(const uint8_t *ascii, uint64_t n_bases, uint64_t u0, uint64_t u1, uint32_t *words, uint32_t *flags,
+                   std::vector<mq_exc> &exc, bool fold_case) {
+    const uint64_t b0 = u0 * 2048, b1 = std::min(n_bases, u1 * 2048);
+    memset(flags + u0, 0, (u1 - u0) * 4);
+    if (b1 <= b0) return;
+    // whole 32-base groups are written with plain stores; only the words of the trailing partial group are OR-ed into
+    const uint64_t tail = b0 + ((b1 - b0) & ~31ull);
+    memset(words + (tail >> 4), 0, ((b1 + 15) / 16 - (tail >> 4)) * 4);
+    ExcSink ex;
+    ex.v.swap(exc);
+    pack_range(ascii + b0, b1 - b0, b0, words, flags, ex, fold_case);
+    exc.swap(ex.v);
+}
+
 extern "C" {
 
 uint64_t mq_packed_words(uint64_t n_bases) { return (n_bases + 15) / 16 + 64; }       // + 256 bytes of slack (word loads past the end)
@@ -185,17 +203,9 @@ int mq_pack(const uint8_t *ascii, uint64_t n_bases, uint32_t *words, uint32_t *f
         // pieces of whole 2048-base flag words: no word of the destination is shared between two threads
         const uint64_t units = (n_bases + 2047) / 2048;
         n_threads = (int)std::min<uint64_t>((uint64_t)n_threads, std::max<uint64_t>(1, units / 64));
-        std::vector<ExcSink> sinks(n_threads);
+        std::vector<std::vector<mq_exc>> sinks(n_threads);
         auto work = [&](int t) {
-            const uint64_t u0 = units * t / n_threads, u1 = units * (t + 1) / n_threads;
-            const uint64_t b0 = u0 * 2048, b1 = std::min(n_bases, u1 * 2048);
-            if (b1 <= b0) return;
-            // b0 is a multiple of 2048: whole 32-base groups are written with plain stores, only the words of the
-            // trailing partial group are OR-ed into and must start out as zero
-            const uint64_t tail = b0 + ((b1 - b0) & ~31ull);
-            memset(words + (tail >> 4), 0, ((b1 + 15) / 16 - (tail >> 4)) * 4);
-            memset(flags + u0, 0, (u1 - u0) * 4);
-            pack_range(ascii + b0, b1 - b0, b0, words, flags, sinks[t], fold_case != 0);
+            mq_pack_units(ascii, n_bases, units * t / n_threads, units * (t + 1) / n_threads, words, flags, sinks[t], fold_case != 0);
         };
         if (n_threads == 1) work(0);
         else {
@@ -208,11 +218,11 @@ int mq_pack(const uint8_t *ascii, uint64_t n_bases, uint32_t *words, uint32_t *f
         memset(words + wend, 0, (mq_packed_words(n_bases) - wend) * 4);
         memset(flags + units, 0, (mq_packed_flag_words(n_bases) - units) * 4);
         uint64_t tot = 0;
-        for (auto &s : sinks) tot += s.v.size();
+        for (auto &s : sinks) tot += s.size();
         *n_exc = tot;
         if (tot > exc_cap) return MQ_ERR_RANGE;
         uint64_t w = 0;
-        for (auto &s : sinks) for (auto &e : s.v) {
+        for (auto &s : sinks) for (auto &e : s) {
             // an interval that continues the previous thread's last one is merged (cosmetic: either form is exact)
             if (w && exc[w - 1].byte == e.byte && exc[w - 1].start + exc[w - 1].len == e.start && (uint64_t)exc[w - 1].len + e.len <= 0xFFFFFFFFull) exc[w - 1].len += e.len;
             else exc[w++] = e;

@@ -352,5 +352,14 @@ class Index:
     def launch_count(self):
         return self._L.mq_launch_count(self._h)
 
+    def set_host_threads(self, n):
+        """host threads the mapping calls may use to pack ASCII input on the fly (the reference's --threads, main.rs:138-141)"""
+        rc = self._L.mq_set_host_threads(self._h, int(n))
+        if rc:
+            raise MapquikError(rc, self._L.mq_last_error(self._h))
+
+    def last_counter(self, name):
+        return int(self._L.mq_last_counter(self._h, name.encode()))
+
     def table_bytes(self):
         return self._L.mq_table_bytes(self._h)

@@ -38,7 +38,7 @@ def test_reference_arm_other_ranks_stay_silent():
     assert r.returncode == 0 and r.stdout.strip() == ""
 
 
-GPU_KEYS = {"roofline", "gpu_launches", "clocks", "parity", "e2e_prepacked", "e2e_packed", "value_ascii", "index_build"}
+GPU_KEYS = {"roofline", "gpu_launches", "clocks", "parity", "e2e_prepacked", "e2e_packed", "e2e_ascii_link_only", "value_ascii", "index_build"}
 
 
 def check_gpu_line(d, n_reads):
@@ -48,6 +48,7 @@ def check_gpu_line(d, n_reads):
     assert rf["bound"] == "hbm" and rf["unit"] == "GB/s" and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9
     assert d["gpu_launches"] > 0 and d["e2e"]["h2d_bytes_per_step"] > n_reads * 1000 and d["e2e"]["d2h_bytes_per_step"] == n_reads * 48
     assert d["e2e"]["value"] < d["value"]                       # the PCIe copies are inside the e2e region
+    assert d["e2e_ascii_link_only"]["h2d_bytes_per_step"] >= d["config"]["bases_total"] >= d["e2e"]["h2d_bytes_per_step"] * 0.99
     assert d["e2e_prepacked"]["h2d_bytes_per_base"] < 0.27      # 2 bits per base + offsets + bitmap
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     par = d["parity"]

@@ -639,6 +639,40 @@ def test_multi_gpu_context_equals_single(n_dev):
     one.close(); multi.close(); multi2.close()
 
 
+# ---- on-the-fly packing of ASCII host input (mq_set_host_threads) -------------------------------------------------
+@pytest.mark.parametrize("threads,n_dev", [(1, 1), (3, 1), (16, 1), (5, 2)])
+def test_host_threads_pack_on_the_fly_equals_plain(threads, n_dev, monkeypatch):
+    """mq_map_batch on ASCII with host threads: sub-batches packed on the host from the back of the batch, ASCII ones
+    uploaded from the front -- same hits as the plain path and as the oracle, whatever route a read took"""
+    monkeypatch.setenv("MQ_SUB_BASES", str(1 << 20))          # 1 Mbase sub-batches: ~45 of them from a small input
+    p = Params()
+    g, go, names = sim.genome(211, [900000, 400000])
+    g = g.copy(); g[200000:200300] = ord("N")
+    ix, oix = build_both(p, names, g, go)
+    rb, ro, rn, _ = sim.reads(211, g, go, 5000, 9000, 3000, contig_names=names)
+    rb = rb.copy()
+    rng = np.random.default_rng(7)
+    for s0 in rng.integers(0, rb.size - 100, 300):          # N runs, IUPAC codes, lower case, bytes >= 0x80 inside reads
+        rb[s0:s0 + int(rng.integers(1, 60))] = int(rng.choice(np.frombuffer(b"NNNRYacgt\xc1\xff", np.uint8)))
+    want = compare_hits(ix, oix, rb, ro, rn)
+    dev = Index(p, devices=_device_ids(n_dev)) if n_dev > 1 else ix
+    if n_dev > 1:
+        dev.add_batch(names, g, go); dev.freeze()
+    dev.set_host_threads(threads)
+    for _ in range(3):                                        # the split between the two routes differs from call to call
+        got = dev.map_batch(rb, ro)
+        assert got.tobytes() == want.tobytes()
+        assert dev.last_counter("sub_batches") >= 40
+        assert 1 <= dev.last_counter("host_packed_sub_batches") < dev.last_counter("sub_batches")
+        assert dev.last_counter("h2d_bytes") < rb.size + 64 * ro.size       # some of it crossed the link at 2 bits per base
+    dev.set_host_threads(0)
+    assert dev.map_batch(rb, ro).tobytes() == want.tobytes() and dev.last_counter("host_packed_sub_batches") == 0
+    assert dev.last_counter("h2d_bytes") >= rb.size
+    if n_dev > 1:
+        dev.close()
+    ix.close()
+
+
 # ---- BASELINE configs 2-5 at a scale the oracle finishes in seconds (the full sizes run in bench.py / scripts) -----------
 def _config3_like(scale, seed=3):
     lens = [int(3.1e9 / scale * x / sum(sim.CHM13_PROPS)) for x in sim.CHM13_PROPS]
