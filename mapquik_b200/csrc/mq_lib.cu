@@ -81,7 +81,8 @@ struct Slot2 {                 // resources of one in-flight sub-batch
 
 // pinned staging of one sub-batch packed on the fly by host threads (mq_set_host_threads)
 struct PackBuf { HBuf words, flags; std::vector<mq_exc> exc; int state = 0; };   // 0 free, 1 being packed, 2 ready, 3 uploading
-constexpr int N_PACK_BUFS = 4;
+constexpr int N_PACK_BUFS = 8;
+constexpr int N_SLOTS = 4;       // sub-batches in flight in the mapping pipeline (the index build uses two of them)
 
 }  // namespace
 
@@ -108,7 +109,7 @@ struct mq_ctx {
     uint32_t ovf_cap = 1u << 16;
     uint64_t mini_cap = 0;        // entries d_pos / d_hash / d_matches can hold
     double mini_rate = 0;         // learned upper estimate of minimizers per base (grows on overflow)
-    Slot2 slot[2];
+    Slot2 slot[N_SLOTS];
     // on-the-fly packing of ASCII host input (mq_set_host_threads)
     int host_threads = 0;
     uint64_t sub_bases = SUB_BASES, sub_bases_light = SUB_BASES_LIGHT;     // MQ_SUB_BASES (test knob, read at mq_create) shrinks both
@@ -420,7 +421,8 @@ int init_slot(mq_ctx *c, Slot2 &s) {
     if (s.ev_done) return MQ_OK;
     CK(cudaEventCreateWithFlags(&s.ev_copied, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&s.ev_comp, cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
+    // the host sleeps on this one (it has nothing to do until the slot is free, and its core is wanted by the packers)
+    CK(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming | cudaEventBlockingSync));
     int rc;
     if ((rc = ensure(c, s.d_sc, sizeof(BatchScalars)))) return rc;
     if ((rc = ensure_host(c, s.h_sc, sizeof(BatchScalars)))) return rc;
@@ -714,10 +716,18 @@ int map_pipeline(mq_ctx *c, const SeqInput &in, const uint64_t *offs, uint32_t n
         if (s.pack_buf >= 0 && hp) { hp->release(s.pack_buf); s.pack_buf = -1; }
         return MQ_OK;
     };
+    // a staging buffer of the packers is free again as soon as its upload has finished (long before the slot retires)
+    auto release_uploaded = [&]() {
+        if (!hp) return;
+        for (auto &s : c->slot)
+            if (s.pack_buf >= 0 && cudaEventQuery(s.ev_copied) == cudaSuccess) { hp->release(s.pack_buf); s.pack_buf = -1; }
+        cudaGetLastError();
+    };
 
     for (size_t i = 0; i < ns; i++) {
-        Slot2 &s = c->slot[i & 1];
+        Slot2 &s = c->slot[i % N_SLOTS];
         if ((rc = retire(s))) return rc;
+        release_uploaded();
         uint32_t j = (uint32_t)i;                    // the sub-batch this iteration stages
         const HostPacker::Job *job = nullptr;
         if (hp && !hp->next(&j, &job)) { c->err = "packing the input on the host failed (out of memory)"; return MQ_ERR_NOMEM; }
