@@ -421,8 +421,7 @@ int init_slot(mq_ctx *c, Slot2 &s) {
     if (s.ev_done) return MQ_OK;
     CK(cudaEventCreateWithFlags(&s.ev_copied, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&s.ev_comp, cudaEventDisableTiming));
-    // the host sleeps on this one (it has nothing to do until the slot is free, and its core is wanted by the packers)
-    CK(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming | cudaEventBlockingSync));
+    CK(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
     int rc;
     if ((rc = ensure(c, s.d_sc, sizeof(BatchScalars)))) return rc;
     if ((rc = ensure_host(c, s.h_sc, sizeof(BatchScalars)))) return rc;
@@ -692,7 +691,13 @@ int map_pipeline(mq_ctx *c, const SeqInput &in, const uint64_t *offs, uint32_t n
     // finish the sub-batch a slot holds: wait for its hits, look at its status, redo it if a buffer was too small
     auto retire = [&](Slot2 &s) -> int {
         if (!s.busy) return MQ_OK;
-        CK(cudaEventSynchronize(s.ev_done));
+        if (hp) {
+            // the packers want this core: poll with short sleeps instead of spinning inside cudaEventSynchronize (a
+            // blocking-sync event would do, but its wake-up took milliseconds on the virtualised hosts this ran on)
+            cudaError_t q;
+            while ((q = cudaEventQuery(s.ev_done)) == cudaErrorNotReady) std::this_thread::sleep_for(std::chrono::microseconds(20));
+            CK(q);
+        } else CK(cudaEventSynchronize(s.ev_done));
         s.busy = false;
         const BatchScalars *hs = (const BatchScalars *)s.h_sc.p;
         c->last_minimizers += hs->n_minimizers;

@@ -79,7 +79,12 @@ def adversarial_seqs(rng):
                                            (32, 0.02, True), (2, 0.5, True), (25, 1.0, True),
                                            # full 128-symbol lane streams with the longest window: the least spare rows
                                            # for parked candidates (v3), first sparse, then every l-mer selected
-                                           (32, 0.05, False), (32, 1.0, False)])
+                                           (32, 0.05, False), (32, 1.0, False),
+                                           # l = 31 (the default) without HPC (full 128-symbol streams), densities right
+                                           # under / over 1/64 (hash threshold around 2^58: twice the usual number of
+                                           # parked candidates per lane), and a threshold far below the 32-bit pre-filter
+                                           (31, 0.01, False), (31, 0.0156, True), (31, 0.0156, False), (31, 0.0157, True),
+                                           (31, 0.0005, True)])
 def test_minimizers_adversarial(l, density, hpc, fmt):
     rng = np.random.default_rng(7)
     buf, offs = concat_raw(adversarial_seqs(rng))
