@@ -14,15 +14,18 @@ for tool in memcheck racecheck synccheck initcheck; do
   timeout 1200 compute-sanitizer --tool $tool --log-file gpurun_out/${tag}_sanitizer_$tool.log python scripts/sanitize_smoke.py > gpurun_out/${tag}_san_$tool.out 2>&1
   tail -1 gpurun_out/${tag}_san_$tool.out; tail -2 gpurun_out/${tag}_sanitizer_$tool.log
 done
-B3="python bench.py --reads 100000 --steps 2 --warmup 3 --no-cpu-baseline --no-e2e-packed --check 0"
+B3="python bench.py --reads 200000 --steps 2 --warmup 3 --no-cpu-baseline --no-e2e-packed --check 0"
 B2="python bench.py --config 2 --steps 2 --warmup 3 --no-cpu-baseline --no-e2e-packed --check 0"
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/${tag}_launches.csv $B3 > gpurun_out/${tag}_ncu_launch.log 2>&1
-# config 2: one index scan launch, then per call the sub-batches 64 M / 512 M / rest: launch 2 = the 512 Mbase packed one,
-# launch 17 = the 512 Mbase ASCII one (packed-resident region = 5 calls x 3 launches)
-timeout 900 ncu --set full --import-source on --clock-control none -k regex:k_scan_minimizers -s 2 -c 1 -o gpurun_out/${tag}_scan_packed -f $B2 > gpurun_out/${tag}_ncu_sp.log 2>&1
-timeout 900 ncu --set full --import-source on --clock-control none -k regex:k_scan_minimizers -s 17 -c 1 -o gpurun_out/${tag}_scan_ascii -f $B2 > gpurun_out/${tag}_ncu_sa.log 2>&1
+# launch list of the `value` region alone (index build + 5 packed-resident steps of 200,000 reads on config 3)
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/${tag}_launches.csv $B3 --value-only > gpurun_out/${tag}_ncu_launch.log 2>&1
+# config 2 scan launches: 0-2 index builds (ASCII, packed, packed), then per resident call the sub-batches 64 M / 512 M / rest.
+# launch 4 = the 512 Mbase packed one; the ASCII-resident region starts at launch 18: launch 19 = the 512 Mbase ASCII one
+timeout 900 ncu --set full --import-source on --clock-control none -k regex:k_scan_minimizers -s 4 -c 1 -o gpurun_out/${tag}_scan_packed -f $B2 > gpurun_out/${tag}_ncu_sp.log 2>&1
+timeout 900 ncu --set full --import-source on --clock-control none -k regex:k_scan_minimizers -s 19 -c 1 -o gpurun_out/${tag}_scan_ascii -f $B2 > gpurun_out/${tag}_ncu_sa.log 2>&1
 timeout 900 ncu --set full --import-source on --clock-control none -k regex:k_probe_match -s 7 -c 1 -o gpurun_out/${tag}_probe -f $B3 > gpurun_out/${tag}_ncu_pr.log 2>&1
 MQ_NO_BLOOM=1 timeout 900 ncu --set full --clock-control none -k regex:k_probe_match -s 7 -c 1 -o gpurun_out/${tag}_probe_nobloom -f $B3 > gpurun_out/${tag}_ncu_prn.log 2>&1
 timeout 900 ncu --set full --clock-control none -k regex:k_insert_kminmers -c 1 -o gpurun_out/${tag}_insert -f $B3 > gpurun_out/${tag}_ncu_in.log 2>&1
+for r in scan_packed scan_ascii probe probe_nobloom insert; do ncu -i gpurun_out/${tag}_$r.ncu-rep --page raw --csv > gpurun_out/${tag}_${r}_ncu_raw.csv 2>/dev/null; done
+ncu -i gpurun_out/${tag}_scan_packed.ncu-rep --page source --csv > gpurun_out/${tag}_scan_packed_source.csv 2>/dev/null
 timeout 600 python scripts/cli_e2e.py --config 3 --reads 200000 > gpurun_out/${tag}_cli_e2e.json 2> gpurun_out/${tag}_cli_e2e.err
 ls -la gpurun_out | head -50
