@@ -28,6 +28,7 @@ pub enum MqCtx {}
 extern "C" {
     pub fn mq_create(out: *mut *mut MqCtx, p: *const MqParams, device: c_int) -> c_int;
     pub fn mq_create_multi(out: *mut *mut MqCtx, p: *const MqParams, devices: *const c_int, n_devices: c_int) -> c_int;
+    pub fn mq_set_host_threads(c: *mut MqCtx, n: c_int) -> c_int;
     pub fn mq_packed_words(n_bases: u64) -> u64;
     pub fn mq_packed_flag_words(n_bases: u64) -> u64;
     pub fn mq_pack_at(ascii: *const u8, n_bases: u64, at_base: u64, words: *mut u32, flags: *mut u32, exc: *mut MqExc, exc_cap: u64,
@@ -71,6 +72,11 @@ impl GpuIndex {
         let mut ctx: *mut MqCtx = std::ptr::null_mut();
         check(std::ptr::null(), unsafe { mq_create_multi(&mut ctx, &params, devices.as_ptr(), devices.len() as c_int) }, "mq_create_multi");
         GpuIndex { ctx, ref_lens: Vec::new() }
+    }
+    /// `--threads` (main.rs:138-141, 212): host threads `find_matches_batch` may use to pack ASCII batches on the fly
+    /// (sub-batches from the back of the batch are packed to 2 bits per base while ASCII ones cross PCIe from the front)
+    pub fn set_host_threads(&mut self, threads: usize) {
+        check(self.ctx, unsafe { mq_set_host_threads(self.ctx, threads as c_int) }, "mq_set_host_threads");
     }
     /// ≙ mers::ref_extract for a batch of upper-cased records (closures.rs:48,63); returns the k-min-mer count of each
     pub fn ref_extract_batch(&mut self, seqs: &[u8], offs: &[u64]) -> Vec<u64> {
