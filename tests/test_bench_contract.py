@@ -85,5 +85,17 @@ def test_committed_round_lines_keep_the_contract():
     assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
     r = json.loads(open(os.path.join(prof, "r01_bench_reference_arm.json")).read().strip().splitlines()[-1])
     assert r["impl"] == "reference" and r["metric"] == d["metric"] and r["unit"] == d["unit"] and r["config"]["workload"] == d["config"]["workload"]
+    # round 2: the default workload is BASELINE configs[2]; traffic / issue figures come from profiles/scan_traffic.json
+    d2 = json.loads(open(os.path.join(prof, "r02_bench_n1_config3.json")).read().strip().splitlines()[-1])
+    assert COMMON | GPU_KEYS <= set(d2) and "configs[2]" in d2["config"]["workload"] and d2["scaling"] == "strong"
+    rf2 = d2["roofline"]
+    assert rf2["bound"] == "hbm" and abs(rf2["frac"] - rf2["achieved"] / rf2["peak"]) < 1e-9
     t = json.load(open(os.path.join(prof, "scan_traffic.json")))
-    assert t["kernel"] == rf["kernel"] and t["dram_bytes_per_launch"] == rf["traffic"]
+    per_launch = t["packed"]["dram_bytes_per_base"] * d2["config"]["bases_total"] * d2["steps"] / rf2["launches"]
+    assert abs(rf2["traffic"] - per_launch) < 1e-6 * per_launch and 0.5 < rf2["traffic"] / rf2["algorithmic_bytes_per_launch"] < 1.5
+    assert 0 < rf2["issue"]["frac"] < 1 and abs(rf2["issue"]["thread_instructions_per_base"] - 32 * t["packed"]["warp_instructions_per_base"]) < 1e-6
+    par = d2["parity"]
+    assert par["paths_identical"] is True and par["hits_identical"] is True and par["index_identical"] is True and par["checked_reads"] >= 20000
+    assert d2["e2e"]["value"] > d2["e2e_ascii_link_only"]["value"] and d2["e2e"]["h2d_bytes_per_step"] < d2["e2e_ascii_link_only"]["h2d_bytes_per_step"]
+    r2 = json.loads(open(os.path.join(prof, "r02_bench_reference_arm.json")).read().strip().splitlines()[-1])
+    assert r2["impl"] == "reference" and r2["metric"] == d2["metric"] and r2["config"]["workload"] == d2["config"]["workload"]
