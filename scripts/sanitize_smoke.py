@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Small end-to-end run meant to be executed under compute-sanitizer (memcheck / racecheck / initcheck):
 adversarial minimizer inputs in both input formats, index build, mapping (ASCII, packed, one context over two
-device slots), the overflow / redo path."""
+device slots, ASCII with host threads packing sub-batches on the fly), the overflow / redo path."""
 import os
 import sys
 
@@ -28,6 +28,15 @@ def main():
     multi = Index(Params(), devices=[0, 0]); multi.add_batch(names, g, go); multi.freeze()
     assert multi.map_batch(rb, ro).tobytes() == hits.tobytes()
     ix.close(); multi.close()
+    # on-the-fly packing: small sub-batches so that this input is cut into ~10 of them and both routes are taken
+    os.environ["MQ_SUB_BASES"] = str(1 << 17)
+    hy = Index(Params()); hy.add_batch(names, g, go); hy.freeze(); hy.set_host_threads(3)
+    rb2 = rb.copy(); rb2[1000:1040] = ord("N"); rb2[-5000:-4990] = ord("R")
+    plain = Index(Params()); plain.add_batch(names, g, go); plain.freeze()
+    want = plain.map_batch(rb2, ro)
+    for _ in range(2):
+        assert hy.map_batch(rb2, ro).tobytes() == want.tobytes() and hy.last_counter("host_packed_sub_batches") >= 1
+    hy.close(); plain.close(); del os.environ["MQ_SUB_BASES"]
     print("sanitize smoke ok")
 
 
