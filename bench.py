@@ -260,22 +260,17 @@ def build_index_ranks(ix, g, go, names, p, rank, world, dist, torch, device, L):
             slot[q] = off; off += counts[q][0]; order.append(q)
     torch.cuda.synchronize(); dist.barrier()
     tg = time.perf_counter()
-    if all(c[0] > 0 for c in counts):
-        # one grouped collective per array: every rank's share lands in place at its exact size (uneven all-gather: NCCL
-        # runs the per-rank broadcasts of a group concurrently), no padding, no concatenation copies
-        for t, w in ((pos_t, 4), (hash_t, 8)):
-            views = [t[slot[q] * w:(slot[q] + counts[q][0]) * w] for q in range(world)]
-            dist.all_gather(views, views[rank])
-    else:
-        works = []
-        for q in range(world):
-            cnt = counts[q][0]
-            if cnt == 0:
-                continue
-            works.append(dist.broadcast(pos_t[slot[q] * 4:(slot[q] + cnt) * 4], src=q, async_op=True))
-            works.append(dist.broadcast(hash_t[slot[q] * 8:(slot[q] + cnt) * 8], src=q, async_op=True))
-        for w in works:
-            w.wait()
+    # one in-place broadcast per rank and array (exact sizes, no padding, no concatenation copies), all in flight at once.
+    # (One uneven all_gather per array was tried instead: 6.0 ms against 2.6 ms at two GPUs.)
+    works = []
+    for q in range(world):
+        cnt = counts[q][0]
+        if cnt == 0:
+            continue
+        works.append(dist.broadcast(pos_t[slot[q] * 4:(slot[q] + cnt) * 4], src=q, async_op=True))
+        works.append(dist.broadcast(hash_t[slot[q] * 8:(slot[q] + cnt) * 8], src=q, async_op=True))
+    for w in works:
+        w.wait()
     torch.cuda.synchronize()
     t_exchange = time.perf_counter() - tg
     dirs = np.array([d for q in order for d in counts[q][1]], dtype=np.uint64).reshape(-1, 3)
