@@ -23,7 +23,7 @@ Printed JSON (one line, rank 0), see the contract in the task statement:
   e2e_packed     ASCII in host memory, mq_pack on all host threads of the rank + mq_map_batch_packed, pipelined by chunk,
                  all of it inside the timed region
   roofline       the dominant kernel k_scan_minimizers<hpc, packed> of the `value` region
-  parity         untimed: hits of the first >= 20,000 reads and every index count against the CPU oracle; all GPU paths
+  parity         untimed: hits of the first 100,000 reads and every index count against the CPU oracle; all GPU paths
                  byte-identical on all reads
   cpu_baseline   the CPU oracle (a port, not the upstream Rust binary) on the box's host cores (N = 1 only)
 """
@@ -289,7 +289,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", type=int, default=3, choices=[3, 2, 4])
     ap.add_argument("--reads", type=int, default=0, help="total reads per step (config 3) / per rank (config 2); default: the named workload")
-    ap.add_argument("--check", type=int, default=20000, help="reads compared with the CPU oracle inside the run (untimed)")
+    ap.add_argument("--check", type=int, default=100000, help="reads compared with the CPU oracle inside the run (untimed)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e-packed", action="store_true", help="skip the pack-inside-the-timed-region variant")
     ap.add_argument("--value-only", action="store_true", help="profiling runs (ncu launch lists): only the `value` region, no JSON line")

@@ -48,7 +48,11 @@ struct HBuf { void *p = nullptr; size_t cap = 0; };      // pinned host memory
 #define MQ_SUB_MBASES_LIGHT 512
 #endif
 constexpr uint64_t SUB_BASES = (uint64_t)MQ_SUB_MBASES << 20;             // bases per pipelined mapping sub-batch (ASCII from the host: 1 byte per base over PCIe)
-constexpr uint64_t SUB_BASES_LIGHT = (uint64_t)MQ_SUB_MBASES_LIGHT << 20; // ... when the upload is light or absent (packed, device-resident): fewer, fuller launches
+constexpr uint64_t SUB_BASES_LIGHT = (uint64_t)MQ_SUB_MBASES_LIGHT << 20; // ... when the upload is light (packed input from the host): fewer, fuller launches
+#ifndef MQ_SUB_MBASES_RESIDENT
+#define MQ_SUB_MBASES_RESIDENT 2048
+#endif
+constexpr uint64_t SUB_BASES_RESIDENT = (uint64_t)MQ_SUB_MBASES_RESIDENT << 20;   // ... when there is no upload at all (inputs in HBM): nothing to overlap, only launch gaps to lose
 constexpr uint64_t ADD_BASES = 256ull << 20;            // bases per pipelined index-build piece batch
 constexpr size_t   PAD = 256;                          // zeroed slack behind sequence buffers (word loads past the end)
 
@@ -112,7 +116,7 @@ struct mq_ctx {
     Slot2 slot[N_SLOTS];
     // on-the-fly packing of ASCII host input (mq_set_host_threads)
     int host_threads = 0;
-    uint64_t sub_bases = SUB_BASES, sub_bases_light = SUB_BASES_LIGHT;     // MQ_SUB_BASES (test knob, read at mq_create) shrinks both
+    uint64_t sub_bases = SUB_BASES, sub_bases_light = SUB_BASES_LIGHT, sub_bases_resident = SUB_BASES_RESIDENT;   // MQ_SUB_BASES (test knob, read at mq_create) sets all three
     PackBuf pack_buf[N_PACK_BUFS];
     uint64_t ctr_h2d_bytes = 0, ctr_host_packed_bases = 0, ctr_host_packed_subs = 0, ctr_subs = 0;   // of the last mapping call
     // minimizer store (reference side)
@@ -663,7 +667,7 @@ int map_pipeline(mq_ctx *c, const SeqInput &in, const uint64_t *offs, uint32_t n
     c->ctr_h2d_bytes = c->ctr_host_packed_bases = c->ctr_host_packed_subs = c->ctr_subs = 0;
     // sub-batch boundaries; the first one is an eighth of the size so that the GPU starts while the host prepares the next
     std::vector<uint32_t> cut{0};
-    const uint64_t sub = (in.packed || in.resident) ? c->sub_bases_light : c->sub_bases;
+    const uint64_t sub = in.resident ? c->sub_bases_resident : (in.packed ? c->sub_bases_light : c->sub_bases);
     for (uint32_t i0 = 0; i0 < n;) {
         const uint64_t want = offs[i0] + (i0 == 0 ? sub / 8 : sub);
         uint32_t i1 = (uint32_t)(std::upper_bound(offs + i0 + 1, offs + n + 1, want) - offs) - 1;
@@ -912,8 +916,10 @@ static int create_one(mq_ctx **out, const mq_params *p, int device) {
     c->p = *p; c->device = device; c->bound = hash_bound(p->density);
     if (const char *e = getenv("MQ_SUB_BASES")) {        // tests: many small sub-batches from small inputs
         const uint64_t v = strtoull(e, nullptr, 10);
-        if (v >= 4096) c->sub_bases = c->sub_bases_light = v;
+        if (v >= 4096) c->sub_bases = c->sub_bases_light = c->sub_bases_resident = v;
     }
+    if (const char *e = getenv("MQ_SUB_BASES_RESIDENT")) { const uint64_t v = strtoull(e, nullptr, 10); if (v >= 4096) c->sub_bases_resident = v; }   // tuning runs
+    if (const char *e = getenv("MQ_SUB_BASES_PACKED")) { const uint64_t v = strtoull(e, nullptr, 10); if (v >= 4096) c->sub_bases_light = v; }
     fill_tables(c->tab, p->l);
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->n_sm = prop.multiProcessorCount;
