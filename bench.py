@@ -429,7 +429,7 @@ def main():
 
     if args.value_only:
         print(f"[value-only] {total_reads * args.steps / (t_dev / 1e3):.0f} reads/s, scan kernel {scan_ms / max(args.steps, 1):.3f} ms per step "
-              f"of {t_dev / max(args.steps, 1):.3f}, {launches} launches", file=sys.stderr)
+              f"of {t_dev / max(args.steps, 1):.3f}, {launches} launches, stages {stage_ms}", file=sys.stderr)
         clocks.stop()
         return
 

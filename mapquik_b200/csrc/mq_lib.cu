@@ -1287,8 +1287,9 @@ namespace {
 int build_bloom(mq_ctx *c) {
     dfree(c->d_bloom); c->bloom_wmask = 0;
     if (const char *e = getenv("MQ_NO_BLOOM")) if (e[0] == '1') return MQ_OK;
-    uint64_t bits = 1ull << 16;
-    while (bits < 4 * c->n_unique && bits < (1ull << 33)) bits <<= 1;
+    uint64_t bits = 1ull << 16, per_key = 4;
+    if (const char *e = getenv("MQ_BLOOM_BITS")) { const uint64_t v = strtoull(e, nullptr, 10); if (v >= 1 && v <= 64) per_key = v; }   // tuning runs
+    while (bits < per_key * c->n_unique && bits < (1ull << 33)) bits <<= 1;
     const uint64_t words = bits / 64;
     int rc;
     if ((rc = ensure(c, c->d_bloom, words * 8))) return rc;
@@ -1299,7 +1300,9 @@ int build_bloom(mq_ctx *c) {
     CK(cudaGetLastError());
     // keep it in L2 while reads stream through: persisting lines for the filter, streaming for everything else on this stream
     cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, c->device) == cudaSuccess && prop.persistingL2CacheMaxSize > 0 && prop.accessPolicyMaxWindowSize > 0) {
+    if (!getenv("MQ_BLOOM_NO_PERSIST") && cudaGetDeviceProperties(&prop, c->device) == cudaSuccess && prop.persistingL2CacheMaxSize > 0 && prop.accessPolicyMaxWindowSize > 0) {
+        if (getenv("MQ_BLOOM_VERBOSE")) fprintf(stderr, "[bloom] %llu bytes, persistingL2CacheMaxSize %d, accessPolicyMaxWindowSize %d, l2CacheSize %d\n",
+                                                (unsigned long long)(words * 8), prop.persistingL2CacheMaxSize, prop.accessPolicyMaxWindowSize, prop.l2CacheSize);
         const size_t want = std::min<size_t>(words * 8, (size_t)prop.persistingL2CacheMaxSize);
         cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
         cudaStreamAttrValue av{};
