@@ -75,6 +75,15 @@ def test_bad_params_rejected_before_any_device_work():
     assert L.mq_create_multi(C.byref(h), C.byref(capi.Params(5, 31, 0.01, 1, 4, 11, 2000)), d, 0) == -1
 
 
+def test_null_context_calls_fail_cleanly():
+    """entry points that take a context reject NULL with a status code (nothing dereferenced, nothing thrown)"""
+    L = capi.lib()
+    assert L.mq_set_host_threads(None, 4) == -1
+    assert L.mq_last_counter(None, b"h2d_bytes") == 0
+    assert L.mq_device_count(None) == 0 and L.mq_launch_count(None) == 0
+    assert L.mq_map_batch(None, None, None, 0, None) == -1
+
+
 def test_upper_casing_mirror():
     from mapquik_b200 import to_upper_u8, concat
     assert to_upper_u8("acgtNn").tobytes() == b"ACGTNN"
