@@ -665,11 +665,12 @@ int map_pipeline(mq_ctx *c, const SeqInput &in, const uint64_t *offs, uint32_t n
     int rc;
     if ((rc = init_streams(c))) return rc;
     c->ctr_h2d_bytes = c->ctr_host_packed_bases = c->ctr_host_packed_subs = c->ctr_subs = 0;
-    // sub-batch boundaries; the first one is an eighth of the size so that the GPU starts while the host prepares the next
+    // sub-batch boundaries; from the host the first one is an eighth of the size so that the GPU starts while the next is
+    // still being uploaded (resident input: nothing to wait for, full size from the start)
     std::vector<uint32_t> cut{0};
     const uint64_t sub = in.resident ? c->sub_bases_resident : (in.packed ? c->sub_bases_light : c->sub_bases);
     for (uint32_t i0 = 0; i0 < n;) {
-        const uint64_t want = offs[i0] + (i0 == 0 ? sub / 8 : sub);
+        const uint64_t want = offs[i0] + ((i0 == 0 && !in.resident) ? sub / 8 : sub);
         uint32_t i1 = (uint32_t)(std::upper_bound(offs + i0 + 1, offs + n + 1, want) - offs) - 1;
         if (i1 <= i0) i1 = i0 + 1;
         cut.push_back(i1); i0 = i1;
