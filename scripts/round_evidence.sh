@@ -18,12 +18,12 @@ B3="python bench.py --reads 200000 --steps 2 --warmup 3 --no-cpu-baseline --no-e
 B2="python bench.py --config 2 --steps 2 --warmup 3 --no-cpu-baseline --no-e2e-packed --check 0"
 # launch list of the `value` region alone (index build + 5 packed-resident steps of 200,000 reads on config 3)
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/${tag}_launches.csv $B3 --value-only > gpurun_out/${tag}_ncu_launch.log 2>&1
-# config 2 scan launches: 0-2 index builds (ASCII, packed, packed), then per resident call two sub-batches (256 Mi bases, the rest);
-# MQ_SUB_BASES_RESIDENT=512Mi restores the 64 Mi / 512 Mi / rest cut the committed captures were taken with:
-# launch 4 = the 512 Mi-base packed one; the ASCII-resident region starts at launch 18: launch 19 = the 512 Mi-base ASCII one
+# config 2 scan launches: 0-2 index builds (ASCII, packed, packed), then per resident call one sub-batch (1 Gbp < 2 Gi bases);
+# MQ_SUB_BASES_RESIDENT=512Mi cuts a call into 512 Mi bases + the rest, the launch size of the committed captures:
+# launch 3 = the first 512 Mi-base packed one; the ASCII-resident region starts at launch 13 with the 512 Mi-base ASCII one
 export MQ_SUB_BASES_RESIDENT=536870912
-timeout 900 ncu --set full --import-source on --clock-control none -k regex:k_scan_minimizers -s 4 -c 1 -o gpurun_out/${tag}_scan_packed -f $B2 > gpurun_out/${tag}_ncu_sp.log 2>&1
-timeout 900 ncu --set full --import-source on --clock-control none -k regex:k_scan_minimizers -s 19 -c 1 -o gpurun_out/${tag}_scan_ascii -f $B2 > gpurun_out/${tag}_ncu_sa.log 2>&1
+timeout 900 ncu --set full --import-source on --clock-control none -k regex:k_scan_minimizers -s 3 -c 1 -o gpurun_out/${tag}_scan_packed -f $B2 > gpurun_out/${tag}_ncu_sp.log 2>&1
+timeout 900 ncu --set full --import-source on --clock-control none -k regex:k_scan_minimizers -s 13 -c 1 -o gpurun_out/${tag}_scan_ascii -f $B2 > gpurun_out/${tag}_ncu_sa.log 2>&1
 timeout 900 ncu --set full --import-source on --clock-control none -k regex:k_probe_match -s 7 -c 1 -o gpurun_out/${tag}_probe -f $B3 > gpurun_out/${tag}_ncu_pr.log 2>&1
 MQ_NO_BLOOM=1 timeout 900 ncu --set full --clock-control none -k regex:k_probe_match -s 7 -c 1 -o gpurun_out/${tag}_probe_nobloom -f $B3 > gpurun_out/${tag}_ncu_prn.log 2>&1
 timeout 900 ncu --set full --clock-control none -k regex:k_insert_kminmers -c 1 -o gpurun_out/${tag}_insert -f $B3 > gpurun_out/${tag}_ncu_in.log 2>&1
