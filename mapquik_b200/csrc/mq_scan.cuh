@@ -165,6 +165,7 @@ __device__ __noinline__ uint32_t overlay4(const ScanArgs &a, uint64_t x, uint32_
     return u;
 }
 __device__ __forceinline__ bool block_flag(const ScanArgs &a, uint64_t x) {
+    if (a.n_exc == 0) return false;                  // no exception interval in this slice: the bitmap is all zero
     const uint64_t blk = x >> 6;
     return (__ldg(a.flags + (blk >> 5)) >> (blk & 31)) & 1u;
 }
@@ -514,7 +515,8 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32, 32 / SCAN_WARPS) k_scan_minim
             const uint64_t r0 = max(tlo + c_lo, gs + 1) - 1, r1 = min(tlo + c_lo + Cs, ge);
             uint32_t w_prev, w0;
             packed_prefetch(a, tlo, gs, c_lo, gpl, own_lo, own_hi, w_prev, w0);       // in flight while the bitmap is read
-            generic = __any_sync(0xffffffffu, any_flag(a, r0, r1));
+            // a slice without a single exception interval (reads without N: the usual case) has an all-zero bitmap
+            generic = a.n_exc != 0 && __any_sync(0xffffffffu, any_flag(a, r0, r1));
             if (!generic) stage_chunk<HPC, true, false>(a, tlo, gs, c_lo, gpl, own_lo, own_hi, sb, cum_l, runm_l, ta, q, bad, w_prev, w0);
         } else {
             stage_chunk<HPC, false, false>(a, tlo, gs, c_lo, gpl, own_lo, own_hi, sb, cum_l, runm_l, ta, q, bad);
