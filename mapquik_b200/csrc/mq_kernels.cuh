@@ -655,12 +655,26 @@ __global__ void __launch_bounds__(128) k_chain(ChainArgs a) {
         // best / second-best chain score over references (mers.rs:110-129)
         uint64_t best_score = 0, second = 0; uint32_t groups = 0;
         uint32_t b_ref = 0, b_rc = 0, b_mapq = 0; uint64_t b_qs = 0, b_qe = 0, b_rs = 0, b_re = 0;
+        // leader = first Match of its reference.  Up to 32 Matches (nearly every read that gets here): one MATCH.ANY finds
+        // them all and the loop visits leaders only; longer lists test every Match against the ones before it.
+        const bool few = n <= 32;
+        uint32_t leaders = 0;
+        if (few) {
+            const uint32_t myref = lane < n ? (ms[lane].ref_rc >> 1) : 0xFFFFFFFFu;      // reference ids are < 2^31
+            const uint32_t same = __match_any_sync(0xffffffffu, myref);
+            leaders = __ballot_sync(0xffffffffu, lane < n && (uint32_t)(__ffs(same) - 1) == lane);
+        }
         for (uint32_t i = 0; i < n; i++) {
+            if (few) {
+                if (!leaders) break;
+                i = (uint32_t)__ffs(leaders) - 1; leaders &= leaders - 1;
+            }
             const uint32_t ref = ms[i].ref_rc >> 1;
-            // leader = first match of its reference
-            bool seen = false;
-            for (uint32_t q = lane; q < i; q += 32) seen |= (ms[q].ref_rc >> 1) == ref;
-            if (__any_sync(0xffffffffu, seen)) continue;
+            if (!few) {
+                bool seen = false;
+                for (uint32_t q = lane; q < i; q += 32) seen |= (ms[q].ref_rc >> 1) == ref;
+                if (__any_sync(0xffffffffu, seen)) continue;
+            }
             // C1: first match with the strictly greatest count (chain.rs:93-104)
             uint32_t bc = 0, bi = 0xFFFFFFFFu, glen = 0;
             for (uint32_t q = i + lane; q < n; q += 32) {
