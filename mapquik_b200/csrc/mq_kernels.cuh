@@ -457,6 +457,11 @@ __global__ void __launch_bounds__(128) k_probe_match(ProbeArgs a, Table t, Bloom
             const uint32_t j = j0 + lane;
             bool hit = false; Entry e; e.id = e.start = e.end = e.offrc = 0;
             uint32_t qstart = 0, qend = 0, qrev = 0;
+            // the next block's minimizers: in flight while this block waits for the filter and the table
+            if (j + 32 < M) {
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(a.hash + m0 + j + 32));
+                if ((lane & 1u) == 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.pos + m0 + j + 32));
+            }
             if (j < Q) {
                 uint64_t key = kminmer_hash_at(a.hash + m0 + j, a.k, &qrev);
                 qstart = __ldg(a.pos + m0 + j); qend = __ldg(a.pos + m0 + j + a.k - 1) + a.l;
