@@ -622,18 +622,20 @@ struct HostPacker {
                 mq_pack_units(seqs + job->base, job->n_bases, units * t / T, units * (t + 1) / T, (uint32_t *)pb.words.p, (uint32_t *)pb.flags.p,
                               job->part_exc[t], false);
             } catch (...) { ok = false; }
+            bool wake = false;
             {
                 std::lock_guard<std::mutex> lk(mu);
-                if (!ok) failed = true;
-                if (++job->done == T) {
+                if (!ok) { failed = true; wake = true; }
+                if (++job->done == T) {                            // the last thread out hands the sub-batch over
                     pb.exc.clear();
                     for (auto &v : job->part_exc) pb.exc.insert(pb.exc.end(), v.begin(), v.end());
                     ((uint32_t *)pb.flags.p)[units] = 0; ((uint32_t *)pb.flags.p)[units + 1] = 0;     // the stager reads one word past the slice
                     pb.state = 2; packing--;
                     ready.push_back(seq);
+                    wake = true;
                 }
             }
-            cv.notify_all();
+            if (wake) cv.notify_all();
         }
     }
     // next sub-batch for the uploader: a packed one if one is ready, else the next ASCII one from the front.
@@ -665,6 +667,7 @@ int map_pipeline(mq_ctx *c, const SeqInput &in, const uint64_t *offs, uint32_t n
     int rc;
     if ((rc = init_streams(c))) return rc;
     c->ctr_h2d_bytes = c->ctr_host_packed_bases = c->ctr_host_packed_subs = c->ctr_subs = 0;
+    for (auto &s : c->slot) s.pack_buf = -1;         // (a call that failed half-way may have left one set)
     // sub-batch boundaries; from the host the first one is an eighth of the size so that the GPU starts while the next is
     // still being uploaded (resident input: nothing to wait for, full size from the start)
     std::vector<uint32_t> cut{0};
