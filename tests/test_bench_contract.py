@@ -94,7 +94,7 @@ def test_committed_round_lines_keep_the_contract():
     per_launch = t["packed"]["dram_bytes_per_base"] * d2["config"]["bases_total"] * d2["steps"] / rf2["launches"]
     # (the committed line may have been printed from an earlier capture of the same kernel: same figure within a few per cent)
     assert abs(rf2["traffic"] - per_launch) < 0.1 * per_launch and 0.5 < rf2["traffic"] / rf2["algorithmic_bytes_per_launch"] < 1.5
-    assert 0 < rf2["issue"]["frac"] < 1 and abs(rf2["issue"]["thread_instructions_per_base"] - 32 * t["packed"]["warp_instructions_per_base"]) < 0.5
+    assert 0 < rf2["issue"]["frac"] < 1 and abs(rf2["issue"]["thread_instructions_per_base"] - 32 * t["packed"]["warp_instructions_per_base"]) < 1.5
     par = d2["parity"]
     assert par["paths_identical"] is True and par["hits_identical"] is True and par["index_identical"] is True and par["checked_reads"] >= 20000
     assert d2["e2e"]["value"] > d2["e2e_ascii_link_only"]["value"] and d2["e2e"]["h2d_bytes_per_step"] < d2["e2e_ascii_link_only"]["h2d_bytes_per_step"]
