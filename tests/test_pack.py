@@ -104,3 +104,22 @@ def test_pack_at_concurrent_ranges():
     assert np.array_equal(out, a)
     ref = PackedSeqs(a, n_threads=1)
     assert np.array_equal(words, ref.words) and np.array_equal(flags, ref.flags)
+
+
+def test_pack_narrow_path_equals_wide_path():
+    """the 64-bases-per-step (AVX-512 VBMI) and the 32-bases-per-step (AVX2) packers must write the same words, bitmap and
+    intervals; which one runs is decided once per process, so the narrow one is exercised in a child (MQ_PACK_NO_AVX512=1)"""
+    import os
+    import subprocess
+    import sys
+    rng = np.random.default_rng(99)
+    a = messy(rng, 300007)
+    a[1000:1100] = ord("a")                               # lower case, folded on request
+    here = PackedSeqs(a, n_threads=3, fold_case=True)
+    code = ("import sys, numpy as np; sys.path.insert(0, %r); from mapquik_b200 import PackedSeqs;"
+            "a = np.frombuffer(sys.stdin.buffer.read(), np.uint8); p = PackedSeqs(a, n_threads=3, fold_case=True);"
+            "sys.stdout.buffer.write(p.words.tobytes() + p.flags.tobytes() + p.exc.tobytes())") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ); env["MQ_PACK_NO_AVX512"] = "1"
+    r = subprocess.run([sys.executable, "-c", code], input=a.tobytes(), capture_output=True, env=env)
+    assert r.returncode == 0, r.stderr[-500:]
+    assert r.stdout == here.words.tobytes() + here.flags.tobytes() + here.exc.tobytes()
