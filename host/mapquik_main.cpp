@@ -23,6 +23,7 @@
 #include <algorithm>
 #include <chrono>
 #include <condition_variable>
+#include <functional>
 #include <memory>
 #include <mutex>
 #include <thread>
@@ -222,24 +223,65 @@ struct BatchQueue {          // single producer / single consumer over two slots
     std::mutex m; std::condition_variable cv; Batch slot[2]; int filled[2] = {0, 0};
 };
 // ---- block-parallel parser for plain (uncompressed) files ---------------------------------------------------
-// The file is consumed in blocks that are cut at record boundaries.  Per block: (1) worker threads index the
-// newlines of their slice, (2) one pass over the line table assembles records and a list of copy jobs,
-// (3) worker threads copy + upper-case the sequence pieces straight into the pinned batch buffer.
+// The file is consumed in blocks that are cut at record boundaries.  Per block:
+//   (1) worker threads index the newlines of their slice of the block (and note which lines start with '>' and whether
+//       any line ends in CR) -- the only pass besides (4) that reads the file bytes;
+//   (2) worker threads turn line ends into a running base count per line (`cum`: bases of the block before line i;
+//       header / '+' / quality lines count 0), so that any base of the batch can be located by binary search;
+//   (3) one pass over the RECORDS (header lines only, not every line) fills ids and offsets;
+//   (4) worker threads each own a range of the batch's bases, cut on 2,048-base units (one word of the packed format's
+//       block bitmap, so no two threads share a word and nothing is zeroed or OR-ed), gather the line pieces of their
+//       range through a small staging buffer and pack 64-base-aligned chunks with mq_pack_at at full SIMD width -- a
+//       60-column reference FASTA packs as fast as single-line reads; with --ascii they upper-case the pieces in place.
 int g_parse_threads = (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
-template <class Fn> void parallel_for(int n, Fn fn) {
-    if (n <= 1) { if (n == 1) fn(0); return; }
+
+// persistent workers: a block is a few milliseconds of work per phase, thread creation would be a tenth of it.
+// Never destroyed (die() may exit from inside a worker).
+struct Pool {
+    std::mutex m, run_m; std::condition_variable cv_go, cv_done;
     std::vector<std::thread> th;
-    for (int t = 1; t < n; t++) th.emplace_back([&fn, t] { fn(t); });
-    fn(0);
-    for (auto &x : th) x.join();
+    const std::function<void(int)> *fn = nullptr; int n = 0, next = 0, pending = 0;
+    void worker() {
+        for (;;) {
+            int t;
+            {
+                std::unique_lock<std::mutex> lk(m);
+                cv_go.wait(lk, [&] { return next < n; });
+                t = next++;
+            }
+            (*fn)(t);
+            { std::lock_guard<std::mutex> lk(m); if (--pending == 0) cv_done.notify_all(); }
+        }
+    }
+    void run(int n_, const std::function<void(int)> &f) {
+        if (n_ <= 1) { if (n_ == 1) f(0); return; }
+        std::lock_guard<std::mutex> one(run_m);
+        {
+            std::lock_guard<std::mutex> lk(m);
+            while ((int)th.size() < n_ - 1) { th.emplace_back([this] { worker(); }); th.back().detach(); }
+            fn = &f; next = 1; pending = n_ - 1; n = n_;
+        }
+        cv_go.notify_all();
+        f(0);
+        std::unique_lock<std::mutex> lk(m);
+        cv_done.wait(lk, [&] { return pending == 0; });
+        n = 0; next = 0;
+    }
+};
+Pool &the_pool() { static Pool *pool = new Pool; return *pool; }
+template <class Fn> void parallel_for(int n, Fn fn) {
+    const std::function<void(int)> f = fn;
+    the_pool().run(n, f);
 }
+
 struct BlockParser {
     // The file is mapped once; a block is a window [pos, pos + block_bytes) of the mapping that next_batch() advances
     // past the records it consumed -- no read() copy and no carry-over of an incomplete trailing record.
     int fd; bool fasta; size_t block_bytes;
     const char *base = nullptr; size_t file_size = 0, pos = 0;
     const char *raw = nullptr; size_t fill = 0; bool eof = false;
-    struct Job { size_t src, len, dst; };
+    bool populate = getenv("MQ_CLI_NO_POPULATE") == nullptr;
+    std::vector<uint32_t> nl, cum;            // per line: offset of its '\n' (or of the end of the block); bases before it
     BlockParser(int fd_, bool fasta_, size_t block_bytes_, size_t file_size_) : fd(fd_), fasta(fasta_), block_bytes(block_bytes_), file_size(file_size_) {
         if (file_size) {
             void *m = mmap(nullptr, file_size, PROT_READ, MAP_PRIVATE, fd, 0);
@@ -253,6 +295,19 @@ struct BlockParser {
         fill = std::min(block_bytes, file_size - pos);
         raw = base + pos;
         eof = pos + fill >= file_size;
+    }
+    size_t line_start(size_t i) const { return i ? (size_t)nl[i - 1] + 1 : 0; }
+    // pieces of the batch's bases [d0, d1): fn(source pointer, length, first base)
+    template <class Fn> void for_pieces(size_t n_lines, uint64_t d0, uint64_t d1, Fn fn) const {
+        if (d0 >= d1) return;
+        size_t i = (size_t)(std::upper_bound(cum.begin(), cum.begin() + n_lines + 1, (uint32_t)d0) - cum.begin()) - 1;   // cum[i] <= d0 < cum[i+1]
+        uint64_t d = d0;
+        while (d < d1) {
+            while (cum[i + 1] == cum[i]) i++;
+            const uint64_t e = std::min<uint64_t>(cum[i + 1], d1);
+            fn(raw + line_start(i) + (d - cum[i]), (size_t)(e - d), d);
+            d = e; i++;
+        }
     }
     // fills B with the records of the next block; false when the file is exhausted
     bool next_batch(Batch &B) {
@@ -268,97 +323,203 @@ struct BlockParser {
         for (;;) {
             top_up();
             if (fill == 0) return false;
-            // (1) newline index
-            const int T = (int)std::max<size_t>(1, std::min<size_t>((size_t)g_parse_threads, fill / (4u << 20) + 1));
-            std::vector<std::vector<uint32_t>> nlv(T);
+            // (1) newline index; a line is a header iff it starts with '>' (FASTA)
+            const int T = (int)std::max<size_t>(1, std::min<size_t>((size_t)g_parse_threads, fill / (2u << 20) + 1));
+            std::vector<std::vector<uint32_t>> nlv(T), hdv(T);      // per slice: newline offsets; local indices of lines FOLLOWED by a header line
+            std::vector<char> crv(T, 0);
             parallel_for(T, [&](int t) {
                 size_t a = fill * (size_t)t / T, b = fill * (size_t)(t + 1) / T;
-                const char *p = raw + a, *e = raw + b;
-                auto &v = nlv[t];
-                while (p < e) { const char *q = (const char *)memchr(p, '\n', (size_t)(e - p)); if (!q) break; v.push_back((uint32_t)(q - raw)); p = q + 1; }
+                const char *p = raw + a, *e = raw + b, *end = raw + fill;
+#ifdef MADV_POPULATE_READ
+                if (populate) {                        // map the slice's pages in one call instead of one fault per 16 pages (Linux >= 5.14; ignored elsewhere)
+                    const uintptr_t pa = (uintptr_t)p & ~(uintptr_t)4095, pe = ((uintptr_t)e + 4095) & ~(uintptr_t)4095;
+                    if (madvise((void *)pa, pe - pa, MADV_POPULATE_READ) != 0) populate = false;
+                }
+#endif
+                auto &v = nlv[t]; auto &h = hdv[t];
+                v.reserve((size_t)(b - a) / 48 + 16);
+                bool cr = false;
+                while (p < e) {
+                    const char *q = (const char *)memchr(p, '\n', (size_t)(e - p));
+                    if (!q) break;
+                    if (q > raw && q[-1] == '\r') cr = true;
+                    if (fasta && q + 1 < end && q[1] == '>') h.push_back((uint32_t)v.size());
+                    v.push_back((uint32_t)(q - raw));
+                    p = q + 1;
+                }
+                crv[t] = cr;
             });
-            std::vector<uint32_t> nl;
-            { size_t tot = 0; for (auto &v : nlv) tot += v.size(); nl.reserve(tot + 1); for (auto &v : nlv) nl.insert(nl.end(), v.begin(), v.end()); }
-            lap("newlines");
-            if (eof && (nl.empty() || nl.back() != fill - 1)) nl.push_back((uint32_t)fill);     // last line without '\n'
-            // (2) records
-            std::vector<Job> jobs; size_t consumed = 0, dst = 0;
-            auto line = [&](size_t i, size_t &a, size_t &n) {
-                a = i ? (size_t)nl[i - 1] + 1 : 0; n = (size_t)nl[i] - a;
-                if (n && raw[a + n - 1] == '\r') n--;
-            };
-            if (fasta) {
-                bool open_rec = false; size_t last_hdr = 0;
-                for (size_t i = 0; i < nl.size(); i++) {
-                    size_t a, n; line(i, a, n);
-                    if (n && raw[a] == '>') {
-                        if (open_rec) B.offs.push_back(dst);
-                        B.ids.push_back(Fastx::id_of(raw + a, n)); open_rec = true; last_hdr = a;
-                    } else if (open_rec && n) { jobs.push_back({a, n, dst}); dst += n; }
-                }
-                if (eof) { if (open_rec) B.offs.push_back(dst); consumed = fill; }
-                else if (B.ids.size() >= 2) {          // the last record may continue in the next block: carry it
-                    while (!jobs.empty() && jobs.back().src > last_hdr) { dst -= jobs.back().len; jobs.pop_back(); }
-                    B.ids.pop_back(); consumed = last_hdr;
-                } else { B.clear(); jobs.clear(); dst = 0; }
-            } else {
-                const size_t nrec = nl.size() / 4;
-                for (size_t r = 0; r < nrec; r++) {
-                    size_t a, n; line(4 * r, a, n);
-                    if (!n || raw[a] != '@') die("malformed FASTQ record");
-                    B.ids.push_back(Fastx::id_of(raw + a, n));
-                    line(4 * r + 1, a, n);
-                    if (n) { jobs.push_back({a, n, dst}); dst += n; }
-                    B.offs.push_back(dst);
-                }
-                consumed = nrec ? (size_t)nl[4 * nrec - 1] + 1 : 0;
-                if (eof) consumed = fill;
+            std::vector<size_t> lbase(T + 1, 0);
+            for (int t = 0; t < T; t++) lbase[t + 1] = lbase[t] + nlv[t].size();
+            size_t n_lines = lbase[T];
+            bool last_open = false;                   // last line without '\n' (only at the end of the file)
+            {
+                uint32_t last_nl = 0; bool any = false;
+                for (int t = T - 1; t >= 0 && !any; t--) if (!nlv[t].empty()) { last_nl = nlv[t].back(); any = true; }
+                last_open = eof && (!any || (size_t)last_nl != fill - 1);
             }
-            if (B.ids.empty() && !eof) {                  // not even one complete record in the window: enlarge it
-                if (block_bytes >= (size_t)3 << 30) die("record larger than 3 GB");      // line offsets are 32-bit
-                block_bytes *= 2;
+            if (nl.size() < n_lines + 2) nl.resize(n_lines + 2 + n_lines / 4);
+            if (cum.size() < n_lines + 3) cum.resize(n_lines + 3 + n_lines / 4);
+            parallel_for(T, [&](int t) { if (!nlv[t].empty()) memcpy(nl.data() + lbase[t], nlv[t].data(), nlv[t].size() * 4); });
+            if (last_open) {
+                if (fill > 0 && raw[fill - 1] == '\r') crv[T - 1] = 1;
+                nl[n_lines++] = (uint32_t)fill;
+            }
+            bool any_cr = false; for (char c : crv) any_cr |= c != 0;
+            // header lines, in order (global line indices)
+            std::vector<uint32_t> hdr;
+            if (fasta) {
+                if (raw[0] == '>') hdr.push_back(0);
+                for (int t = 0; t < T; t++) for (uint32_t li : hdv[t]) hdr.push_back((uint32_t)(lbase[t] + li + 1));
+                while (!hdr.empty() && hdr.back() >= n_lines) hdr.pop_back();      // a '>' that is the very last byte of the block
+            }
+            lap("newlines");
+            // stripped end of line i
+            auto line_end = [&](size_t i) -> size_t {
+                size_t e = nl[i]; const size_t a = line_start(i);
+                if (any_cr && e > a && raw[e - 1] == '\r') e--;
+                return e;
+            };
+            // which records does the block hold, and how many of its lines belong to them
+            size_t n_rec = 0, used_lines = 0, consumed = 0;
+            if (fasta) {
+                n_rec = hdr.size();
+                used_lines = n_lines;
+                if (eof) consumed = fill;
+                else if (n_rec >= 2) { n_rec--; used_lines = hdr[n_rec]; consumed = line_start(used_lines); }   // the last record may continue in the next block
+                else n_rec = 0;
+            } else {
+                n_rec = n_lines / 4;
+                used_lines = 4 * n_rec;
+                consumed = eof ? fill : (n_rec ? (size_t)nl[used_lines - 1] + 1 : 0);
+            }
+            if (n_rec == 0 && !eof) {                     // not even one complete record in the window: enlarge it
+                if (block_bytes >= 0xFFFFFFF0ull) die("record larger than 4 GB");        // line offsets are 32-bit
+                block_bytes = (size_t)std::min<uint64_t>((uint64_t)block_bytes * 2, 0xFFFFFFF0ull);
                 continue;
             }
+            // (2) bases before every line: per-thread running sums over line ranges, then the thread bases
+            const int T1 = (int)std::max<size_t>(1, std::min<size_t>((size_t)g_parse_threads, used_lines / 65536 + 1));
+            std::vector<uint64_t> tsum(T1 + 1, 0);
+            const size_t first_seq_line = fasta ? (hdr.empty() ? used_lines : (size_t)hdr[0]) : 0;   // FASTA: lines before the first header belong to no record
+            auto line_bases = [&](size_t i, size_t &hp) -> uint32_t {      // hp: cursor into hdr (FASTA)
+                if (fasta) {
+                    if (i < first_seq_line) return 0;
+                    while (hp < hdr.size() && hdr[hp] < i) hp++;
+                    if (hp < hdr.size() && hdr[hp] == i) return 0;
+                } else if ((i & 3) != 1) return 0;
+                return (uint32_t)(line_end(i) - line_start(i));
+            };
+            parallel_for(T1, [&](int t) {
+                const size_t l0 = used_lines * (size_t)t / T1, l1 = used_lines * (size_t)(t + 1) / T1;
+                size_t hp = fasta ? (size_t)(std::lower_bound(hdr.begin(), hdr.end(), (uint32_t)l0) - hdr.begin()) : 0;
+                uint64_t s = 0;
+                for (size_t i = l0; i < l1; i++) { cum[i] = (uint32_t)s; s += line_bases(i, hp); }
+                tsum[t + 1] = s;
+            });
+            for (int t = 0; t < T1; t++) tsum[t + 1] += tsum[t];
+            const uint64_t dst = tsum[T1];
+            if (dst >= 0xFFFFFFFFull) die("block holds 2^32 bases or more");
+            parallel_for(T1, [&](int t) {
+                if (t == 0 || tsum[t] == 0) return;
+                const size_t l0 = used_lines * (size_t)t / T1, l1 = used_lines * (size_t)(t + 1) / T1;
+                const uint32_t add = (uint32_t)tsum[t];
+                for (size_t i = l0; i < l1; i++) cum[i] += add;
+            });
+            cum[used_lines] = (uint32_t)dst; cum[used_lines + 1] = (uint32_t)dst + 1;       // sentinel: the piece walk stops on a non-empty "line"
+            lap("lines");
+            // (3) records
+            B.ids.reserve(n_rec); B.offs.reserve(n_rec + 1);
+            if (fasta) {
+                for (size_t r = 0; r < n_rec; r++) {
+                    const size_t li = hdr[r];
+                    B.ids.push_back(Fastx::id_of(raw + line_start(li), line_end(li) - line_start(li)));
+                    B.offs.push_back(r + 1 < hdr.size() && hdr[r + 1] <= used_lines ? cum[hdr[r + 1]] : (uint32_t)dst);
+                }
+            } else {
+                for (size_t r = 0; r < n_rec; r++) {
+                    const size_t a = line_start(4 * r), n = line_end(4 * r) - a;
+                    if (!n || raw[a] != '@') die("malformed FASTQ record");
+                    B.ids.push_back(Fastx::id_of(raw + a, n));
+                    B.offs.push_back(cum[4 * r + 2]);
+                }
+            }
             lap("records");
-            // (3) copy into the pinned batch: packed (2 bits per base, upper-casing folded in) or upper-cased ASCII
-            const int T2 = (int)std::max<size_t>(1, std::min<size_t>((size_t)g_parse_threads, dst / (4u << 20) + 1));
-            std::vector<size_t> cut(T2 + 1, jobs.size()); cut[0] = 0;
-            { size_t j = 0; for (int t = 1; t < T2; t++) { const size_t want = dst * (size_t)t / T2; while (j < jobs.size() && jobs[j].dst < want) j++; cut[t] = j; } }
+            // (4) sequence bytes into the pinned batch: packed (2 bits per base, upper-casing folded in) or upper-cased ASCII
             if (g_pack) {
-                const size_t cap_bases = std::max(dst, block_bytes) + 64;
+                const size_t cap_bases = std::max<size_t>(dst, block_bytes) + 64;
                 const size_t wbytes = (size_t)mq_packed_words(cap_bases) * 4, fbytes = (size_t)mq_packed_flag_words(cap_bases) * 4;
                 B.words.reserve(wbytes); B.flags.reserve(fbytes);            // sized once per slot
                 B.words.size = (size_t)mq_packed_words(dst) * 4; B.flags.size = (size_t)mq_packed_flag_words(dst) * 4;
                 B.packed = true; B.n_bases = dst;
                 lap("reserve");
+                const uint64_t units = (dst + 2047) / 2048;
+                const int T2 = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)g_parse_threads, units / 1024 + 1));
                 std::vector<std::vector<mq_exc>> ex(T2);
+                uint32_t *words = (uint32_t *)B.words.p, *flags = (uint32_t *)B.flags.p;
                 parallel_for(T2, [&](int t) {
-                    // zero my share of the destination first: mq_pack_at ORs the edge words of a range in
-                    const size_t w0 = B.words.size * (size_t)t / T2 & ~(size_t)3, w1 = t + 1 == T2 ? B.words.size : (B.words.size * (size_t)(t + 1) / T2 & ~(size_t)3);
-                    memset(B.words.p + w0, 0, w1 - w0);
-                    if (t == 0) memset(B.flags.p, 0, B.flags.size);
-                });
-                parallel_for(T2, [&](int t) {
-                    std::vector<mq_exc> tmp(256);
-                    for (size_t j = cut[t]; j < cut[t + 1]; j++) {
+                    const uint64_t u0 = units * (uint64_t)t / T2, u1 = units * (uint64_t)(t + 1) / T2;
+                    const uint64_t d0 = u0 * 2048, d1 = std::min<uint64_t>(dst, u1 * 2048);
+                    memset(flags + u0, 0, (size_t)(u1 - u0) * 4);
+                    if (t + 1 == T2) {                 // the ragged tail is OR-ed in, and the slack behind the last base reads as zero
+                        const uint64_t tail = dst & ~31ull;
+                        memset(words + (tail >> 4), 0, B.words.size - (size_t)(tail >> 4) * 4);
+                        memset(flags + units, 0, B.flags.size - (size_t)units * 4);
+                    }
+                    std::vector<mq_exc> tmp(256); auto &out = ex[t];
+                    auto pack = [&](const uint8_t *src, uint64_t n, uint64_t at) {
+                        if (!n) return;
                         uint64_t ne = 0;
-                        int rc = mq_pack_at((const uint8_t *)raw + jobs[j].src, jobs[j].len, jobs[j].dst, (uint32_t *)B.words.p, (uint32_t *)B.flags.p,
-                                            tmp.data(), tmp.size(), &ne, 1);
+                        int rc = mq_pack_at(src, n, at, words, flags, tmp.data(), tmp.size(), &ne, 1);
                         if (rc == MQ_ERR_RANGE) {      // more exception intervals than the scratch list holds: the codes are in place, list them again
                             tmp.resize((size_t)ne + 16);
-                            rc = mq_pack_at((const uint8_t *)raw + jobs[j].src, jobs[j].len, jobs[j].dst, (uint32_t *)B.words.p, (uint32_t *)B.flags.p,
-                                            tmp.data(), tmp.size(), &ne, 1);
+                            rc = mq_pack_at(src, n, at, words, flags, tmp.data(), tmp.size(), &ne, 1);
                         }
                         if (rc != MQ_OK) die("mq_pack_at failed");
-                        ex[t].insert(ex[t].end(), tmp.begin(), tmp.begin() + (size_t)ne);
-                    }
+                        for (uint64_t k = 0; k < ne; k++) {       // an interval that continues the previous chunk's last one is merged
+                            const mq_exc &e = tmp[k];
+                            if (!out.empty() && out.back().byte == e.byte && out.back().start + out.back().len == e.start &&
+                                (uint64_t)out.back().len + e.len <= 0xFFFFFFFFull) out.back().len += e.len;
+                            else out.push_back(e);
+                        }
+                    };
+                    // staging: bases [sb, sb + sn) of the batch, sb a multiple of 64
+                    constexpr size_t STAGE = 8192;
+                    alignas(64) uint8_t stage[STAGE + 64];
+                    uint64_t sb = d0; size_t sn = 0;
+                    auto flush = [&](bool all) {
+                        const size_t n = all ? sn : (sn & ~(size_t)63);
+                        pack(stage, n, sb);
+                        if (n < sn) memmove(stage, stage + n, sn - n);
+                        sb += n; sn -= n;
+                    };
+                    for_pieces(used_lines, d0, d1, [&](const char *src, size_t len, uint64_t) {
+                        while (len) {
+                            if (len >= 256) {              // long piece: top the staging buffer up to a 64-base boundary, then straight from the file
+                                if (sn & 63) { const size_t take = 64 - (sn & 63); memcpy(stage + sn, src, take); sn += take; src += take; len -= take; }
+                                flush(false);
+                                const size_t n = len & ~(size_t)63;
+                                pack((const uint8_t *)src, n, sb);
+                                sb += n; src += n; len -= n;
+                                continue;
+                            }
+                            const size_t take = std::min(len, STAGE - sn);
+                            memcpy(stage + sn, src, take);
+                            sn += take; src += take; len -= take;
+                            if (sn == STAGE) flush(false);
+                        }
+                    });
+                    flush(true);
                 });
                 for (auto &v : ex) B.exc.insert(B.exc.end(), v.begin(), v.end());     // thread order == position order
             } else {
-                B.seqs.reserve(std::max(dst, block_bytes) + 64); B.seqs.size = dst;     // sequence bytes never exceed the block: one allocation per slot
+                B.seqs.reserve(std::max<size_t>(dst, block_bytes) + 64); B.seqs.size = dst;     // sequence bytes never exceed the block: one allocation per slot
                 lap("reserve");
-                if (!jobs.empty())
-                    parallel_for(T2, [&](int t) { for (size_t j = cut[t]; j < cut[t + 1]; j++) copy_upper(B.seqs.p + jobs[j].dst, raw + jobs[j].src, jobs[j].len); });
+                const int T2 = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)g_parse_threads, dst / (2u << 20) + 1));
+                parallel_for(T2, [&](int t) {
+                    for_pieces(used_lines, dst * (uint64_t)t / T2, dst * (uint64_t)(t + 1) / T2,
+                               [&](const char *src, size_t len, uint64_t d) { copy_upper(B.seqs.p + d, src, len); });
+                });
             }
             lap("copy");
             {   // the consumed part of the mapping is not needed again: drop it from this process's resident set
@@ -482,7 +643,10 @@ int main(int argc, char **argv) {
         uint64_t h = 1469598103934665603ull, nrec = 0, nbase = 0;
         auto mixb = [&](const uint8_t *p, size_t n) { for (size_t i = 0; i < n; i++) { h ^= p[i]; h *= 1099511628211ull; } };
         std::vector<uint8_t> rec;
-        for_each_batch(o.reads, is_fasta_name(o.reads), 256u << 20, [&](Batch &B) {
+        static const bool no_digest = getenv("MQ_CLI_NODIGEST") != nullptr;     // parser throughput runs: count only
+        const size_t bb = getenv("MQ_CLI_BATCH") ? (size_t)atol(getenv("MQ_CLI_BATCH")) : (size_t)(256u << 20);
+        for_each_batch(o.reads, is_fasta_name(o.reads), bb, [&](Batch &B) {
+            if (no_digest) { nrec += B.ids.size(); nbase += B.offs.back(); return; }
             for (size_t i = 0; i < B.ids.size(); i++) {
                 mixb((const uint8_t *)B.ids[i].data(), B.ids[i].size()); mixb((const uint8_t *)"\n", 1);
                 B.record_bytes(i, rec);

@@ -195,6 +195,43 @@ def test_parser_paths_agree(tmp_path):
     assert digests["a.fa"].startswith(f"records 300 bases {n_bases} ")
 
 
+def test_parser_parallel_phases_on_large_wrapped_input(tmp_path):
+    # enough lines and bases that every phase of the block-parallel parser runs on several threads (line sums split over
+    # line ranges, packing split over 2,048-base units): 60- and 80-column records with soft-masked stretches, N-gaps longer
+    # than the staging buffer, an 'r', one very long single line (straight-from-the-file packing), CRLF -- against the serial
+    # zlib reader, as ASCII and packed, at several thread counts and block sizes
+    import numpy as np
+    rng = np.random.default_rng(11)
+    recs = []
+    for i, n in enumerate([2_500_001, 63, 1_700_000, 0, 3_000_000, 900_037]):
+        s = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, n)].copy()
+        if n > 100000:
+            s[5000:5000 + 20011] = ord("N")                                   # a gap over several staging chunks
+            s[70000:90000] = np.frombuffer(b"acgt", np.uint8)[rng.integers(0, 4, 20000)]
+            s[n // 2] = ord("r")
+            s[rng.integers(0, n, 50)] = ord("n")
+        recs.append((f"chr{i} len={n}".encode(), s.tobytes()))
+    def fasta(widths, eol=b"\n"):
+        out = []
+        for (h, s), w in zip(recs, widths):
+            out.append(b">" + h + eol)
+            out += [s + eol] if w is None else [s[j:j + w] + eol for j in range(0, len(s), w)]
+        return b"".join(out)
+    files = {"w60.fa": fasta([60, 60, 80, 60, None, 61]), "crlf.fa": fasta([70, None, 60, 60, 60, None], b"\r\n")}
+    want = None
+    for name, data in files.items():
+        (tmp_path / name).write_bytes(data)
+        with gzip.open(tmp_path / (name + ".gz"), "wb", compresslevel=1) as f:
+            f.write(data)
+        serial = _digest(tmp_path / (name + ".gz"))
+        want = want or serial
+        assert serial == want, name
+        for env, th in (({}, 8), ({"MQ_CLI_PACK": "1"}, 8), ({"MQ_CLI_PACK": "1"}, 3), ({"MQ_CLI_PACK": "1", "MQ_CLI_BLOCK": "4000000"}, 5),
+                        ({"MQ_CLI_BLOCK": "3100000"}, 8), ({"MQ_CLI_PACK": "1", "MQ_CLI_NO_POPULATE": "1"}, 2)):
+            assert _digest(tmp_path / name, env, th) == want, (name, env, th)
+    assert want.startswith(f"records 6 bases {sum(len(s) for _, s in recs)} ")
+
+
 @pytest.mark.gpu
 def test_cli_input_formats_and_device_lists_agree(tmp_path):
     """the packed parser (default), --ascii, a multi-GPU context (--devices, a one-GPU box lists its device twice), lz4
