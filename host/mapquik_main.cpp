@@ -5,10 +5,11 @@
 //     mapquik <reads.fa|fq[.gz|.lz4]> --reference <ref.fa[.gz|.lz4]> [-k K] [-l L] [-d D] [-c C] [-s S] [-g G]
 //             [-p PREFIX] [--nohpc] [--threads N] [-b B] [-q Q] [--low-memory] [--nosimd]
 //             [--parallelfastx] [--debug] [--gpu ID | --gpus N] [--ascii] [--save-index F] [--load-index F] [--rescue k,l,d]
-// Host I/O: one reader thread parses records straight into pinned batch buffers while the main thread maps the previous
-// batch on the GPU(s) and writes its PAF lines in input order (closures.rs:117-123).  Where the reference upper-cases a
-// copy of every record (closures.rs:63,106), the block-parallel parser PACKS it (mq_pack_at: 2-bit codes + exception
-// intervals, upper-casing folded in), so a quarter of the bytes cross PCIe; --ascii keeps one byte per base.
+// Host I/O: a reader thread (plus a worker pool, plus a decompressor thread for gz / lz4) parses records straight into
+// pinned batch buffers while the main thread maps the previous batch on the GPU(s) and writes its PAF lines in input
+// order (closures.rs:117-123).  Where the reference upper-cases a copy of every record (closures.rs:63,106), the
+// block-parallel parser PACKS it (mq_pack_at: 2-bit codes + exception intervals, upper-casing folded in), so a quarter
+// of the bytes cross PCIe; --ascii keeps one byte per base.
 // All compute happens in the library.
 #include "../include/mapquik_b200.h"
 
@@ -120,21 +121,17 @@ struct PinnedBuf {
         if (p) release(p);
         p = np; cap = nc;
     }
-    void append_upper(const char *src, size_t n) { reserve(size + n); copy_upper(p + size, src, n); size += n; }
     void clear() { size = 0; }
 };
 
-// FASTA / FASTQ reader (gz transparently via zlib; multi-line FASTA accepted).  Lines are handed out as
-// views into a large refillable buffer; only lines that straddle a refill are copied.
-struct Fastx {
-    gzFile f = nullptr; int fd = -1; bool fasta;     // plain files bypass zlib (read(2) straight into the buffer)
+// An input file: plain (regular files are mapped), gzip (zlib) or lz4 frames (main.rs:68,71).  Everything that is not a
+// plain regular file is a byte stream that a feeder thread decompresses ahead of the parser.
+struct Input {
+    gzFile f = nullptr; int fd = -1; bool fasta;
     std::unique_ptr<Lz4Reader> lz4;
-    std::vector<char> buf; size_t pos = 0, len = 0; bool eof = false;
-    std::string spill;            // storage for a line that straddled a refill
-    size_t file_bytes = ~(size_t)0 >> 1;   // on-disk size of a plain file (bounds the batch allocation)
-    bool regular = false;                  // plain regular file with a known size (block-parallel parser)
-    bool have_hdr = false; std::string hdr;   // FASTA header already consumed
-    Fastx(const std::string &path, bool fasta_) : fasta(fasta_) {
+    size_t file_bytes = 0;                 // size of a plain regular file
+    bool regular = false;                  // plain regular file with a known size: mmap
+    Input(const std::string &path, bool fasta_) : fasta(fasta_) {
         unsigned char magic[2] = {0, 0};
         fd = open(path.c_str(), O_RDONLY);
         if (fd < 0) die("Error opening file: " + path);
@@ -150,58 +147,46 @@ struct Fastx {
             posix_fadvise(fd, 0, 0, POSIX_FADV_SEQUENTIAL);
             struct stat st; if (fstat(fd, &st) == 0 && S_ISREG(st.st_mode)) { file_bytes = (size_t)st.st_size; regular = true; }
         }
-        buf.resize(32u << 20);
     }
-    ~Fastx() { if (f) gzclose(f); if (fd >= 0) close(fd); }
-    bool refill() {
-        if (eof) return false;
-        long r = f ? (long)gzread(f, buf.data(), (unsigned)buf.size()) : lz4 ? lz4->read(buf.data(), buf.size()) : (long)read(fd, buf.data(), buf.size());
-        if (r <= 0) { eof = true; return false; }
-        pos = 0; len = (size_t)r;
-        return true;
-    }
-    // next line without its terminator; the view stays valid until the next call
-    bool getline(const char *&ptr, size_t &n) {
-        if (pos == len && !refill()) return false;
-        char *nl = (char *)memchr(buf.data() + pos, '\n', len - pos);
-        if (nl) { ptr = buf.data() + pos; n = (size_t)(nl - ptr); pos += n + 1; }
-        else {
-            spill.assign(buf.data() + pos, len - pos); pos = len;
-            for (;;) {
-                if (!refill()) break;
-                char *q = (char *)memchr(buf.data(), '\n', len);
-                if (q) { spill.append(buf.data(), (size_t)(q - buf.data())); pos = (size_t)(q - buf.data()) + 1; break; }
-                spill.append(buf.data(), len); pos = len;
-            }
-            ptr = spill.data(); n = spill.size();
-        }
-        if (n && ptr[n - 1] == '\r') n--;
-        return true;
+    ~Input() { if (f) gzclose(f); if (fd >= 0) close(fd); }
+    long read_some(char *dst, size_t cap) {      // next (decompressed) bytes of a stream; <= 0 at its end
+        return f ? (long)gzread(f, dst, (unsigned)std::min<size_t>(cap, 1u << 30)) : lz4 ? lz4->read(dst, cap) : (long)read(fd, dst, cap);
     }
     static std::string id_of(const char *p, size_t n) {       // seq_io record.id(): the header up to the first SPACE
         size_t e = 1; while (e < n && p[e] != ' ') e++;
         return std::string(p + 1, e - 1);
     }
-    // next record: id + upper-cased sequence appended to seq
-    bool next(std::string &id, PinnedBuf &seq) {
-        const char *p; size_t n;
-        if (fasta) {
-            if (have_hdr) { id = hdr; have_hdr = false; }
-            else { do { if (!getline(p, n)) return false; } while (n == 0 || p[0] != '>'); id = id_of(p, n); }
-            while (getline(p, n)) {
-                if (n && p[0] == '>') { hdr = id_of(p, n); have_hdr = true; break; }
-                seq.append_upper(p, n);
-            }
-            return true;
+};
+
+// decompresses a stream in chunks ahead of the parser (inflate is the slowest stage of a .gz input: it gets a thread of its own)
+struct Feeder {
+    static constexpr size_t CHUNK = 8u << 20; static constexpr int DEPTH = 12;
+    Input *in; std::mutex m; std::condition_variable cv; std::thread th;
+    struct Chunk { std::unique_ptr<char[]> p; size_t n = 0; };
+    std::vector<Chunk> ring; size_t head = 0, tail = 0;      // [head, tail) are full
+    bool done = false, quit = false;
+    explicit Feeder(Input *in_) : in(in_), ring(DEPTH) { th = std::thread([this] { run(); }); }
+    ~Feeder() { { std::lock_guard<std::mutex> lk(m); quit = true; } cv.notify_all(); th.join(); }
+    void run() {
+        for (;;) {
+            Chunk *c;
+            { std::unique_lock<std::mutex> lk(m); cv.wait(lk, [&] { return quit || tail - head < (size_t)DEPTH; }); if (quit) return; c = &ring[tail % DEPTH]; }
+            if (!c->p) c->p.reset(new char[CHUNK]);
+            size_t n = 0;
+            while (n < CHUNK) { const long r = in->read_some(c->p.get() + n, CHUNK - n); if (r <= 0) break; n += (size_t)r; }
+            c->n = n;
+            { std::lock_guard<std::mutex> lk(m); if (n) tail++; if (n < CHUNK) done = true; }
+            cv.notify_all();
+            if (n < CHUNK) return;
         }
-        do { if (!getline(p, n)) return false; } while (n == 0);
-        if (p[0] != '@') die("malformed FASTQ record");
-        id = id_of(p, n);
-        if (!getline(p, n)) return false;
-        seq.append_upper(p, n);
-        getline(p, n); getline(p, n);      // '+' line, qualities
-        return true;
     }
+    // the oldest full chunk (nullptr at the end of the stream); release() hands it back
+    const Chunk *front() {
+        std::unique_lock<std::mutex> lk(m);
+        cv.wait(lk, [&] { return head < tail || done; });
+        return head < tail ? &ring[head % DEPTH] : nullptr;
+    }
+    void release() { { std::lock_guard<std::mutex> lk(m); head++; } cv.notify_all(); }
 };
 
 // one batch of records; two of them rotate between the reader thread and the GPU
@@ -275,14 +260,16 @@ template <class Fn> void parallel_for(int n, Fn fn) {
 }
 
 struct BlockParser {
-    // The file is mapped once; a block is a window [pos, pos + block_bytes) of the mapping that next_batch() advances
-    // past the records it consumed -- no read() copy and no carry-over of an incomplete trailing record.
-    int fd; bool fasta; size_t block_bytes;
-    const char *base = nullptr; size_t file_size = 0, pos = 0;
+    // A plain file is mapped once; a block is a window [pos, pos + block_bytes) of the mapping that next_batch() advances
+    // past the records it consumed -- no read() copy and no carry-over of an incomplete trailing record.  A stream
+    // (gz / lz4 / pipe) is decompressed ahead by a Feeder; its block is a buffer that keeps the unconsumed tail.
+    bool fasta; size_t block_bytes;
+    const char *base = nullptr; size_t file_size = 0, pos = 0;             // mapped file
+    Feeder *feed = nullptr; std::unique_ptr<char[]> sbuf; size_t s_cap = 0, s_have = 0, s_off = 0; bool s_end = false;   // stream
     const char *raw = nullptr; size_t fill = 0; bool eof = false;
     bool populate = getenv("MQ_CLI_NO_POPULATE") == nullptr;
     std::vector<uint32_t> nl, cum;            // per line: offset of its '\n' (or of the end of the block); bases before it
-    BlockParser(int fd_, bool fasta_, size_t block_bytes_, size_t file_size_) : fd(fd_), fasta(fasta_), block_bytes(block_bytes_), file_size(file_size_) {
+    BlockParser(int fd, bool fasta_, size_t block_bytes_, size_t file_size_) : fasta(fasta_), block_bytes(block_bytes_), file_size(file_size_) {
         if (file_size) {
             void *m = mmap(nullptr, file_size, PROT_READ, MAP_PRIVATE, fd, 0);
             if (m == MAP_FAILED) die("mmap failed");
@@ -290,11 +277,40 @@ struct BlockParser {
             madvise(m, file_size, MADV_SEQUENTIAL);
         }
     }
+    BlockParser(Feeder *feed_, bool fasta_, size_t block_bytes_) : fasta(fasta_), block_bytes(block_bytes_), feed(feed_) { populate = false; }
     ~BlockParser() { if (base) munmap((void *)base, file_size); }
     void top_up() {                                   // position the window
-        fill = std::min(block_bytes, file_size - pos);
-        raw = base + pos;
-        eof = pos + fill >= file_size;
+        if (!feed) {
+            fill = std::min(block_bytes, file_size - pos);
+            raw = base + pos;
+            eof = pos + fill >= file_size;
+            return;
+        }
+        if (s_cap < block_bytes) {                    // (first call, or the window was enlarged)
+            std::unique_ptr<char[]> nb(new char[block_bytes]);
+            if (s_have) memcpy(nb.get(), sbuf.get(), s_have);
+            sbuf = std::move(nb); s_cap = block_bytes;
+        }
+        while (s_have < block_bytes && !s_end) {
+            const Feeder::Chunk *c = feed->front();
+            if (!c) { s_end = true; break; }
+            const size_t take = std::min(c->n - s_off, block_bytes - s_have);
+            memcpy(sbuf.get() + s_have, c->p.get() + s_off, take);
+            s_have += take; s_off += take;
+            if (s_off == c->n) { feed->release(); s_off = 0; }
+        }
+        raw = sbuf.get(); fill = s_have; eof = s_end;
+    }
+    void advance(size_t consumed) {                   // the block's first `consumed` bytes are done with
+        if (!feed) {
+            // the consumed part of the mapping is not needed again: drop it from this process's resident set
+            const size_t pg = 4096, a0 = pos & ~(pg - 1), a1 = (pos + consumed) & ~(pg - 1);
+            if (a1 > a0) madvise((void *)(base + a0), a1 - a0, MADV_DONTNEED);
+            pos += consumed;
+            return;
+        }
+        if (consumed < s_have) memmove(sbuf.get(), sbuf.get() + consumed, s_have - consumed);
+        s_have -= consumed;
     }
     size_t line_start(size_t i) const { return i ? (size_t)nl[i - 1] + 1 : 0; }
     // pieces of the batch's bases [d0, d1): fn(source pointer, length, first base)
@@ -433,14 +449,14 @@ struct BlockParser {
             if (fasta) {
                 for (size_t r = 0; r < n_rec; r++) {
                     const size_t li = hdr[r];
-                    B.ids.push_back(Fastx::id_of(raw + line_start(li), line_end(li) - line_start(li)));
+                    B.ids.push_back(Input::id_of(raw + line_start(li), line_end(li) - line_start(li)));
                     B.offs.push_back(r + 1 < hdr.size() && hdr[r + 1] <= used_lines ? cum[hdr[r + 1]] : (uint32_t)dst);
                 }
             } else {
                 for (size_t r = 0; r < n_rec; r++) {
                     const size_t a = line_start(4 * r), n = line_end(4 * r) - a;
                     if (!n || raw[a] != '@') die("malformed FASTQ record");
-                    B.ids.push_back(Fastx::id_of(raw + a, n));
+                    B.ids.push_back(Input::id_of(raw + a, n));
                     B.offs.push_back(cum[4 * r + 2]);
                 }
             }
@@ -522,40 +538,28 @@ struct BlockParser {
                 });
             }
             lap("copy");
-            {   // the consumed part of the mapping is not needed again: drop it from this process's resident set
-                const size_t pg = 4096, a0 = pos & ~(pg - 1), a1 = (pos + consumed) & ~(pg - 1);
-                if (a1 > a0) madvise((void *)(base + a0), a1 - a0, MADV_DONTNEED);
-            }
-            pos += consumed;
+            advance(consumed);
             B.last = eof && consumed == fill;
             return true;
         }
     }
 };
 
-void reader_thread(Fastx *fx, BatchQueue *q, size_t batch_bytes) {
-    int b = 0; std::string id;
+void reader_thread(Input *in, BatchQueue *q, size_t batch_bytes) {
+    int b = 0;
+    size_t blk = in->regular ? std::min<size_t>(batch_bytes, in->file_bytes + 1) : batch_bytes;
+    if (const char *e = getenv("MQ_CLI_BLOCK")) blk = (size_t)atol(e);      // tests: tiny blocks exercise the carry logic
+    blk = std::max<size_t>(blk, 64);
+    std::unique_ptr<Feeder> feed;
     std::unique_ptr<BlockParser> bp;
-    if (fx->fd >= 0 && fx->regular) {                    // plain regular file: block-parallel path
-        size_t blk = std::min<size_t>(batch_bytes, fx->file_bytes + 1);
-        if (const char *e = getenv("MQ_CLI_BLOCK")) blk = (size_t)atol(e);      // tests: tiny blocks exercise the carry logic
-        bp.reset(new BlockParser(fx->fd, fx->fasta, std::max<size_t>(blk, 64), fx->file_bytes));
-    }
+    if (in->regular) bp.reset(new BlockParser(in->fd, in->fasta, blk, in->file_bytes));
+    else { feed.reset(new Feeder(in)); bp.reset(new BlockParser(feed.get(), in->fasta, blk)); }
     for (;;) {
         { std::unique_lock<std::mutex> lk(q->m); q->cv.wait(lk, [&] { return !q->filled[b]; }); }
         Batch &B = q->slot[b];
         bool more = true;
-        if (bp) {
-            if (!bp->next_batch(B)) { B.clear(); more = false; }
-            else more = !B.last;
-        } else {
-            B.clear();
-            B.seqs.reserve(std::min<size_t>(batch_bytes, fx->file_bytes) + (48u << 20));   // one allocation per slot, no growth copies
-            while (B.seqs.size < batch_bytes) {
-                if (!fx->next(id, B.seqs)) { more = false; break; }
-                B.offs.push_back(B.seqs.size); B.ids.push_back(id);
-            }
-        }
+        if (!bp->next_batch(B)) { B.clear(); more = false; }
+        else more = !B.last;
         B.last = !more;
         { std::lock_guard<std::mutex> lk(q->m); q->filled[b] = 1; }
         q->cv.notify_all();
@@ -565,9 +569,9 @@ void reader_thread(Fastx *fx, BatchQueue *q, size_t batch_bytes) {
 }
 // run fn(batch) over every batch of the file; parsing of batch i+1 overlaps fn(batch i)
 template <class Fn> void for_each_batch(const std::string &path, bool fasta, size_t batch_bytes, Fn fn) {
-    Fastx fx(path, fasta);
+    Input in(path, fasta);
     BatchQueue q;
-    std::thread th(reader_thread, &fx, &q, batch_bytes);
+    std::thread th(reader_thread, &in, &q, batch_bytes);
     int b = 0;
     for (;;) {
         { std::unique_lock<std::mutex> lk(q.m); q.cv.wait(lk, [&] { return q.filled[b] != 0; }); }
