@@ -1674,13 +1674,29 @@ int mq_map_batch_packed_device(mq_ctx *c, const mq_packed *d_pk, const uint64_t 
     } catch (...) { c->err = "host allocation failed"; return MQ_ERR_NOMEM; }
 }
 
+// mers.rs:181 -- hand-rolled (a CLI writes millions of these per second of GPU time; snprintf with twelve conversions was
+// half a microsecond per line)
 int mq_format_paf(char *buf, size_t cap, const char *q_id, uint64_t q_len, const char *r_id, uint64_t r_len, const mq_hit *h) {
     if (!buf || !q_id || !r_id || !h) return MQ_ERR_ARG;
-    int w = snprintf(buf, cap, "%s\t%llu\t%llu\t%llu\t%s\t%s\t%llu\t%llu\t%llu\t%llu\t%llu\t%u", q_id, (unsigned long long)q_len,
-                     (unsigned long long)h->q_start, (unsigned long long)h->q_end, h->rc ? "-" : "+", r_id, (unsigned long long)r_len,
-                     (unsigned long long)h->r_start, (unsigned long long)h->r_end, (unsigned long long)h->score,
-                     (unsigned long long)r_len, (unsigned)h->mapq);
-    return (w < 0 || (size_t)w >= cap) ? MQ_ERR_ARG : w;
+    const size_t lq = strlen(q_id), lr = strlen(r_id);
+    if (cap < lq + lr + 10 * 20 + 16) {                          // (ten numbers of <= 20 digits, strand, eleven tabs, NUL always fit above that)
+        auto digits = [](uint64_t v) { size_t n = 1; while (v >= 10) { v /= 10; n++; } return n; };
+        const size_t need = lq + lr + digits(q_len) + digits(h->q_start) + digits(h->q_end) + 2 * digits(r_len) + digits(h->r_start) +
+                            digits(h->r_end) + digits(h->score) + digits(h->mapq) + 1 + 11 + 1;
+        if (cap < need) return MQ_ERR_ARG;
+    }
+    char *w = buf;
+    auto str = [&](const char *s_, size_t n) { memcpy(w, s_, n); w += n; *w++ = '\t'; };
+    auto num = [&](uint64_t v, char sep) {
+        char tmp[20]; int n = 0;
+        do { tmp[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+        while (n) *w++ = tmp[--n];
+        *w++ = sep;
+    };
+    str(q_id, lq); num(q_len, '\t'); num(h->q_start, '\t'); num(h->q_end, '\t');
+    *w++ = h->rc ? '-' : '+'; *w++ = '\t';
+    str(r_id, lr); num(r_len, '\t'); num(h->r_start, '\t'); num(h->r_end, '\t'); num(h->score, '\t'); num(r_len, '\t'); num(h->mapq, '\0');
+    return (int)(w - buf) - 1;
 }
 
 // ---- introspection (single-GPU contexts; synchronous) ---------------------------------------------------------

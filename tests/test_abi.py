@@ -47,6 +47,17 @@ def test_format_paf_golden_line():
     L.mq_format_paf(buf, 512, b"q", 10, b"r", 20, hit.ctypes.data)
     assert buf.value.decode().split("\t")[4] == "-"
     assert L.mq_format_paf(buf, 8, b"q", 10, b"r", 20, hit.ctypes.data) < 0      # buffer too small
+    # every column at its extremes; the line fits a buffer of exactly its length + NUL and nothing smaller
+    big = 2 ** 64 - 1
+    for q_len, r_len, fields in ((0, 0, (1, 0, 0, 0, 0, 0, 0, 0, 0, 0)), (big, big, (1, 1, 255, 0, 2 ** 32 - 1, big, big, big, big, big))):
+        hit[0] = fields
+        n = L.mq_format_paf(buf, 512, b"read/1", q_len, b"chrUn_x", r_len, hit.ctypes.data)
+        h = hit[0]
+        want = "\t".join(str(x) for x in ("read/1", q_len, int(h["q_start"]), int(h["q_end"]), "-" if h["rc"] else "+", "chrUn_x", r_len,
+                                          int(h["r_start"]), int(h["r_end"]), int(h["score"]), r_len, int(h["mapq"])))
+        assert n == len(want) and buf.value.decode() == want
+        assert L.mq_format_paf(buf, n + 1, b"read/1", q_len, b"chrUn_x", r_len, hit.ctypes.data) == n
+        assert L.mq_format_paf(buf, n, b"read/1", q_len, b"chrUn_x", r_len, hit.ctypes.data) < 0
 
 
 def test_no_cpu_fallback(have_gpu):
