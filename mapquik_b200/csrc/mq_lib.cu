@@ -3,8 +3,8 @@
 // MQ_ERR_CUDA when no CUDA device is usable.
 //
 // Shape of the mapping path (mq_map_batch*): the batch is cut into sub-batches of <= SUB_BASES bases that flow
-// through two slots -- upload of sub-batch i+1 (copy stream) overlaps the kernels of sub-batch i (compute stream) and
-// the download of the hits of sub-batch i-1 (d2h stream).  The host never waits for the GPU between the upload of a
+// through four slots -- uploads (copy stream) run ahead of the kernels (compute stream), which run ahead of the
+// downloads of the hits (d2h stream).  The host never waits for the GPU between the upload of a
 // sub-batch and the download of its hits: tile tables are computed on the host from the offsets it already has,
 // device buffers are sized from upper bounds, and the one thing only the GPU knows (how many minimizers a sub-batch
 // produced, whether a pool overflowed) comes back in a 48-byte status record next to the hits and is looked at when

@@ -3,7 +3,7 @@
 parser / --ascii / --gpus N), checks that every mode writes the byte-identical PAF and that it equals the library's own
 hits, prints the timings as JSON.
 
-    python scripts/cli_e2e.py [--config 2|3] [--reads N] [--gpus N]
+    python scripts/cli_e2e.py [--config 2|3] [--reads N] [--gpus N] [--wrap COLUMNS]
 """
 import argparse
 import json
@@ -19,12 +19,23 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def write_fasta(path, names, buf, offs):
+def write_fasta(path, names, buf, offs, wrap=0):
+    """one line per record, or `wrap` columns per line (what reference FASTA files look like)"""
     with open(path, "wb") as f:
         for i, n in enumerate(names):
             f.write(b">" + n.encode() + b"\n")
-            f.write(buf[int(offs[i]):int(offs[i + 1])].tobytes())
-            f.write(b"\n")
+            s = buf[int(offs[i]):int(offs[i + 1])]
+            if wrap and s.size:
+                full = s.size // wrap * wrap
+                if full:
+                    lines = np.empty((full // wrap, wrap + 1), np.uint8)
+                    lines[:, :wrap] = s[:full].reshape(-1, wrap); lines[:, wrap] = 10
+                    f.write(lines.tobytes())
+                if full < s.size:
+                    f.write(s[full:].tobytes() + b"\n")
+            else:
+                f.write(s.tobytes())
+                f.write(b"\n")
 
 
 def main():
@@ -32,6 +43,7 @@ def main():
     ap.add_argument("--config", type=int, default=2)
     ap.add_argument("--reads", type=int, default=0)
     ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--wrap", type=int, default=0, help="write the reference with this many columns per line (0: one line per record)")
     a = ap.parse_args()
     from mapquik_b200 import Index, Params, sim
     import bench
@@ -41,7 +53,7 @@ def main():
     rb, ro, rn, _ = sim.reads(cfg["seed"], g, go, n_reads, cfg["mean"], cfg["sd"], cfg["min_len"], cfg["err"], contig_names=names)
     d = tempfile.mkdtemp(prefix="mq_cli_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
     ref, reads = os.path.join(d, "ref.fa"), os.path.join(d, "reads.fa")
-    write_fasta(ref, names, g, go); write_fasta(reads, rn, rb, ro)
+    write_fasta(ref, names, g, go, a.wrap); write_fasta(reads, rn, rb, ro)
     subprocess.check_call(["make", "-C", os.path.join(ROOT, "host"), "-s"])
     ix = Index(Params()); ix.add_batch(names, g, go); ix.freeze()
     hits = ix.map_batch(rb, ro)
@@ -51,7 +63,8 @@ def main():
     if a.gpus > 1:
         modes[f"packed_{a.gpus}gpu"] = ["--gpus", str(a.gpus)]
         modes[f"ascii_{a.gpus}gpu"] = ["--gpus", str(a.gpus), "--ascii"]
-    out = {"config": a.config, "reads": n_reads, "read_bp": int(ro[-1]), "genome_bp": int(go[-1]), "modes": {}}
+    out = {"config": a.config, "reads": n_reads, "read_bp": int(ro[-1]), "genome_bp": int(go[-1]), "reference_columns": a.wrap or None,
+           "reference_file_bytes": os.path.getsize(ref), "reads_file_bytes": os.path.getsize(reads), "host_cores": os.cpu_count(), "modes": {}}
     for tag, extra in modes.items():
         best = None
         for rep in range(2):                     # second run: files are in the page cache, CUDA modules loaded once more
