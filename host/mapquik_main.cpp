@@ -20,6 +20,9 @@
 #include <unistd.h>
 #include <zlib.h>
 #include <dlfcn.h>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 
 #include <algorithm>
 #include <chrono>
@@ -220,6 +223,44 @@ struct BatchQueue {          // single producer / single consumer over two slots
 //       60-column reference FASTA packs as fast as single-line reads; with --ascii they upper-case the pieces in place.
 int g_parse_threads = (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
 
+// offsets (relative to `origin`) of the '\n' bytes of [p, e), appended to v; calls on_nl(q) for each (q = its address).
+// Short lines (a 60-column FASTA has a newline in nearly every 64-byte block) make one memchr call per line expensive:
+// with AVX2 the block's newline mask is computed once and its bits are walked.
+#if defined(__x86_64__)
+__attribute__((target("avx2"))) inline uint64_t nl_mask64(const char *p) {
+    const __m256i nl = _mm256_set1_epi8('\n');
+    const uint32_t lo = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(_mm256_loadu_si256((const __m256i *)p), nl));
+    const uint32_t hi = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(_mm256_loadu_si256((const __m256i *)(p + 32)), nl));
+    return (uint64_t)lo | ((uint64_t)hi << 32);
+}
+const bool g_avx2 = __builtin_cpu_supports("avx2") && !getenv("MQ_CLI_NO_AVX2");
+#else
+inline uint64_t nl_mask64(const char *) { return 0; }
+const bool g_avx2 = false;
+#endif
+template <class OnNl> void scan_newlines(const char *p, const char *e, OnNl on_nl) {
+    // 64 KB at a time; a chunk is walked by masks when the one before it averaged a newline per < 256 bytes, else by memchr
+    // (which is faster than two compares per 64 bytes when lines are long)
+    bool dense = false;
+    while (p < e) {
+        const char *ce = std::min(e, p + 65536);
+        size_t found = 0;
+        if (dense && g_avx2) {
+            for (; p + 64 <= ce; p += 64) {
+                uint64_t m = nl_mask64(p);
+                while (m) { on_nl(p + __builtin_ctzll(m)); m &= m - 1; found++; }
+            }
+        }
+        while (p < ce) {
+            const char *q = (const char *)memchr(p, '\n', (size_t)(ce - p));
+            if (!q) { p = ce; break; }
+            on_nl(q); found++;
+            p = q + 1;
+        }
+        dense = found > 256;
+    }
+}
+
 // persistent workers: a block is a few milliseconds of work per phase, thread creation would be a tenth of it.
 // Never destroyed (die() may exit from inside a worker).
 struct Pool {
@@ -355,14 +396,11 @@ struct BlockParser {
                 auto &v = nlv[t]; auto &h = hdv[t];
                 v.reserve((size_t)(b - a) / 48 + 16);
                 bool cr = false;
-                while (p < e) {
-                    const char *q = (const char *)memchr(p, '\n', (size_t)(e - p));
-                    if (!q) break;
+                scan_newlines(p, e, [&](const char *q) {
                     if (q > raw && q[-1] == '\r') cr = true;
                     if (fasta && q + 1 < end && q[1] == '>') h.push_back((uint32_t)v.size());
                     v.push_back((uint32_t)(q - raw));
-                    p = q + 1;
-                }
+                });
                 crv[t] = cr;
             });
             std::vector<size_t> lbase(T + 1, 0);
@@ -473,6 +511,7 @@ struct BlockParser {
                 const int T2 = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)g_parse_threads, units / 1024 + 1));
                 std::vector<std::vector<mq_exc>> ex(T2);
                 uint32_t *words = (uint32_t *)B.words.p, *flags = (uint32_t *)B.flags.p;
+                const char *const raw_end = raw + fill;
                 parallel_for(T2, [&](int t) {
                     const uint64_t u0 = units * (uint64_t)t / T2, u1 = units * (uint64_t)(t + 1) / T2;
                     const uint64_t d0 = u0 * 2048, d1 = std::min<uint64_t>(dst, u1 * 2048);
@@ -517,6 +556,12 @@ struct BlockParser {
                                 const size_t n = len & ~(size_t)63;
                                 pack((const uint8_t *)src, n, sb);
                                 sb += n; src += n; len -= n;
+                                continue;
+                            }
+                            if (len <= 64 && sn + 64 <= STAGE && src + 64 <= raw_end) {      // a line of a wrapped FASTA: one fixed-size copy (the surplus is overwritten)
+                                memcpy(stage + sn, src, 64);
+                                sn += len; len = 0;
+                                if (sn == STAGE) flush(false);
                                 continue;
                             }
                             const size_t take = std::min(len, STAGE - sn);
