@@ -130,7 +130,7 @@ struct PinnedBuf {
 // An input file: plain (regular files are mapped), gzip (zlib) or lz4 frames (main.rs:68,71).  Everything that is not a
 // plain regular file is a byte stream that a feeder thread decompresses ahead of the parser.
 struct Input {
-    gzFile f = nullptr; int fd = -1; bool fasta;
+    gzFile f = nullptr; int fd = -1, bgzf_fd = -1; bool fasta;
     std::unique_ptr<Lz4Reader> lz4;
     size_t file_bytes = 0;                 // size of a plain regular file
     bool regular = false;                  // plain regular file with a known size: mmap
@@ -140,6 +140,7 @@ struct Input {
         if (fd < 0) die("Error opening file: " + path);
         ssize_t got = pread(fd, magic, 2, 0);
         if (got == 2 && magic[0] == 0x1f && magic[1] == 0x8b) {        // gzip: hand the descriptor to zlib
+            bgzf_fd = dup(fd);                                          // (the feeder maps the file instead if it turns out to be BGZF)
             f = gzdopen(fd, "rb");
             if (!f) die("Error opening compressed file: " + path);
             gzbuffer(f, 1 << 20);
@@ -151,13 +152,122 @@ struct Input {
             struct stat st; if (fstat(fd, &st) == 0 && S_ISREG(st.st_mode)) { file_bytes = (size_t)st.st_size; regular = true; }
         }
     }
-    ~Input() { if (f) gzclose(f); if (fd >= 0) close(fd); }
+    ~Input() { if (f) gzclose(f); if (fd >= 0) close(fd); if (bgzf_fd >= 0) close(bgzf_fd); }
     long read_some(char *dst, size_t cap) {      // next (decompressed) bytes of a stream; <= 0 at its end
         return f ? (long)gzread(f, dst, (unsigned)std::min<size_t>(cap, 1u << 30)) : lz4 ? lz4->read(dst, cap) : (long)read(fd, dst, cap);
     }
     static std::string id_of(const char *p, size_t n) {       // seq_io record.id(): the header up to the first SPACE
         size_t e = 1; while (e < n && p[e] != ' ') e++;
         return std::string(p + 1, e - 1);
+    }
+};
+
+int g_parse_threads = (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+
+// persistent workers: a block is a few milliseconds of work per phase, thread creation would be a tenth of it.
+// Never destroyed (die() may exit from inside a worker).
+struct Pool {
+    std::mutex m, run_m; std::condition_variable cv_go, cv_done;
+    std::vector<std::thread> th;
+    const std::function<void(int)> *fn = nullptr; int n = 0, next = 0, pending = 0;
+    void worker() {
+        for (;;) {
+            int t;
+            {
+                std::unique_lock<std::mutex> lk(m);
+                cv_go.wait(lk, [&] { return next < n; });
+                t = next++;
+            }
+            (*fn)(t);
+            { std::lock_guard<std::mutex> lk(m); if (--pending == 0) cv_done.notify_all(); }
+        }
+    }
+    void run(int n_, const std::function<void(int)> &f) {
+        if (n_ <= 1) { if (n_ == 1) f(0); return; }
+        std::lock_guard<std::mutex> one(run_m);
+        {
+            std::lock_guard<std::mutex> lk(m);
+            while ((int)th.size() < n_ - 1) { th.emplace_back([this] { worker(); }); th.back().detach(); }
+            fn = &f; next = 1; pending = n_ - 1; n = n_;
+        }
+        cv_go.notify_all();
+        f(0);
+        std::unique_lock<std::mutex> lk(m);
+        cv_done.wait(lk, [&] { return pending == 0; });
+        n = 0; next = 0;
+    }
+};
+Pool &the_pool() { static Pool *pool = new Pool; return *pool; }
+template <class Fn> void parallel_for(int n, Fn fn) {
+    const std::function<void(int)> f = fn;
+    the_pool().run(n, f);
+}
+
+// BGZF (bgzip, htslib): a multi-member gzip file whose members are <= 64 KB and carry their own compressed size in a
+// 'BC' extra field, so members inflate independently -- here on the worker pool instead of zlib's one thread.
+struct Bgzf {
+    const uint8_t *base = nullptr; size_t size = 0, pos = 0;
+    static bool header(const uint8_t *p, size_t avail, size_t *block_bytes, size_t *data_off) {
+        if (avail < 18 || p[0] != 0x1f || p[1] != 0x8b || p[2] != 8 || !(p[3] & 4)) return false;
+        const size_t xlen = p[10] | ((size_t)p[11] << 8);
+        if (avail < 12 + xlen) return false;
+        for (size_t o = 12; o + 4 <= 12 + xlen;) {
+            const size_t slen = p[o + 2] | ((size_t)p[o + 3] << 8);
+            if (p[o] == 'B' && p[o + 1] == 'C' && slen == 2 && o + 6 <= 12 + xlen) {
+                *block_bytes = (size_t)(p[o + 4] | ((size_t)p[o + 5] << 8)) + 1;
+                *data_off = 12 + xlen;
+                return (p[3] & ~4) == 0 && *block_bytes >= *data_off + 8;      // no name / comment / header CRC fields (bgzip writes none)
+            }
+            o += 4 + slen;
+        }
+        return false;
+    }
+    bool open(int fd) {
+        struct stat st;
+        if (fstat(fd, &st) != 0 || !S_ISREG(st.st_mode) || st.st_size < 28) return false;
+        void *m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+        if (m == MAP_FAILED) return false;
+        size_t bb, off;
+        if (!header((const uint8_t *)m, (size_t)st.st_size, &bb, &off)) { munmap(m, (size_t)st.st_size); return false; }
+        base = (const uint8_t *)m; size = (size_t)st.st_size;
+        madvise(m, size, MADV_SEQUENTIAL);
+        return true;
+    }
+    ~Bgzf() { if (base) munmap((void *)base, size); }
+    // inflate the next members into dst (at most cap bytes); returns the bytes written, *end = the file is exhausted
+    size_t fill(char *dst, size_t cap, bool *end) {
+        struct Mem { size_t src, csize, out, isize; uint32_t crc; };
+        std::vector<Mem> ms; size_t out = 0;
+        while (pos < size) {
+            size_t bb, off;
+            if (!header(base + pos, size - pos, &bb, &off) || pos + bb > size) die("corrupt BGZF member (or a plain gzip member inside a BGZF file)");
+            const uint8_t *tr = base + pos + bb - 8;
+            const uint32_t crc = tr[0] | (tr[1] << 8) | (tr[2] << 16) | ((uint32_t)tr[3] << 24);
+            const size_t isize = tr[4] | (tr[5] << 8) | (tr[6] << 16) | ((size_t)tr[7] << 24);
+            if (isize > cap) die("corrupt BGZF member (size)");
+            if (out + isize > cap) break;
+            ms.push_back({pos + off, bb - off - 8, out, isize, crc});
+            out += isize; pos += bb;
+        }
+        *end = pos >= size;
+        const int T = (int)std::max<size_t>(1, std::min<size_t>((size_t)g_parse_threads, ms.size() / 4 + 1));
+        std::vector<char> bad(T, 0);
+        parallel_for(T, [&](int t) {
+            z_stream zs; memset(&zs, 0, sizeof zs);
+            if (inflateInit2(&zs, -15) != Z_OK) { bad[t] = 1; return; }
+            for (size_t i = ms.size() * (size_t)t / T, e = ms.size() * (size_t)(t + 1) / T; i < e; i++) {
+                const Mem &m = ms[i];
+                if (m.isize == 0) continue;
+                inflateReset(&zs);
+                zs.next_in = (Bytef *)(base + m.src); zs.avail_in = (uInt)m.csize;
+                zs.next_out = (Bytef *)(dst + m.out); zs.avail_out = (uInt)m.isize;
+                if (inflate(&zs, Z_FINISH) != Z_STREAM_END || zs.avail_out != 0 ||
+                    (uint32_t)crc32(crc32(0L, Z_NULL, 0), (const Bytef *)(dst + m.out), (uInt)m.isize) != m.crc) { bad[t] = 1; break; }
+            }
+            inflateEnd(&zs);
+        });
+        for (char b : bad) if (b) die("corrupt BGZF member (inflate / CRC)");
+        return out;
     }
 };
 
@@ -168,19 +278,26 @@ struct Feeder {
     struct Chunk { std::unique_ptr<char[]> p; size_t n = 0; };
     std::vector<Chunk> ring; size_t head = 0, tail = 0;      // [head, tail) are full
     bool done = false, quit = false;
-    explicit Feeder(Input *in_) : in(in_), ring(DEPTH) { th = std::thread([this] { run(); }); }
+    std::unique_ptr<Bgzf> bgzf;
+    explicit Feeder(Input *in_) : in(in_), ring(DEPTH) {
+        if (in->bgzf_fd >= 0 && !getenv("MQ_CLI_NO_BGZF")) { bgzf.reset(new Bgzf); if (!bgzf->open(in->bgzf_fd)) bgzf.reset(); }
+        th = std::thread([this] { run(); });
+    }
     ~Feeder() { { std::lock_guard<std::mutex> lk(m); quit = true; } cv.notify_all(); th.join(); }
     void run() {
         for (;;) {
             Chunk *c;
             { std::unique_lock<std::mutex> lk(m); cv.wait(lk, [&] { return quit || tail - head < (size_t)DEPTH; }); if (quit) return; c = &ring[tail % DEPTH]; }
             if (!c->p) c->p.reset(new char[CHUNK]);
-            size_t n = 0;
-            while (n < CHUNK) { const long r = in->read_some(c->p.get() + n, CHUNK - n); if (r <= 0) break; n += (size_t)r; }
+            size_t n = 0; bool end = false;
+            if (bgzf) n = bgzf->fill(c->p.get(), CHUNK, &end);
+            else {
+                while (n < CHUNK) { const long r = in->read_some(c->p.get() + n, CHUNK - n); if (r <= 0) { end = true; break; } n += (size_t)r; }
+            }
             c->n = n;
-            { std::lock_guard<std::mutex> lk(m); if (n) tail++; if (n < CHUNK) done = true; }
+            { std::lock_guard<std::mutex> lk(m); if (n) tail++; if (end) done = true; }
             cv.notify_all();
-            if (n < CHUNK) return;
+            if (end) return;
         }
     }
     // the oldest full chunk (nullptr at the end of the stream); release() hands it back
@@ -221,8 +338,6 @@ struct BatchQueue {          // single producer / single consumer over two slots
 //       block bitmap, so no two threads share a word and nothing is zeroed or OR-ed), gather the line pieces of their
 //       range through a small staging buffer and pack 64-base-aligned chunks with mq_pack_at at full SIMD width -- a
 //       60-column reference FASTA packs as fast as single-line reads; with --ascii they upper-case the pieces in place.
-int g_parse_threads = (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
-
 // offsets (relative to `origin`) of the '\n' bytes of [p, e), appended to v; calls on_nl(q) for each (q = its address).
 // Short lines (a 60-column FASTA has a newline in nearly every 64-byte block) make one memchr call per line expensive:
 // with AVX2 the block's newline mask is computed once and its bits are walked.
@@ -259,45 +374,6 @@ template <class OnNl> void scan_newlines(const char *p, const char *e, OnNl on_n
         }
         dense = found > 256;
     }
-}
-
-// persistent workers: a block is a few milliseconds of work per phase, thread creation would be a tenth of it.
-// Never destroyed (die() may exit from inside a worker).
-struct Pool {
-    std::mutex m, run_m; std::condition_variable cv_go, cv_done;
-    std::vector<std::thread> th;
-    const std::function<void(int)> *fn = nullptr; int n = 0, next = 0, pending = 0;
-    void worker() {
-        for (;;) {
-            int t;
-            {
-                std::unique_lock<std::mutex> lk(m);
-                cv_go.wait(lk, [&] { return next < n; });
-                t = next++;
-            }
-            (*fn)(t);
-            { std::lock_guard<std::mutex> lk(m); if (--pending == 0) cv_done.notify_all(); }
-        }
-    }
-    void run(int n_, const std::function<void(int)> &f) {
-        if (n_ <= 1) { if (n_ == 1) f(0); return; }
-        std::lock_guard<std::mutex> one(run_m);
-        {
-            std::lock_guard<std::mutex> lk(m);
-            while ((int)th.size() < n_ - 1) { th.emplace_back([this] { worker(); }); th.back().detach(); }
-            fn = &f; next = 1; pending = n_ - 1; n = n_;
-        }
-        cv_go.notify_all();
-        f(0);
-        std::unique_lock<std::mutex> lk(m);
-        cv_done.wait(lk, [&] { return pending == 0; });
-        n = 0; next = 0;
-    }
-};
-Pool &the_pool() { static Pool *pool = new Pool; return *pool; }
-template <class Fn> void parallel_for(int n, Fn fn) {
-    const std::function<void(int)> f = fn;
-    the_pool().run(n, f);
 }
 
 struct BlockParser {

@@ -163,6 +163,21 @@ def _lz4_frame(data):
     return out.raw[:n]
 
 
+def _bgzf(data, block=65280):
+    """`data` as a BGZF file (bgzip / htslib): gzip members of <= 64 KB with a 'BC' extra field, then the empty EOF member"""
+    import struct
+    import zlib
+    out = []
+    for i in list(range(0, len(data), block)) + [None]:
+        chunk = b"" if i is None else data[i:i + block]
+        co = zlib.compressobj(6, zlib.DEFLATED, -15)
+        cdata = co.compress(chunk) + co.flush()
+        bsize = 12 + 6 + len(cdata) + 8
+        out.append(b"\x1f\x8b\x08\x04" + b"\0\0\0\0" + b"\0\xff" + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, bsize - 1) + cdata +
+                   struct.pack("<II", zlib.crc32(chunk) & 0xFFFFFFFF, len(chunk)))
+    return b"".join(out)
+
+
 def test_parser_paths_agree(tmp_path):
     # mapped plain files and decompressed streams (gz, lz4) at every block size / thread count must hand the library
     # exactly the records that were written: single-line and multi-line FASTA, CRLF, no final newline, FASTQ
@@ -196,11 +211,21 @@ def test_parser_paths_agree(tmp_path):
         assert plain == _digest(tmp_path / (name + ".gz")), name                       # mapped file == zlib stream
         assert plain == _digest(tmp_path / (name + ".gz"), {"MQ_CLI_PACK": "1", "MQ_CLI_BLOCK": "777"}, 2), name
         assert plain == _digest(tmp_path / (name + ".lz4")), name                      # ... == lz4 frame reader (main.rs:68,71)
+        (tmp_path / (name + ".bgz")).write_bytes(_bgzf(data, 5000 if len(digests) % 2 else 65280))
+        assert gzip.decompress((tmp_path / (name + ".bgz")).read_bytes()) == data
+        assert plain == _digest(tmp_path / (name + ".bgz"), None, 6), name             # ... == BGZF members inflated on the worker pool
+        assert plain == _digest(tmp_path / (name + ".bgz"), {"MQ_CLI_NO_BGZF": "1"}), name   # ... == the same file as an ordinary multi-member gzip
+        assert plain == _digest(tmp_path / (name + ".bgz"), {"MQ_CLI_PACK": "1", "MQ_CLI_BLOCK": "20000"}, 3), name
         assert plain == _digest(tmp_path / name, {"MQ_CLI_PACK": "1"}, 4), name        # ... == the packing parser (codes + exceptions)
         assert plain == _digest(tmp_path / name, {"MQ_CLI_PACK": "1", "MQ_CLI_BLOCK": "3000"}, 3), name
         for blk, th in (("64", 1), ("1000", 3), ("70000", 8), ("5000000", 2)):
             assert _digest(tmp_path / name, {"MQ_CLI_BLOCK": blk}, th) == plain, (name, blk, th)
         digests[name] = plain
+    # a BGZF member whose payload does not match its CRC is refused
+    bad = bytearray(_bgzf(files["a.fa"])); bad[200] ^= 0x55
+    (tmp_path / "bad.fa.bgz").write_bytes(bytes(bad))
+    r = subprocess.run([ensure_cli(), str(tmp_path / "bad.fa.bgz"), "--parse-only"], capture_output=True, text=True)
+    assert r.returncode != 0 and "BGZF" in r.stderr
     assert len(set(digests.values())) == 1                                             # same records in every container
     assert digests["a.fa"] == _expected_digest(recs)                                   # ... and they are the records written
 
