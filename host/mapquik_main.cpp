@@ -384,7 +384,7 @@ struct BlockParser {
     const char *base = nullptr; size_t file_size = 0, pos = 0;             // mapped file
     Feeder *feed = nullptr; std::unique_ptr<char[]> sbuf; size_t s_cap = 0, s_have = 0, s_off = 0; bool s_end = false;   // stream
     const char *raw = nullptr; size_t fill = 0; bool eof = false;
-    bool populate = getenv("MQ_CLI_NO_POPULATE") == nullptr;
+    bool populate = getenv("MQ_CLI_POPULATE") != nullptr;     // measured on the 16-core box: 28 GB/s with, 29.5 without -- off unless asked for
     std::vector<uint32_t> nl, cum;            // per line: offset of its '\n' (or of the end of the block); bases before it
     BlockParser(int fd, bool fasta_, size_t block_bytes_, size_t file_size_) : fasta(fasta_), block_bytes(block_bytes_), file_size(file_size_) {
         if (file_size) {

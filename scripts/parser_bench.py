@@ -53,11 +53,11 @@ def main():
     out = {"host_cores": os.cpu_count(), "files": {}, "runs": []}
     for path in (reads, ref, fq):
         out["files"][os.path.basename(path)] = os.path.getsize(path)
-    variants = [(reads, mb, pop) for mb in (16, 32, 64, 128, 256) for pop in (1, 0)] + [(ref, mb, 1) for mb in (128, 512)] + [(fq, 64, 1), (fq, 256, 1)]
+    variants = [(reads, mb, pop) for mb in (16, 32, 64, 128, 256) for pop in (1, 0)] + [(ref, mb, 0) for mb in (128, 512)] + [(fq, 64, 0), (fq, 256, 0)]
     for path, mb, pop in variants:
         env = dict(os.environ, MQ_CLI_NODIGEST="1", MQ_CLI_PACK="1", MQ_CLI_BATCH=str(mb << 20))
-        if not pop:
-            env["MQ_CLI_NO_POPULATE"] = "1"
+        if pop:
+            env["MQ_CLI_POPULATE"] = "1"
         ts = []
         for _ in range(a.reps):
             t0 = time.perf_counter()

@@ -262,7 +262,7 @@ def test_parser_parallel_phases_on_large_wrapped_input(tmp_path):
         want = want or serial
         assert serial == want, name
         for env, th in (({}, 8), ({"MQ_CLI_PACK": "1"}, 8), ({"MQ_CLI_PACK": "1"}, 3), ({"MQ_CLI_PACK": "1", "MQ_CLI_BLOCK": "4000000"}, 5),
-                        ({"MQ_CLI_BLOCK": "3100000"}, 8), ({"MQ_CLI_PACK": "1", "MQ_CLI_NO_POPULATE": "1"}, 2)):
+                        ({"MQ_CLI_BLOCK": "3100000"}, 8), ({"MQ_CLI_PACK": "1", "MQ_CLI_POPULATE": "1"}, 2)):
             assert _digest(tmp_path / name, env, th) == want, (name, env, th)
     assert want == _expected_digest(recs)
 
