@@ -385,6 +385,7 @@ struct BlockParser {
     Feeder *feed = nullptr; std::unique_ptr<char[]> sbuf; size_t s_cap = 0, s_have = 0, s_off = 0; bool s_end = false;   // stream
     const char *raw = nullptr; size_t fill = 0; bool eof = false;
     bool populate = getenv("MQ_CLI_POPULATE") != nullptr;     // measured on the 16-core box: 28 GB/s with, 29.5 without -- off unless asked for
+    std::vector<std::vector<uint32_t>> nlv, hdv;     // per slice: newline offsets; local indices of lines FOLLOWED by a header line
     std::vector<uint32_t> nl, cum;            // per line: offset of its '\n' (or of the end of the block); bases before it
     BlockParser(int fd, bool fasta_, size_t block_bytes_, size_t file_size_) : fasta(fasta_), block_bytes(block_bytes_), file_size(file_size_) {
         if (file_size) {
@@ -458,7 +459,8 @@ struct BlockParser {
             if (fill == 0) return false;
             // (1) newline index; a line is a header iff it starts with '>' (FASTA)
             const int T = (int)std::max<size_t>(1, std::min<size_t>((size_t)g_parse_threads, fill / (2u << 20) + 1));
-            std::vector<std::vector<uint32_t>> nlv(T), hdv(T);      // per slice: newline offsets; local indices of lines FOLLOWED by a header line
+            if ((int)nlv.size() < T) { nlv.resize(T); hdv.resize(T); }      // (members: their capacity is reused from block to block)
+            for (int t = 0; t < T; t++) { nlv[t].clear(); hdv[t].clear(); }
             std::vector<char> crv(T, 0);
             parallel_for(T, [&](int t) {
                 size_t a = fill * (size_t)t / T, b = fill * (size_t)(t + 1) / T;
@@ -470,7 +472,6 @@ struct BlockParser {
                 }
 #endif
                 auto &v = nlv[t]; auto &h = hdv[t];
-                v.reserve((size_t)(b - a) / 48 + 16);
                 bool cr = false;
                 scan_newlines(p, e, [&](const char *q) {
                     if (q > raw && q[-1] == '\r') cr = true;
