@@ -105,7 +105,9 @@ int mq_pack(const uint8_t *ascii, uint64_t n_bases, uint32_t *words, uint32_t *f
 /* Pack n_bases bytes to base positions [at_base, at_base + n_bases) of a ZEROED destination.  Safe to call concurrently
  * for disjoint ranges (shared edge words are OR-ed in atomically) -- a FASTX parser's copy jobs call this instead of
  * their upper-casing memcpy.  exc receives this range's intervals (absolute positions); the caller concatenates the
- * lists of all ranges in position order. */
+ * lists of all ranges in position order.  Whole 32-base groups at 32-aligned positions are written with plain stores:
+ * a caller that only ever passes such chunks (plus one ragged tail) needs zeros in the block bitmap and under the tail
+ * only, and runs at full SIMD width -- the C++ CLI's parser stages wrapped FASTA lines into such chunks. */
 int mq_pack_at(const uint8_t *ascii, uint64_t n_bases, uint64_t at_base, uint32_t *words, uint32_t *flags, mq_exc *exc,
                uint64_t exc_cap, uint64_t *n_exc, int fold_case);
 int mq_unpack(const uint32_t *words, const mq_exc *exc, uint64_t n_exc, uint64_t first, uint64_t n, uint8_t *ascii);

@@ -106,6 +106,35 @@ def test_pack_at_concurrent_ranges():
     assert np.array_equal(words, ref.words) and np.array_equal(flags, ref.flags)
 
 
+def test_pack_at_aligned_chunks_need_no_zeroing():
+    """what the CLI's parser relies on: a chunk that starts on a 32-base boundary and holds whole 32-base groups is written
+    with plain stores (code words are overwritten, not OR-ed), so a destination full of stale bits needs no clearing; only
+    the block bitmap and the words of a ragged tail must be zero beforehand"""
+    L = capi.lib()
+    rng = np.random.default_rng(17)
+    n = 64 * 3000 + 37
+    a = messy(rng, n)
+    a[7000:7100] = ord("g")
+    ref = PackedSeqs(a, n_threads=1, fold_case=True)
+    words = np.full(int(L.mq_packed_words(n)), 0xFFFFFFFF, np.uint32); flags = np.zeros(int(L.mq_packed_flag_words(n)), np.uint32)
+    tail = n & ~31
+    words[tail >> 4:] = 0
+    excs = []; at = 0
+    for size in [64 * int(x) for x in rng.integers(1, 130, 400)]:
+        size = min(size, n - at) if at + size >= tail else size
+        if size <= 0:
+            break
+        ex = np.zeros(size + 1, EXC_DTYPE); k = C.c_uint64()
+        assert L.mq_pack_at(a[at:at + size].ctypes.data, size, at, words.ctypes.data, flags.ctypes.data, ex.ctypes.data, ex.size, C.byref(k), 1) == 0
+        excs.append(ex[:k.value]); at += size
+    assert at == n
+    assert np.array_equal(words, ref.words) and np.array_equal(flags, ref.flags)
+    exc = np.concatenate(excs)
+    out = np.zeros(n, np.uint8)
+    assert L.mq_unpack(words.ctypes.data, exc.ctypes.data, exc.size, 0, n, out.ctypes.data) == 0
+    assert np.array_equal(out, ref.unpack())
+
+
 def test_pack_narrow_path_equals_wide_path():
     """the 64-bases-per-step (AVX-512 VBMI) and the 32-bases-per-step (AVX2) packers must write the same words, bitmap and
     intervals; which one runs is decided once per process, so the narrow one is exercised in a child (MQ_PACK_NO_AVX512=1)"""
